@@ -1,0 +1,174 @@
+// common.cuh -- internal types, error handling and exact modular-arithmetic device helpers of libgffm.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/gffm.h"
+
+#define GFFM_REF_PAD 32  // TILE_WIDTH, reference src/CuModMatrix/CuModMatrix.jl:2,62
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void gffm_set_error(const char* fmt, ...);
+#define GFFM_FAIL(code, ...)            \
+  do {                                  \
+    gffm_set_error(__VA_ARGS__);        \
+    return (code);                      \
+  } while (0)
+#define GFFM_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      gffm_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                     cudaGetErrorString(_e));                                             \
+      return GFFM_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+#define GFFM_TRY(expr)            \
+  do {                            \
+    int32_t _s = (expr);          \
+    if (_s != GFFM_OK) return _s; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context / matrix
+// ---------------------------------------------------------------------------------------------
+struct gffm_workspace {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct gffm_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  // grow-only scratch buffers (stream-ordered reuse)
+  gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned;
+  std::vector<double> timings;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct gffm_mat {
+  gffm_ctx* ctx = nullptr;
+  uint32_t* data = nullptr;  // column-major, element (i,j) at data[j*ld + i]
+  int64_t rows = 0, cols = 0;
+  int64_t ld = 0;     // physical leading dimension (elements), >= rows + pad, multiple of 32
+  int64_t pcols = 0;  // physical columns allocated (>= cols + pad)
+  int32_t pad = GFFM_REF_PAD;
+  uint64_t N = 0;
+  bool owned = true;
+};
+
+int32_t gffm_ws_reserve(gffm_ctx* ctx, gffm_workspace* ws, size_t bytes);
+int32_t gffm_pinned_reserve(gffm_ctx* ctx, size_t bytes);
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// ---------------------------------------------------------------------------------------------
+// exact modular arithmetic
+// ---------------------------------------------------------------------------------------------
+// Barrett constants for a modulus P < 2^63: mu = floor((2^64-1)/P).  q = mulhi(v,mu) underestimates
+// floor(v/P) by at most 2 (mu may be one less than floor(2^64/P) when P | 2^64), so up to two conditional
+// subtractions restore r in [0,P).
+struct ModP {
+  uint64_t P;
+  uint64_t mu;
+};
+static inline ModP make_modp(uint64_t P) {
+  ModP m;
+  m.P = P;
+  m.mu = P ? (~0ull) / P : 0;
+  return m;
+}
+__host__ __device__ __forceinline__ uint64_t mulhi64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+// v arbitrary u64 -> v mod P
+__host__ __device__ __forceinline__ uint64_t mod_u64(uint64_t v, const ModP& m) {
+  uint64_t q = mulhi64(v, m.mu);
+  uint64_t r = v - q * m.P;
+  if (r >= m.P) r -= m.P;
+  if (r >= m.P) r -= m.P;
+  return r;
+}
+// (a*b) mod P for a,b < P < 2^32
+__host__ __device__ __forceinline__ uint32_t mulmod_u32(uint32_t a, uint32_t b, const ModP& m) {
+  return (uint32_t)mod_u64((uint64_t)a * b, m);
+}
+__host__ __device__ __forceinline__ uint32_t addmod_u32(uint32_t a, uint32_t b, uint32_t P) {
+  uint64_t s = (uint64_t)a + b;
+  return (uint32_t)(s >= P ? s - P : s);
+}
+__host__ __device__ __forceinline__ uint32_t submod_u32(uint32_t a, uint32_t b, uint32_t P) {
+  return a >= b ? a - b : (uint32_t)((uint64_t)a + P - b);
+}
+// extended Euclid (reference pluq_kernels.jl:11-31); returns 0 when gcd != 1
+__host__ __device__ inline uint64_t modinv_u64(uint64_t p, uint64_t P) {
+  int64_t inv = 0, new_inv = 1;
+  int64_t rem = (int64_t)P, new_rem = (int64_t)(p % P);
+  while (new_rem != 0) {
+    int64_t q = rem / new_rem;
+    int64_t t = inv - q * new_inv;
+    inv = new_inv;
+    new_inv = t;
+    t = rem - q * new_rem;
+    rem = new_rem;
+    new_rem = t;
+  }
+  if (rem != 1) return 0;
+  if (inv < 0) inv += (int64_t)P;
+  return (uint64_t)inv;
+}
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x ^= x >> 30;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27;
+  x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// internal entry points shared between translation units
+// ---------------------------------------------------------------------------------------------
+struct MatView {  // a sub-block of a column-major uint32 matrix
+  uint32_t* p;
+  int64_t ld;
+  int64_t rows, cols;
+};
+static inline MatView view_of(gffm_mat* m) { return MatView{m->data, m->ld, m->rows, m->cols}; }
+static inline MatView sub_view(const MatView& v, int64_t r0, int64_t c0, int64_t nr, int64_t nc) {
+  return MatView{v.p + c0 * v.ld + r0, v.ld, nr, nc};
+}
+
+// C (op)= A*B mod P on views; inputs < R.  algo as in gffm.h.
+int32_t gffm_gemm_views(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode, int algo);
+// scalar SIMT kernel (exact, any R,P < 2^32)
+int32_t gffm_gemm_simt(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode);
+// tensor-core paths
+int32_t gffm_gemm_tc_limb(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode);
+int32_t gffm_gemm_tc_rns(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode,
+                         bool balanced, uint32_t* kara_hi, uint64_t kara_N1);
+bool gffm_tc_available(gffm_ctx* ctx);
+
+int32_t gffm_ew_views(gffm_ctx* ctx, int op, MatView C, MatView A, const MatView* B, int64_t scalar, uint64_t P);
+int32_t gffm_copy_views(gffm_ctx* ctx, MatView dst, MatView src);
+int32_t gffm_fill_view(gffm_ctx* ctx, MatView dst, uint32_t value);
+
+#define GFFM_LAUNCH_CHECK(ctx)                 \
+  do {                                         \
+    (ctx)->launches++;                         \
+    GFFM_CUDA(cudaGetLastError());             \
+  } while (0)

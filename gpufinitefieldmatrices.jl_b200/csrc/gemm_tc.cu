@@ -1,0 +1,659 @@
+// gemm_tc.cu -- exact modular GEMM on the 5th-gen tensor cores (tcgen05 kind::i8, int32 accumulators in TMEM,
+// operands staged by TMA with the 128-byte swizzle).  Replaces the reference's cuBLAS S/DGEMM K-stripe loop
+// (reference src/CuModMatrix/kernel_mul/stripe_mul.jl:175-244) and its per-stripe k_mod! pass
+// (kernel_ops/mod_ops.jl:3-27): one launch covers all of K, the modular reduction is fused into the epilogue.
+//
+// Two exact encodings of residues as 8-bit planes ("limbs"):
+//   LIMB  positional base-256 digits (inputs < 2^16): L in {1,2} unsigned planes per operand, L^2 MMAs per
+//         K-step accumulated by weight i+j into 2L-1 TMEM accumulators; epilogue recombines sum_w acc_w * 2^(8w)
+//         in 64 bit, one Barrett reduction mod P, optional fused C +/-= (GFFM_GEMM_ADD / SUB).
+//   RNS   residue limbs: balanced residues mod s pairwise-coprime 8-bit moduli m_t (256, 255, 253, ...);
+//         s independent signed-int8 GEMMs (one TMEM accumulator each) whose epilogue reduces mod m_t and
+//         stores one byte per element; a CRT kernel (HBM-bound, 1 pass) reconstructs the exact integer dot
+//         product mod P.  For 17..26-bit moduli this needs 8-9 MMAs per K-step instead of the 9-16 of
+//         positional limbs and only ONE accumulator, so the 128x256 tile + double-buffered TMEM stays available.
+//
+// Kernel anatomy (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer      cp.async.bulk.tensor.3d -> smem ring (full/empty mbarriers)
+//   warp 1      MMA issuer        tcgen05.mma.cta_group::1.kind::i8, tcgen05.commit -> empty[stage] / tmem_full[buf]
+//   warps 2..5  epilogue          tcgen05.ld 32x32b.x16 -> registers -> reduction -> coalesced global stores
+#include <cuda.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int BM = 128;        // UMMA M
+constexpr int BK_BYTES = 128;  // one 128-byte swizzle atom along K per stage
+constexpr int UMMA_K = 32;     // K per tcgen05.mma for 8-bit inputs
+constexpr int MAX_MODS = 15;
+constexpr int GROUP_M = 16;    // rasterisation: 16 m-blocks x (148/16) n-blocks run concurrently -> L2 reuse
+
+enum { EPI_POS = 0, EPI_RNS = 1 };
+
+struct RnsModDev {
+  uint32_t m;    // modulus
+  uint32_t mu;   // floor(2^32 / m)
+  uint32_t off;  // multiple of m, >= 2^31 : makes the int32 accumulator non-negative
+  uint32_t pad;
+};
+
+struct GemmParams {
+  int m, n;
+  int num_kb;
+  int num_m_blk, num_n_blk, batches;
+  // positional epilogue
+  uint32_t* C;
+  int64_t ldc;
+  int mode;
+  ModP modP;
+  // RNS epilogue
+  uint8_t* E;
+  int64_t lde;
+  int64_t e_plane_stride;
+  RnsModDev mods[MAX_MODS];
+};
+
+// ---- schemes ---------------------------------------------------------------------------------------
+struct SchemeL1 {  // inputs < 2^8 : one unsigned plane, one accumulator, 128x256 tile, 2 TMEM buffers
+  static constexpr int PA = 1, PB = 1, NSLOT = 1, BN = 256, NPROD = 1, STAGES = 4, EPI = EPI_POS;
+  static constexpr bool SIGNED = false;
+  __host__ __device__ static constexpr int pa(int) { return 0; }
+  __host__ __device__ static constexpr int pb(int) { return 0; }
+  __host__ __device__ static constexpr int slot(int) { return 0; }
+};
+struct SchemeL2 {  // inputs < 2^16: two unsigned planes, weights 0,1,2 -> 3 accumulators x 128 columns
+  static constexpr int PA = 2, PB = 2, NSLOT = 3, BN = 128, NPROD = 4, STAGES = 3, EPI = EPI_POS;
+  static constexpr bool SIGNED = false;
+  __host__ __device__ static constexpr int pa(int i) { return i >> 1; }
+  __host__ __device__ static constexpr int pb(int i) { return i & 1; }
+  __host__ __device__ static constexpr int slot(int i) { return (i >> 1) + (i & 1); }
+};
+struct SchemeRNS {  // one signed plane per modulus, batch index = modulus
+  static constexpr int PA = 1, PB = 1, NSLOT = 1, BN = 256, NPROD = 1, STAGES = 4, EPI = EPI_RNS;
+  static constexpr bool SIGNED = true;
+  __host__ __device__ static constexpr int pa(int) { return 0; }
+  __host__ __device__ static constexpr int pb(int) { return 0; }
+  __host__ __device__ static constexpr int slot(int) { return 0; }
+};
+
+template <class S>
+struct Cfg {
+  static constexpr int A_TILE = BM * BK_BYTES;
+  static constexpr int B_TILE = S::BN * BK_BYTES;
+  static constexpr int STAGE_BYTES = S::PA * A_TILE + S::PB * B_TILE;
+  static constexpr int ACC_COLS = S::NSLOT * S::BN;
+  static constexpr int NBUF = (512 / ACC_COLS) >= 2 ? 2 : 1;
+  static constexpr int SMEM_BYTES = S::STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void decode_tile(int tile, const GemmParams& p, int& z, int& mb, int& nb) {
+  const int per_batch = p.num_m_blk * p.num_n_blk;
+  z = tile / per_batch;
+  int t = tile - z * per_batch;
+  const int per_group = GROUP_M * p.num_n_blk;
+  const int g = t / per_group;
+  const int first_m = g * GROUP_M;
+  const int gsize = min(p.num_m_blk - first_m, GROUP_M);
+  const int r = t - g * per_group;
+  mb = first_m + (r % gsize);
+  nb = r / gsize;
+}
+
+template <class S>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ GemmParams p) {
+  using C = Cfg<S>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tfull_bar = empty_bar + S::STAGES;
+  uint64_t* tempty_bar = tfull_bar + C::NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + C::NBUF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    for (int s = 0; s < S::STAGES; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < C::NBUF; ++b) {
+      tc::mbar_init(&tfull_bar[b], 1);
+      tc::mbar_init(&tempty_bar[b], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.batches * p.num_m_blk * p.num_n_blk;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int z, mb, nb;
+        decode_tile(tile, p, z, mb, nb);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          tc::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+#pragma unroll
+          for (int a = 0; a < S::PA; ++a)
+            tc::tma_load_3d(st + a * C::A_TILE, &tmA, &full_bar[stage], kb * BK_BYTES, mb * BM, z * S::PA + a);
+#pragma unroll
+          for (int b = 0; b < S::PB; ++b)
+            tc::tma_load_3d(st + S::PA * C::A_TILE + b * C::B_TILE, &tmB, &full_bar[stage], kb * BK_BYTES, nb * S::BN,
+                            z * S::PB + b);
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = tc::make_idesc_i8(BM, S::BN, S::SIGNED, S::SIGNED);
+    int stage = 0;
+    uint32_t phase = 0;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      tc::mbar_wait(&tempty_bar[buf], bphase ^ 1);  // epilogue has drained this accumulator buffer
+      tc::tc_fence_after();
+      const uint32_t acc_base = tmem_base + buf * C::ACC_COLS;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        tc::mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
+        tc::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = tc::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + S::PA * C::A_TILE;
+#pragma unroll
+          for (int kk = 0; kk < BK_BYTES / UMMA_K; ++kk) {
+#pragma unroll
+            for (int pr = 0; pr < S::NPROD; ++pr) {
+              const uint64_t da = tc::make_smem_desc_sw128(sa + S::pa(pr) * C::A_TILE + kk * UMMA_K);
+              const uint64_t db = tc::make_smem_desc_sw128(sb + S::pb(pr) * C::B_TILE + kk * UMMA_K);
+              // first MMA that touches a slot in this tile overwrites, everything else accumulates
+              bool first_in_slot = true;
+#pragma unroll
+              for (int q = 0; q < pr; ++q)
+                if (S::slot(q) == S::slot(pr)) first_in_slot = false;
+              const uint32_t accumulate = (kb > 0 || kk > 0 || !first_in_slot) ? 1u : 0u;
+              tc::mma_i8_ss(acc_base + S::slot(pr) * S::BN, da, db, idesc, accumulate);
+            }
+          }
+          tc::mma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
+          if (kb == p.num_kb - 1) tc::mma_commit(&tfull_bar[buf]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == S::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++buf == C::NBUF) {
+        buf = 0;
+        bphase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int z, mb, nb;
+      decode_tile(tile, p, z, mb, nb);
+      tc::mbar_wait(&tfull_bar[buf], bphase);
+      tc::tc_fence_after();
+      const int row = mb * BM + q * 32 + lane;
+      const bool row_ok = row < p.m;
+      const uint32_t acc_base = tmem_base + buf * C::ACC_COLS + lane_addr;
+      const int col0 = nb * S::BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < S::BN; c0 += 16) {
+        if (col0 + c0 >= p.n) break;  // warp-uniform
+        uint32_t v[S::NSLOT][16];
+#pragma unroll
+        for (int s = 0; s < S::NSLOT; ++s) tc::tmem_ld16(acc_base + s * S::BN + c0, v[s]);
+        tc::tmem_ld_wait();
+        if constexpr (S::EPI == EPI_POS) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = col0 + c0 + c;
+            uint64_t acc = (uint64_t)v[0][c];
+            if constexpr (S::NSLOT == 3) acc += ((uint64_t)v[1][c] << 8) + ((uint64_t)v[2][c] << 16);
+            uint32_t r = (uint32_t)mod_u64(acc, p.modP);
+            if (row_ok && col < p.n) {
+              uint32_t* dst = p.C + (int64_t)col * p.ldc + row;
+              if (p.mode == GFFM_GEMM_ADD) r = addmod_u32(*dst, r, (uint32_t)p.modP.P);
+              else if (p.mode == GFFM_GEMM_SUB) r = submod_u32(*dst, r, (uint32_t)p.modP.P);
+              *dst = r;
+            }
+          }
+        } else {
+          const RnsModDev md = p.mods[z];
+          uint8_t* eplane = p.E + (int64_t)z * p.e_plane_stride;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = col0 + c0 + c;
+            const uint32_t u = v[0][c] + md.off;  // == acc (mod m), non-negative
+            uint32_t e = u - __umulhi(u, md.mu) * md.m;
+            if (e >= md.m) e -= md.m;
+            if (row_ok && col < p.n) eplane[(int64_t)col * p.lde + row] = (uint8_t)e;
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[buf]);
+      if (++buf == C::NBUF) {
+        buf = 0;
+        bphase ^= 1;
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prologue: residues -> 8-bit planes (HBM-bound).  Plane layout: [plane][row][Kp] bytes, K contiguous
+// ("K-major"), rows = output rows of the operand (A: i, B: j), zero-filled for k >= K.
+// ---------------------------------------------------------------------------------------------------
+struct SplitParams {
+  int nplanes;          // planes written per call
+  int mode;             // 0 = positional limb p -> (x >> 8p) & 255 ; 1 = RNS residues
+  uint32_t R;           // RNS: input bound (for balancing), 0 = unbalanced
+  uint32_t half;        // RNS: values > half are shifted by -R
+  int is_b;             // RNS: multiply by u_t (B side)
+  uint32_t m[MAX_MODS], mu[MAX_MODS], u[MAX_MODS], Rm[MAX_MODS];
+};
+
+__device__ __forceinline__ uint32_t small_mod(uint32_t a, uint32_t m, uint32_t mu) {
+  uint32_t r = a - __umulhi(a, mu) * m;
+  if (r >= m) r -= m;
+  return r;
+}
+
+__device__ __forceinline__ uint8_t encode_plane(uint32_t x, int pl, const SplitParams& sp) {
+  if (sp.mode == 0) return (uint8_t)((x >> (8 * pl)) & 255u);
+  const uint32_t m = sp.m[pl];
+  uint32_t r = small_mod(x, m, sp.mu[pl]);
+  if (sp.R && x > sp.half) {  // x - R
+    const uint32_t Rm = sp.Rm[pl];
+    r = r >= Rm ? r - Rm : r + m - Rm;
+  }
+  if (sp.is_b) r = small_mod(r * sp.u[pl], m, sp.mu[pl]);
+  // balance into [-floor(m/2), ceil(m/2)-1] and store as two's complement int8
+  if (r >= (m + 1) / 2) r -= m;
+  return (uint8_t)(r & 255u);
+}
+
+// B operand (k x n column-major, K contiguous already): thread = 4 consecutive k of one column j.
+// Optional second source (Karatsuba prologue fusion, reference KaratsubaKernels.jl:129-139): x = src + src2.
+__global__ void split_b_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2,
+                               int K, int ncols, uint8_t* __restrict__ planes, int64_t Kp, int64_t rowsP,
+                               const __grid_constant__ SplitParams sp) {
+  const int64_t k4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 k
+  const int j = blockIdx.y;
+  if (k4 * 4 >= Kp || j >= ncols) return;
+  uint32_t x[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int64_t k = k4 * 4 + t;
+    x[t] = 0;
+    if (k < K) {
+      x[t] = src[(int64_t)j * ld + k];
+      if (src2) x[t] += src2[(int64_t)j * ld2 + k];
+    }
+  }
+  for (int pl = 0; pl < sp.nplanes; ++pl) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) w |= (uint32_t)encode_plane(x[t], pl, sp) << (8 * t);
+    *reinterpret_cast<uint32_t*>(planes + ((int64_t)pl * rowsP + j) * Kp + k4 * 4) = w;
+  }
+}
+
+// A operand (m x k column-major, M contiguous): 32(i) x 128(k) tile transposed through shared memory.
+__global__ void __launch_bounds__(256)
+split_a_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2, int M, int K,
+               uint8_t* __restrict__ planes, int64_t Kp, int64_t rowsP, const __grid_constant__ SplitParams sp) {
+  __shared__ uint32_t tile[128][33];
+  const int i0 = blockIdx.x * 32;
+  const int k0 = blockIdx.y * 128;
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;  // 8 warps
+  for (int kk = w; kk < 128; kk += 8) {
+    const int k = k0 + kk, i = i0 + lane;
+    uint32_t x = 0;
+    if (k < K && i < M) {
+      x = src[(int64_t)k * ld + i];
+      if (src2) x += src2[(int64_t)k * ld2 + i];
+    }
+    tile[kk][lane] = x;
+  }
+  __syncthreads();
+  const int i = threadIdx.x >> 3;   // 0..31
+  const int kg = threadIdx.x & 7;   // 16-byte group along k
+  if (i0 + i >= M) return;
+  uint32_t x[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) x[t] = tile[kg * 16 + t][i];
+  for (int pl = 0; pl < sp.nplanes; ++pl) {
+    uint32_t wv[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 16; ++t) wv[t >> 2] |= (uint32_t)encode_plane(x[t], pl, sp) << (8 * (t & 3));
+    *reinterpret_cast<uint4*>(planes + ((int64_t)pl * rowsP + (i0 + i)) * Kp + k0 + kg * 16) =
+        make_uint4(wv[0], wv[1], wv[2], wv[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CRT epilogue kernel (RNS): e_t = (x * u_t^-1-scaled) mod m_t planes -> x mod P, fused C +/-= and the Karatsuba
+// carry split (reference KaratsubaKernels.jl:141-158: C1 = cc mod N1, carry = cc div N1).
+//   x = S - round(S/M) * M,  S = sum_t e_t * (M/m_t);   frac(S/M) tracked in 2^-56 fixed point.
+// ---------------------------------------------------------------------------------------------------
+struct CrtParams {
+  int s;
+  int mode;
+  int balanced;
+  ModP modP;
+  uint64_t w[MAX_MODS];  // (M/m_t) mod P
+  uint64_t f[MAX_MODS];  // floor(2^56 / m_t)
+  uint64_t W;            // M mod P
+  uint64_t kara_N1;      // != 0: C <- (x mod P) mod N1, hi <- (x mod P) div N1
+};
+
+__global__ void __launch_bounds__(256)
+crt_kernel(const uint8_t* __restrict__ E, int64_t lde, int64_t plane_stride, int m, int n, uint32_t* __restrict__ C,
+           int64_t ldc, uint32_t* __restrict__ hi, int64_t ldhi, const __grid_constant__ CrtParams cp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= m || j >= n) return;
+  const uint8_t* e = E + (int64_t)j * lde + i;
+  uint64_t acc = 0, F = 0;
+#pragma unroll 1
+  for (int t = 0; t < cp.s; ++t) {
+    const uint64_t et = e[(int64_t)t * plane_stride];
+    acc += et * cp.w[t];
+    F += et * cp.f[t];
+  }
+  const uint64_t qq = cp.balanced ? ((F + (1ull << 55) + (1ull << 12)) >> 56) : ((F + (1ull << 12)) >> 56);
+  const uint64_t t1 = mod_u64(acc, cp.modP);
+  const uint64_t t2 = mod_u64(qq * cp.W, cp.modP);
+  uint64_t r = t1 >= t2 ? t1 - t2 : t1 + cp.modP.P - t2;
+  uint32_t* dst = C + (int64_t)j * ldc + i;
+  if (cp.kara_N1) {
+    hi[(int64_t)j * ldhi + i] = (uint32_t)(r / cp.kara_N1);
+    *dst = (uint32_t)(r % cp.kara_N1);
+    return;
+  }
+  uint32_t r32 = (uint32_t)r;
+  if (cp.mode == GFFM_GEMM_ADD) r32 = addmod_u32(*dst, r32, (uint32_t)cp.modP.P);
+  else if (cp.mode == GFFM_GEMM_SUB) r32 = submod_u32(*dst, r32, (uint32_t)cp.modP.P);
+  *dst = r32;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// planes: [nplanes][rowsP][Kp] bytes; box = {128 bytes of K, box_rows, 1 plane}, 128-byte swizzle
+int32_t make_plane_tmap(CUtensorMap* tm, void* planes, int64_t Kp, int64_t rowsP, int64_t nplanes, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) GFFM_FAIL(GFFM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rowsP, (cuuint64_t)nplanes};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)(Kp * rowsP)};
+  cuuint32_t box[3] = {(cuuint32_t)BK_BYTES, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GFFM_FAIL(GFFM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GFFM_OK;
+}
+
+template <class S>
+int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+  using C = Cfg<S>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GFFM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.batches * p.num_m_blk * p.num_n_blk;
+  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+  gemm_tc_kernel<S><<<grid, 192, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+  GFFM_LAUNCH_CHECK(ctx);
+  return GFFM_OK;
+}
+
+int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2, int64_t k_off, int64_t kc, uint8_t* planes,
+                  int64_t Kp, int64_t rowsP, const SplitParams& sp) {
+  if (is_a) {
+    // A is m x K: rows = i, K along columns of the view
+    const uint32_t* s = X.p + k_off * X.ld;
+    const uint32_t* s2 = X2 ? X2->p + k_off * X2->ld : nullptr;
+    dim3 grid((unsigned)ceil_div(X.rows, 32), (unsigned)(Kp / 128));
+    split_a_kernel<<<grid, 256, 0, ctx->stream>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)X.rows, (int)kc, planes, Kp, rowsP, sp);
+  } else {
+    // B is K x n: K along rows of the view
+    const uint32_t* s = X.p + k_off;
+    const uint32_t* s2 = X2 ? X2->p + k_off : nullptr;
+    dim3 grid((unsigned)ceil_div(Kp / 4, 128), (unsigned)X.cols);
+    split_b_kernel<<<grid, 128, 0, ctx->stream>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)X.cols, planes, Kp, rowsP, sp);
+  }
+  GFFM_LAUNCH_CHECK(ctx);
+  return GFFM_OK;
+}
+
+const uint32_t kModuli[MAX_MODS] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197};
+
+}  // namespace
+
+bool gffm_tc_available(gffm_ctx* ctx) {
+  (void)ctx;
+  return get_encode_fn() != nullptr;
+}
+
+// Optional second addends (A2,B2) implement the Karatsuba prologue fusion: the planes are those of A+A2 / B+B2.
+int32_t gffm_gemm_tc_limb_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView* A2, MatView B, const MatView* B2,
+                             uint64_t R, uint64_t P, int mode) {
+  const int64_t m = A.rows, K = A.cols, n = B.cols;
+  if (m == 0 || n == 0) return GFFM_OK;
+  if (R > 65536 || P >= (1ull << 32) || P == 0) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "limb GEMM needs R <= 2^16 and P < 2^32");
+  const int L = R <= 256 ? 1 : 2;
+  const int BN = L == 1 ? SchemeL1::BN : SchemeL2::BN;
+  // largest K chunk whose worst accumulator stays below 2^31 (exactness budget)
+  const uint64_t top = (R - 1) >> (8 * (L - 1));
+  const uint64_t lo = L == 1 ? 0 : 255;
+  uint64_t worst = L == 1 ? top * top : (2 * lo * top > lo * lo ? 2 * lo * top : lo * lo);
+  if (L == 2 && top * top > worst) worst = top * top;
+  if (worst == 0) worst = 1;
+  int64_t kmax = (int64_t)(((1ull << 31) - 1) / worst);
+  kmax = kmax / 128 * 128;
+  if (kmax < 128) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "accumulator budget");
+  if (kmax > (1 << 20)) kmax = 1 << 20;
+  const int64_t rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
+  const int64_t kchunk_max = K < kmax ? round_up(K > 0 ? K : 1, 128) : kmax;
+  GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_planes_a, (size_t)L * rowsPA * kchunk_max));
+  GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_planes_b, (size_t)L * rowsPB * kchunk_max));
+  SplitParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.nplanes = L;
+  sp.mode = 0;
+  if (K == 0) {
+    if (mode == GFFM_GEMM_STORE) return gffm_fill_view(ctx, Cv, 0);
+    return GFFM_OK;
+  }
+  for (int64_t k0 = 0; k0 < K; k0 += kmax) {
+    const int64_t kc = (K - k0) < kmax ? (K - k0) : kmax;
+    const int64_t Kp = round_up(kc, 128);
+    uint8_t* pa = (uint8_t*)ctx->ws_planes_a.ptr;
+    uint8_t* pb = (uint8_t*)ctx->ws_planes_b.ptr;
+    GFFM_TRY(run_split(ctx, true, A, A2, k0, kc, pa, Kp, rowsPA, sp));
+    GFFM_TRY(run_split(ctx, false, B, B2, k0, kc, pb, Kp, rowsPB, sp));
+    CUtensorMap tmA, tmB;
+    GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, L, BM));
+    GFFM_TRY(make_plane_tmap(&tmB, pb, Kp, rowsPB, L, BN));
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.m = (int)m;
+    p.n = (int)n;
+    p.num_kb = (int)(Kp / 128);
+    p.num_m_blk = (int)(rowsPA / BM);
+    p.num_n_blk = (int)(rowsPB / BN);
+    p.batches = 1;
+    p.C = Cv.p;
+    p.ldc = Cv.ld;
+    p.mode = (k0 == 0) ? mode : (mode == GFFM_GEMM_SUB ? GFFM_GEMM_SUB : GFFM_GEMM_ADD);
+    p.modP = make_modp(P);
+    if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p));
+    else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p));
+  }
+  return GFFM_OK;
+}
+
+int32_t gffm_gemm_tc_limb(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode) {
+  return gffm_gemm_tc_limb_ex(ctx, C, A, nullptr, B, nullptr, R, P, mode);
+}
+
+// RNS path.  balanced: inputs are residues mod R and the result is only needed mod P with P | R (or P == R), so
+// inputs may be shifted into (-R/2, R/2] -- halves the dynamic range twice.  kara_hi != nullptr selects the
+// Karatsuba carry split with N1 = kara_N1 (P = N1*N2 <= 2^52).
+int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView* A2, MatView B, const MatView* B2, uint64_t R,
+                            uint64_t P, int mode, bool balanced, uint32_t* kara_hi, int64_t ldhi, uint64_t kara_N1) {
+  const int64_t m = A.rows, K = A.cols, n = B.cols;
+  if (m == 0 || n == 0) return GFFM_OK;
+  if (R == 0 || R > (1ull << 31) || P == 0 || P > (1ull << 52)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "RNS GEMM needs R <= 2^31, P <= 2^52");
+  if (!kara_hi && P >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "uint32 output needs P < 2^32");
+  if (K == 0) {
+    if (mode == GFFM_GEMM_STORE && !kara_hi) return gffm_fill_view(ctx, Cv, 0);
+    return GFFM_OK;
+  }
+  const int64_t kmax = 65536;  // |acc| <= K * 128 * 128 < 2^31
+  const int BN = SchemeRNS::BN;
+  const int64_t rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
+  for (int64_t k0 = 0; k0 < K; k0 += kmax) {
+    const int64_t kc = (K - k0) < kmax ? (K - k0) : kmax;
+    const int64_t Kp = round_up(kc, 128);
+    // number of moduli: M > 2*X*(1+2^-16) (balanced, |x| <= X = kc*floor(R/2)^2) or M > X*(1+2^-16) (X = kc*(R-1)^2)
+    unsigned __int128 X = balanced ? (unsigned __int128)kc * (R / 2) * (R / 2) * 2 : (unsigned __int128)kc * (R - 1) * (R - 1);
+    X += (X >> 16) + 2;
+    unsigned __int128 Mprod = 1;
+    int s = 0;
+    while (Mprod <= X) {
+      if (s >= MAX_MODS) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "dynamic range exceeds %d moduli", MAX_MODS);
+      Mprod *= kModuli[s++];
+    }
+    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_planes_a, (size_t)s * rowsPA * Kp));
+    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_planes_b, (size_t)s * rowsPB * Kp));
+    const int64_t lde = round_up(m, 128);
+    const int64_t e_plane = lde * n;
+    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_eplanes, (size_t)s * e_plane));
+    // per-modulus constants
+    SplitParams spa;
+    memset(&spa, 0, sizeof(spa));
+    spa.nplanes = s;
+    spa.mode = 1;
+    spa.R = balanced ? (uint32_t)R : 0;
+    spa.half = (uint32_t)(R / 2);
+    CrtParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.s = s;
+    cp.mode = (k0 == 0) ? mode : (mode == GFFM_GEMM_SUB ? GFFM_GEMM_SUB : GFFM_GEMM_ADD);
+    cp.balanced = balanced ? 1 : 0;
+    cp.modP = make_modp(P);
+    cp.kara_N1 = kara_hi ? kara_N1 : 0;
+    cp.W = (uint64_t)(Mprod % P);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    for (int t = 0; t < s; ++t) {
+      const uint32_t mt = kModuli[t];
+      uint64_t others_mod_mt = 1;
+      unsigned __int128 others_mod_P = 1;
+      for (int u = 0; u < s; ++u) {
+        if (u == t) continue;
+        others_mod_mt = (others_mod_mt * (kModuli[u] % mt)) % mt;
+        others_mod_P = (others_mod_P * kModuli[u]) % P;
+      }
+      const uint64_t ut = modinv_u64(others_mod_mt, mt);
+      spa.m[t] = mt;
+      spa.mu[t] = (uint32_t)((1ull << 32) / mt);
+      spa.u[t] = (uint32_t)ut;
+      spa.Rm[t] = (uint32_t)(R % mt);
+      cp.w[t] = (uint64_t)others_mod_P;
+      cp.f[t] = (1ull << 56) / mt;
+      p.mods[t].m = mt;
+      p.mods[t].mu = (uint32_t)((1ull << 32) / mt);
+      p.mods[t].off = (uint32_t)(((1ull << 31) + mt - 1) / mt * mt);
+    }
+    SplitParams spb = spa;
+    spb.is_b = 1;
+    uint8_t* pa = (uint8_t*)ctx->ws_planes_a.ptr;
+    uint8_t* pb = (uint8_t*)ctx->ws_planes_b.ptr;
+    GFFM_TRY(run_split(ctx, true, A, A2, k0, kc, pa, Kp, rowsPA, spa));
+    GFFM_TRY(run_split(ctx, false, B, B2, k0, kc, pb, Kp, rowsPB, spb));
+    CUtensorMap tmA, tmB;
+    GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, s, BM));
+    GFFM_TRY(make_plane_tmap(&tmB, pb, Kp, rowsPB, s, BN));
+    p.m = (int)m;
+    p.n = (int)n;
+    p.num_kb = (int)(Kp / 128);
+    p.num_m_blk = (int)(rowsPA / BM);
+    p.num_n_blk = (int)(rowsPB / BN);
+    p.batches = s;
+    p.E = (uint8_t*)ctx->ws_eplanes.ptr;
+    p.lde = lde;
+    p.e_plane_stride = e_plane;
+    GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p));
+    dim3 grid((unsigned)ceil_div(m, 256), (unsigned)n);
+    crt_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, (int)m, (int)n, Cv.p, Cv.ld,
+                                              kara_hi, ldhi, cp);
+    GFFM_LAUNCH_CHECK(ctx);
+    if (kara_hi && K > kmax) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "Karatsuba carry split with K > 65536");
+  }
+  return GFFM_OK;
+}
+
+int32_t gffm_gemm_tc_rns(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode, bool balanced,
+                         uint32_t* kara_hi, uint64_t kara_N1) {
+  return gffm_gemm_tc_rns_ex(ctx, C, A, nullptr, B, nullptr, R, P, mode, balanced, kara_hi, C.ld, kara_N1);
+}
