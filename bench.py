@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: exact mod-p matrix multiplication, n = 16384, 25-bit prime.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+metric (BASELINE.json): mod-p matmul effective GOPS = 2 n^3 / t.
+  value      : device-timed (CUDA events), inputs already resident in HBM; max over ranks; whole job.
+  e2e        : same product through the public API with HOST (pinned) buffers: H2D of A and B, GEMM, D2H of C per step.
+  roofline   : int8 tensor-pipe ops of the dominant kernel (tcgen05 RNS GEMM) / its CUDA-event duration, vs peak.
+  cpu_baseline: C restatement of the reference tests' `mod.(A*B, N)` ground truth on the host cores (bounded sample).
+  --impl reference: that CPU arm alone (the Julia reference cannot run in this image).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_DEFAULT = 16384
+MOD_DEFAULT = 33554393  # 25-bit prime near the 2^26 limit (BASELINE config 2)
+SEED_A, SEED_B = 5, 6   # SURVEY 8(d) "metric GEMM" seeds
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16": d.get("bf16_tflops", 1590.0), "bf16_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(n_full, N, budget_s=20.0, threads=None):
+    """Times the C oracle (oracle/oracle_c.c, pthreads over all host cores) on a bounded sample of the workload:
+    the leading n_s x n_s x n_s sub-product of the same synthetic matrices.  Returns (GOPS, cores, description, seconds)."""
+    import numpy as np
+    from oracle import oracle as O
+    from oracle import oracle_c as OC
+    cores = OC.num_threads() if threads is None else threads
+    ns = 512
+    A = O.synth_matrix(SEED_A, ns, ns, N); B = O.synth_matrix(SEED_B, ns, ns, N)
+    t0 = time.perf_counter(); OC.matmul_mod(A, B, N); t_small = time.perf_counter() - t0
+    rate = 2.0 * ns ** 3 / max(t_small, 1e-6)
+    ns = 1024
+    while ns * 2 <= min(n_full, 8192) and 2.0 * (2 * ns) ** 3 / rate < budget_s:
+        ns *= 2
+    A = O.synth_matrix(SEED_A, ns, ns, N); B = O.synth_matrix(SEED_B, ns, ns, N)
+    t0 = time.perf_counter(); C = OC.matmul_mod(A, B, N); dt = time.perf_counter() - t0
+    chk = int(np.bitwise_xor.reduce(C.reshape(-1)))
+    gops = 2.0 * ns ** 3 / dt / 1e9
+    return gops, cores, f"{ns}x{ns}x{ns} mod {N} sub-product of the n={n_full} workload, same generator (xor checksum {chk:#x})", dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    gops_all = []
+    desc = ""
+    cores = 1
+    for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
+        pass
+    for i in range(max(1, min(args.steps, 3))):
+        gops, cores, desc, dt = cpu_arm(args.n, args.modulus, budget_s=15.0)
+        gops_all.append(gops)
+    value = statistics.median(gops_all)
+    out = {
+        "impl": "reference", "metric": "mod-p matmul effective GOPS (2n^3/s)", "value": value, "unit": "GOPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 2.0 * args.n ** 3 / (value * 1e9) * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64 accumulate of u32 residues (host integers)", "data": "synthetic",
+        "config": {"workload": f"{args.n}x{args.n} * {args.n}x{args.n} matmul mod {args.modulus}", "n": args.n, "modulus": args.modulus,
+                   "note": "the Julia reference cannot run in this image; this arm is the reference tests' CPU ground truth mod.(A*B,N) restated in C "
+                           "(oracle/oracle_c.c) on all host cores; ms_per_step is the n^3-extrapolated time of the full workload"},
+        "cpu_baseline": {"value": value, "unit": "GOPS", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "GOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--modulus", type=int, default=MOD_DEFAULT)
+    ap.add_argument("--panels", type=int, default=8, help="column panels of B for the pipelined NCCL broadcast (N > 1)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time N=11 and N=65521 and PLUQ (reported under config.extras)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gffm_b200 as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, N = args.n, args.modulus
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    ctx = g.Context(local)
+    stream = torch.cuda.Stream(device=local)
+    ctx.set_stream(stream.cuda_stream)
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        # ---- resident inputs: A row block of this rank, B (broadcast from rank 0 each step when world > 1) -----------
+        rows_per = (n + world - 1) // world
+        r0, r1 = rank * rows_per, min(n, (rank + 1) * rows_per)
+        mloc = r1 - r0
+        if world == 1:
+            A = g.synth(n, n, N, SEED_A, ctx=ctx)
+        else:
+            Afull = g.synth(n, n, N, SEED_A, ctx=ctx)
+            A = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+            g.capi.check(A.lib.gffm_mat_copy_block(A.h, 0, 0, Afull.h, r0, 0, mloc, n))
+            ctx.sync()
+            del Afull
+        ldb = ((n + 31) // 32) * 32
+        Bt = torch.zeros((n, ldb), dtype=torch.int32, device=f"cuda:{local}")  # column-major n x n, leading dim ldb
+        B = g.CuModMatrix.wrap_device(Bt.data_ptr(), n, n, ldb, N, ctx=ctx)
+        if rank == 0:
+            Bs = g.synth(n, n, N, SEED_B, ctx=ctx)
+            g.copy_(B, Bs)
+            ctx.sync()
+            del Bs
+        C = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+        npan = max(1, args.panels) if world > 1 else 1
+        pan = (n + npan - 1) // npan
+
+        def step():
+            if world == 1:
+                g.mul_(C, A, B)
+                return
+            works = []
+            for p in range(npan):
+                c0, c1 = p * pan, min(n, (p + 1) * pan)
+                works.append(dist.broadcast(Bt[c0:c1], src=0, async_op=True))
+            for p in range(npan):
+                c0, c1 = p * pan, min(n, (p + 1) * pan)
+                works[p].wait()  # stream-level dependency: the GEMM of panel p overlaps the broadcast of panel p+1
+                g.capi.check(C.lib.gffm_gemm_block(C.h, 0, c0, A.h, 0, 0, B.h, 0, c0, mloc, c1 - c0, n, 0, 0, g.capi.GEMM_STORE, g.capi.ALGO_AUTO))
+
+        for _ in range(W):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ctx.set_profiling(True)
+        l0 = ctx.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(K):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / K
+        launches = ctx.launch_count() - l0
+        phase_ms = ctx.last_timings()  # phases of the LAST timed step: [split, tcgen05 gemm, crt]
+        clocks = sampler.stop() if rank == 0 else None
+        ctx.set_profiling(False)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local}")
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+            launches = int(lt.item())
+        checksum = C.checksum()
+        value = 2.0 * n ** 3 / (ms * 1e-3) / 1e9
+
+        # ---- roofline of the dominant kernel (tcgen05 GEMM): a few more profiled steps, kernel-only durations --------
+        gemm_ms = [phase_ms[1]] if len(phase_ms) >= 2 else []
+        ctx.set_profiling(True)
+        for _ in range(3):
+            if world == 1:
+                g.mul_(C, A, B)
+            else:
+                g.capi.check(C.lib.gffm_gemm_block(C.h, 0, 0, A.h, 0, 0, B.h, 0, 0, mloc, pan, n, 0, 0, g.capi.GEMM_STORE, g.capi.ALGO_AUTO))
+            pm = ctx.last_timings()
+            if len(pm) >= 2:
+                gemm_ms.append(pm[1])
+        ctx.set_profiling(False)
+        bits = (N - 1).bit_length()
+        if N <= 256:
+            units = 1
+        elif N <= 65536:
+            units = 4
+        else:  # RNS: number of 8-bit moduli with product > 2*K*(N/2)^2
+            need = 2 * n * (N // 2) ** 2
+            need += (need >> 16) + 2
+            mods = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197]
+            prod, units = 1, 0
+            while prod <= need:
+                prod *= mods[units]; units += 1
+        cols_per_launch = n if world == 1 else pan
+        int8_ops = units * 2.0 * mloc * cols_per_launch * n
+        gemm_avg = statistics.mean(gemm_ms[1:] if len(gemm_ms) > 1 and world > 1 else gemm_ms) if gemm_ms else None
+        achieved = int8_ops / (gemm_avg * 1e-3) / 1e12 if gemm_avg else None
+        int8_peak = 2.0 * peaks["bf16"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("gemm_tc_kernel_rns_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<SchemeRNS>" if N > 65536 else "gemm_tc_kernel<limb>",
+                    "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": (achieved / int8_peak) if achieved else None,
+                    "traffic": traffic, "launch_ms": gemm_avg, "int8_mma_units_per_k_step": units,
+                    "peak_source": f"2 x bf16 dense {peaks['bf16']} TFLOP/s, {peaks['src']}; int8 tcgen05 rate is 2x the bf16 rate (nominal 4.5 vs 2.25 P)",
+                    "phases_ms_last_step": phase_ms}
+
+        # ---- e2e through the public API with host buffers (rank-local shard; H2D A,B + GEMM + D2H C per step) --------
+        e2e = None
+        if not args.no_e2e:
+            hA = torch.empty((n, mloc), dtype=torch.int32).pin_memory()   # column-major mloc x n
+            hB = torch.empty((n, n), dtype=torch.int32).pin_memory()
+            hC = torch.empty((n, mloc), dtype=torch.int32).pin_memory()
+            g.capi.check(A.lib.gffm_mat_download(A.h, hA.data_ptr(), g.capi.U32, mloc, 0))
+            g.capi.check(B.lib.gffm_mat_download(B.h, hB.data_ptr(), g.capi.U32, n, 0))
+            A2 = g.zeros(np.float32, mloc, n, N, ctx=ctx); B2 = g.zeros(np.float32, n, n, N, ctx=ctx); C2 = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+
+            def e2e_step():
+                g.capi.check(A2.lib.gffm_mat_upload(A2.h, hA.data_ptr(), g.capi.U32, mloc, 1))
+                g.capi.check(B2.lib.gffm_mat_upload(B2.h, hB.data_ptr(), g.capi.U32, n, 1))
+                g.mul_(C2, A2, B2)
+                g.capi.check(C2.lib.gffm_mat_download(C2.h, hC.data_ptr(), g.capi.U32, mloc, 0))
+
+            e2e_step()
+            ke = max(1, min(K, 3))
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                e2e_step()
+            barrier()
+            te = (time.perf_counter() - t0) / ke
+            if world > 1:
+                t = torch.tensor([te], dtype=torch.float64, device=f"cuda:{local}")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                te = float(t.item())
+            same = bool(C2.equals(C))
+            e2e = {"value": 2.0 * n ** 3 / te / 1e9, "unit": "GOPS", "h2d_bytes_per_step": int(4 * (mloc * n + n * n)), "d2h_bytes_per_step": int(4 * mloc * n),
+                   "ms_per_step": te * 1e3, "steps": ke, "host_dtype": "uint32 residues (pinned)", "matches_resident_result": same}
+            del A2, B2, C2
+
+        extras = {}
+        if args.extras and world == 1:
+            for N2 in (11, 65521):
+                A_, B_ = g.synth(n, n, N2, SEED_A, ctx=ctx), g.synth(n, n, N2, SEED_B, ctx=ctx)
+                C_ = g.zeros(np.float32, n, n, N2, ctx=ctx)
+                for _ in range(3):
+                    g.mul_(C_, A_, B_)
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for _ in range(5):
+                    g.mul_(C_, A_, B_)
+                a1.record(stream); torch.cuda.synchronize()
+                t_ = a0.elapsed_time(a1) / 5
+                extras[f"matmul_n{n}_mod{N2}"] = {"ms": t_, "GOPS": 2.0 * n ** 3 / t_ / 1e6}
+                del A_, B_, C_
+            for (np_, Np) in ((n, 65521), (n, N)):
+                A_ = g.synth(np_, np_, Np, 9, ctx=ctx)
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                U_, L_, pr_, pc_, rk_ = g.pluq_gpu_kernel(A_, return_rank=True)
+                torch.cuda.synchronize(); tp_ = time.perf_counter() - t0
+                extras[f"pluq_n{np_}_mod{Np}"] = {"seconds": tp_, "rank": rk_}
+                del A_, U_, L_
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        gops, cores, desc, dt = cpu_arm(n, N)
+        cpu = {"value": gops, "unit": "GOPS", "cores": cores, "kind": "port", "sample": desc, "seconds": dt}
+
+    if rank == 0:
+        out = {
+            "metric": "mod-p matmul effective GOPS (2n^3/s)", "value": value, "unit": "GOPS", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s8 residue limbs, int32 accumulate (exact)",
+            "data": "synthetic",
+            "config": {"workload": f"{n}x{n} * {n}x{n} matmul mod {N} ({bits}-bit modulus), A,B resident as uint32 residues", "n": n, "modulus": N,
+                       "encoding": "RNS int8 tcgen05" if N > 65536 else "positional int8 limbs tcgen05",
+                       "sharding": "single GPU" if world == 1 else f"row blocks of A over {world} GPUs, B broadcast from rank 0 by NCCL in {npan} column panels overlapped with the GEMM",
+                       "l2_policy": f"inputs larger than L2: A and B are {4 * n * n / 2**20:.0f} MiB each vs 126 MB L2", "checksum_rank0": f"{checksum:016x}",
+                       "extras": extras},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -98,8 +98,23 @@ extern "C" int32_t gffm_get_stream(gffm_ctx* ctx, void** s) {
   *s = (void*)ctx->stream;
   return GFFM_OK;
 }
+extern "C" int32_t gffm_set_profiling(gffm_ctx* ctx, int32_t on) {
+  if (!ctx) GFFM_FAIL(GFFM_ERR_INVALID, "null ctx");
+  ctx->profile = on != 0;
+  ctx->n_ev = 0;
+  return GFFM_OK;
+}
 extern "C" int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t cap, int32_t* n) {
   if (!ctx) GFFM_FAIL(GFFM_ERR_INVALID, "null ctx");
+  ctx->timings.clear();
+  if (ctx->n_ev >= 2) {
+    GFFM_CUDA(cudaEventSynchronize(ctx->ev[ctx->n_ev - 1]));
+    for (int i = 0; i + 1 < ctx->n_ev; ++i) {
+      float t = 0.f;
+      GFFM_CUDA(cudaEventElapsedTime(&t, ctx->ev[i], ctx->ev[i + 1]));
+      ctx->timings.push_back((double)t);
+    }
+  }
   int32_t k = 0;
   for (; k < cap && k < (int32_t)ctx->timings.size(); ++k) ms[k] = ctx->timings[k];
   if (n) *n = k;
@@ -295,6 +310,14 @@ extern "C" int32_t gffm_mat_upload(gffm_mat* m, const void* host, int32_t dtype,
   if (m->rows == 0 || m->cols == 0) return GFFM_OK;
   gffm_ctx* ctx = m->ctx;
   cudaSetDevice(ctx->device);
+  if (dtype == GFFM_U32) {
+    // residues already in storage format: one strided DMA straight into the matrix, reduction in place
+    GFFM_CUDA(cudaMemcpy2DAsync(m->data, (size_t)m->ld * 4, host, (size_t)ld * 4, (size_t)m->rows * 4, (size_t)m->cols,
+                                cudaMemcpyHostToDevice, ctx->stream));
+    if (do_mod && m->N < (1ull << 32)) GFFM_TRY(gffm_ew_views(ctx, GFFM_EW_MOD, view_of(m), view_of(m), nullptr, 0, m->N));
+    GFFM_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffer is caller-owned
+    return GFFM_OK;
+  }
   // staged through a device scratch buffer in column slabs (bounded memory, chunked for 8 GB operands)
   const int64_t slab_cols = std::max<int64_t>(1, std::min<int64_t>(m->cols, (int64_t)((256ull << 20) / (es * (size_t)m->rows))));
   GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_misc, (size_t)slab_cols * m->rows * es + 256));
@@ -339,6 +362,12 @@ extern "C" int32_t gffm_mat_download(gffm_mat* m, void* host, int32_t dtype, int
   if (!host) GFFM_FAIL(GFFM_ERR_INVALID, "null host buffer");
   gffm_ctx* ctx = m->ctx;
   cudaSetDevice(ctx->device);
+  if (dtype == GFFM_U32 && (!with_padding || (rows <= m->ld && cols <= m->pcols))) {
+    GFFM_CUDA(cudaMemcpy2DAsync(host, (size_t)ld * 4, m->data, (size_t)m->ld * 4, (size_t)rows * 4, (size_t)cols,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GFFM_OK;
+  }
   const int64_t slab_cols = std::max<int64_t>(1, std::min<int64_t>(cols, (int64_t)((256ull << 20) / (es * (size_t)rows))));
   GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_misc, (size_t)slab_cols * rows * es));
   for (int64_t c0 = 0; c0 < cols; c0 += slab_cols) {

@@ -51,6 +51,8 @@ struct gffm_ctx {
   // grow-only scratch buffers (stream-ordered reuse)
   gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned;
   std::vector<double> timings;
+  bool profile = false;
+  int n_ev = 0;  // events recorded by the last profiled call
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -484,6 +484,13 @@ int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2,
   return GFFM_OK;
 }
 
+inline void prof_mark(gffm_ctx* ctx, int idx) {
+  if (ctx->profile && idx < 8) {
+    cudaEventRecord(ctx->ev[idx], ctx->stream);
+    ctx->n_ev = idx + 1;
+  }
+}
+
 const uint32_t kModuli[MAX_MODS] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197};
 
 }  // namespace
@@ -528,8 +535,10 @@ int32_t gffm_gemm_tc_limb_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView
     const int64_t Kp = round_up(kc, 128);
     uint8_t* pa = (uint8_t*)ctx->ws_planes_a.ptr;
     uint8_t* pb = (uint8_t*)ctx->ws_planes_b.ptr;
+    prof_mark(ctx, 0);
     GFFM_TRY(run_split(ctx, true, A, A2, k0, kc, pa, Kp, rowsPA, sp));
     GFFM_TRY(run_split(ctx, false, B, B2, k0, kc, pb, Kp, rowsPB, sp));
+    prof_mark(ctx, 1);
     CUtensorMap tmA, tmB;
     GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, L, BM));
     GFFM_TRY(make_plane_tmap(&tmB, pb, Kp, rowsPB, L, BN));
@@ -547,6 +556,7 @@ int32_t gffm_gemm_tc_limb_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView
     p.modP = make_modp(P);
     if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p));
     else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p));
+    prof_mark(ctx, 2);
   }
   return GFFM_OK;
 }
@@ -629,8 +639,10 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     spb.is_b = 1;
     uint8_t* pa = (uint8_t*)ctx->ws_planes_a.ptr;
     uint8_t* pb = (uint8_t*)ctx->ws_planes_b.ptr;
+    prof_mark(ctx, 0);
     GFFM_TRY(run_split(ctx, true, A, A2, k0, kc, pa, Kp, rowsPA, spa));
     GFFM_TRY(run_split(ctx, false, B, B2, k0, kc, pb, Kp, rowsPB, spb));
+    prof_mark(ctx, 1);
     CUtensorMap tmA, tmB;
     GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, s, BM));
     GFFM_TRY(make_plane_tmap(&tmB, pb, Kp, rowsPB, s, BN));
@@ -644,10 +656,12 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     p.lde = lde;
     p.e_plane_stride = e_plane;
     GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p));
+    prof_mark(ctx, 2);
     dim3 grid((unsigned)ceil_div(m, 256), (unsigned)n);
     crt_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, (int)m, (int)n, Cv.p, Cv.ld,
                                               kara_hi, ldhi, cp);
     GFFM_LAUNCH_CHECK(ctx);
+    prof_mark(ctx, 3);
     if (kara_hi && K > kmax) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "Karatsuba carry split with K > 65536");
   }
   return GFFM_OK;

@@ -38,6 +38,15 @@ class Context:
     def set_stream(self, cuda_stream_ptr: int):
         capi.check(self.lib.gffm_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_profiling(self, on: bool):
+        capi.check(self.lib.gffm_set_profiling(self.h, 1 if on else 0))
+
+    def last_timings(self):
+        buf = (C.c_double * 16)()
+        n = C.c_int32(0)
+        capi.check(self.lib.gffm_last_timings(self.h, buf, 16, C.byref(n)))
+        return [buf[i] for i in range(n.value)]
+
     def launch_count(self) -> int:
         n = C.c_int64(0)
         capi.check(self.lib.gffm_launch_count(self.h, C.byref(n)))

@@ -1,0 +1,322 @@
+# GPUFiniteFieldMatricesB200.jl -- drop-in Julia host layer for the B200-native library.
+#
+# Same exported names, argument meaning and error behaviour as the reference module
+# (reference src/GPUFiniteFieldMatrices.jl:36-60), but every operation is one `ccall` into libgffm.so
+# (include/gffm.h): no CUDA.jl kernels, no cuBLAS, no CPU fallback.  This file is declarative on purpose -- one
+# `ccall` per exported function -- and is mirrored 1:1 by the ctypes binding (capi.py / cumodmatrix.py) that the
+# test-suite executes, because no Julia toolchain exists in the build image.
+module GPUFiniteFieldMatricesB200
+
+using LinearAlgebra
+import LinearAlgebra: mul!, rmul!, lmul!, transpose
+import Base: size, length, eltype, getindex, setindex!, show, +, -, *, /, ^, copy, copy!, copyto!, fill!, Array
+
+const libgffm = get(ENV, "GFFM_LIB", joinpath(@__DIR__, "..", "lib", "libgffm.so"))
+const TILE_WIDTH = 32            # reference CuModMatrix.jl:2
+const DEFAULT_TYPE = Float32     # reference CuModMatrix.jl:3
+
+# ---- exceptions (reference CuModMatrix.jl:5-31; MatrixNotInvertibleException is used but never defined there, :485)
+struct CuModArraySizeMismatchException <: Exception; msg::String; end
+struct CuModArrayModulusMismatchException <: Exception; msg::String; end
+struct CuModMatrixTooLargeException <: Exception; msg::String; end
+struct CuModMatrixNotSquareException <: Exception; msg::String; end
+struct CuModMatrixModulusNotPrimeException <: Exception; msg::String; end
+struct InverseOverflowError <: Exception; msg::String; end
+struct InverseNotDefinedException <: Exception; msg::String; end
+struct MatrixNotInvertibleException <: Exception; msg::String; end
+
+last_error() = unsafe_string(ccall((:gffm_last_error, libgffm), Cstring, ()))
+version() = unsafe_string(ccall((:gffm_version, libgffm), Cstring, ()))
+
+function check(st::Int32)
+    st == 0 && return nothing
+    msg = last_error()
+    st == 2 && throw(CuModArraySizeMismatchException(msg))
+    (st == 3 || st == 4) && throw(CuModArrayModulusMismatchException(msg))
+    st == 5 && throw(CuModMatrixNotSquareException(msg))
+    st == 6 && throw(MatrixNotInvertibleException(msg))
+    st == 7 && throw(InverseNotDefinedException(msg))
+    st == 11 && throw(InexactError(:convert, Integer, msg))
+    st == 1 && throw(ArgumentError(msg))
+    error("libgffm status $st: $msg")
+end
+
+# ---- context (CUDA.jl's task-local device/stream state in the reference) ---------------------------------------
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:gffm_create, libgffm), Int32, (Int32, Ref{Ptr{Cvoid}}), device, r))
+        c = new(r[])
+        finalizer(x -> ccall((:gffm_destroy, libgffm), Int32, (Ptr{Cvoid},), x.h), c)
+        return c
+    end
+end
+const _ctx = Ref{Union{Nothing,Context}}(nothing)
+default_context() = (_ctx[] === nothing && (_ctx[] = Context(0)); _ctx[])
+device_count() = (r = Ref{Int32}(0); check(ccall((:gffm_device_count, libgffm), Int32, (Ref{Int32},), r)); Int(r[]))
+synchronize(c::Context=default_context()) = check(ccall((:gffm_sync, libgffm), Int32, (Ptr{Cvoid},), c.h))
+set_stream!(c::Context, s::Ptr{Cvoid}) = check(ccall((:gffm_set_stream, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), c.h, s))
+get_stream(c::Context) = (r = Ref{Ptr{Cvoid}}(C_NULL); check(ccall((:gffm_get_stream, libgffm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), c.h, r)); r[])
+launch_count(c::Context=default_context()) = (r = Ref{Int64}(0); check(ccall((:gffm_launch_count, libgffm), Int32, (Ptr{Cvoid}, Ref{Int64}), c.h, r)); r[])
+set_profiling!(c::Context, on::Bool) = check(ccall((:gffm_set_profiling, libgffm), Int32, (Ptr{Cvoid}, Int32), c.h, on ? 1 : 0))
+function last_timings(c::Context=default_context())
+    buf = zeros(Float64, 16); n = Ref{Int32}(0)
+    check(ccall((:gffm_last_timings, libgffm), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32, Ref{Int32}), c.h, buf, 16, n))
+    buf[1:n[]]
+end
+
+# ---- container: struct CuModArray{T,D} (reference CuModMatrix.jl:42-46) ---------------------------------------------
+_dtype(::Type{Float32}) = Int32(0); _dtype(::Type{Float64}) = Int32(1); _dtype(::Type{Int64}) = Int32(2)
+_dtype(::Type{UInt32}) = Int32(3); _dtype(::Type{Int32}) = Int32(4)
+
+mutable struct CuModArray{T,D}
+    h::Ptr{Cvoid}      # gffm_mat*
+    N::Int
+    ctx::Context
+    function CuModArray{T,D}(h::Ptr{Cvoid}, N::Integer, ctx::Context) where {T,D}
+        m = new{T,D}(h, Int(N), ctx)
+        finalizer(x -> ccall((:gffm_mat_destroy, libgffm), Int32, (Ptr{Cvoid},), x.h), m)   # no Julia callbacks inside
+        return m
+    end
+end
+const CuModMatrix{T} = CuModArray{T,2}
+const CuModVector{T} = CuModArray{T,1}
+
+function _create(::Type{T}, D::Int, rows, cols, N; ctx=default_context()) where {T}
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gffm_mat_create, libgffm), Int32, (Ptr{Cvoid}, Int64, Int64, UInt64, Int32, Ref{Ptr{Cvoid}}), ctx.h, rows, cols, N, -1, r))
+    CuModArray{T,D}(r[], N, ctx)
+end
+
+# host ctor CuModMatrix(A, N; mod=true, new_size=nothing, elem_type=Float32) (reference CuModMatrix.jl:53-99,143-145)
+function CuModArray{T,D}(A::AbstractArray, N::Integer; mod::Bool=true, new_size=nothing, ctx=default_context()) where {T,D}
+    rows = size(A, 1); cols = D == 1 ? 1 : size(A, 2)
+    if new_size !== nothing
+        rows = new_size[1]; cols = D == 1 ? 1 : new_size[2]
+    end
+    m = _create(T, D, rows, cols, N; ctx=ctx)
+    S = eltype(A) <: AbstractFloat ? (eltype(A) == Float32 ? Float32 : Float64) : Int64
+    host = zeros(S, rows, cols)
+    r0 = min(rows, size(A, 1)); c0 = min(cols, size(A, 2))
+    host[1:r0, 1:c0] .= convert.(S, A[1:r0, 1:c0])
+    check(ccall((:gffm_mat_upload, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int32), m.h, host, _dtype(S), rows, mod ? 1 : 0))
+    return m
+end
+CuModMatrix(A::AbstractMatrix, N::Integer; elem_type::Type=DEFAULT_TYPE, kw...) = CuModArray{elem_type,2}(A, N; kw...)
+CuModVector(A::AbstractVector, N::Integer; elem_type::Type=DEFAULT_TYPE, kw...) = CuModArray{elem_type,1}(A, N; kw...)
+# device-wrapper ctor (reference CuModMatrix.jl:113-121): adopt an existing UInt32 device buffer
+function wrap_device(::Type{T}, ptr::Ptr{Cvoid}, rows, cols, ld, N; ctx=default_context()) where {T}
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gffm_mat_wrap, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, UInt64, Ref{Ptr{Cvoid}}), ctx.h, ptr, rows, cols, ld, N, r))
+    CuModArray{T,2}(r[], N, ctx)
+end
+
+_i64(f, A) = (r = Ref{Int64}(0); check(f(A.h, r)); Int(r[]))
+rows(A::CuModArray) = _i64((h, r) -> ccall((:gffm_mat_rows, libgffm), Int32, (Ptr{Cvoid}, Ref{Int64}), h, r), A)
+cols(A::CuModArray) = _i64((h, r) -> ccall((:gffm_mat_cols, libgffm), Int32, (Ptr{Cvoid}, Ref{Int64}), h, r), A)
+leading_dim(A::CuModArray) = _i64((h, r) -> ccall((:gffm_mat_ld, libgffm), Int32, (Ptr{Cvoid}, Ref{Int64}), h, r), A)
+padding(A::CuModArray) = (r = Ref{Int32}(0); check(ccall((:gffm_mat_pad, libgffm), Int32, (Ptr{Cvoid}, Ref{Int32}), A.h, r)); Int(r[]))
+modulus(A::CuModArray) = (r = Ref{UInt64}(0); check(ccall((:gffm_mat_modulus, libgffm), Int32, (Ptr{Cvoid}, Ref{UInt64}), A.h, r)); Int(r[]))
+device_ptr(A::CuModArray) = (r = Ref{Ptr{Cvoid}}(C_NULL); check(ccall((:gffm_mat_device_ptr, libgffm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, r)); r[])
+size(A::CuModArray{T,2}) where {T} = (rows(A), cols(A))
+size(A::CuModArray{T,1}) where {T} = (rows(A),)
+size(A::CuModArray, d::Integer) = d == 1 ? rows(A) : (d == 2 ? cols(A) : 1)
+length(A::CuModArray) = rows(A) * cols(A)
+eltype(::CuModArray{T}) where {T} = T
+
+# Array(A) / unsafe_Array(A) (reference CuModMatrix.jl:251-261)
+function _download(A::CuModArray{T}, padded::Bool) where {T}
+    r = rows(A) + (padded ? TILE_WIDTH : 0); c = cols(A) + (padded ? TILE_WIDTH : 0)
+    out = zeros(T, r, c)
+    check(ccall((:gffm_mat_download, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int32), A.h, out, _dtype(T), max(r, 1), padded ? 1 : 0))
+    return out
+end
+Array(A::CuModArray{T,2}) where {T} = _download(A, false)
+Array(A::CuModArray{T,1}) where {T} = vec(_download(A, false))
+unsafe_Array(A::CuModArray) = _download(A, true)
+function getindex(A::CuModArray{T}, i::Integer, j::Integer=1) where {T}
+    r = Ref{Int64}(0); check(ccall((:gffm_mat_get_elem, libgffm), Int32, (Ptr{Cvoid}, Int64, Int64, Ref{Int64}), A.h, i - 1, j - 1, r)); T(r[])
+end
+setindex!(A::CuModArray, v, i::Integer, j::Integer=1) = check(ccall((:gffm_mat_set_elem, libgffm), Int32, (Ptr{Cvoid}, Int64, Int64, Int64), A.h, i - 1, j - 1, Int64(v)))
+show(io::IO, A::CuModArray{T}) where {T} = print(io, "$(rows(A))x$(cols(A)) CuModMatrix{$T} modulo $(A.N)")
+
+# zeros / eye / rand (reference CuModMatrix.jl:510-556)
+zeros(::Type{T}, r::Integer, c::Integer, N::Integer) where {T} = _create(T, 2, r, c, N)
+eye(::Type{T}, n::Integer, N::Integer) where {T} = (m = _create(T, 2, n, n, N); check(ccall((:gffm_mat_eye, libgffm), Int32, (Ptr{Cvoid},), m.h)); m)
+rand(::Type{T}, r::Integer, c::Integer, N::Integer; seed::Integer=0) where {T} =
+    (m = _create(T, 2, r, c, N); check(ccall((:gffm_mat_rand, libgffm), Int32, (Ptr{Cvoid}, UInt64), m.h, seed)); m)
+synth(::Type{T}, r::Integer, c::Integer, N::Integer, seed::Integer) where {T} =
+    (m = _create(T, 2, r, c, N); check(ccall((:gffm_mat_synth, libgffm), Int32, (Ptr{Cvoid}, UInt64), m.h, seed)); m)
+copy!(dst::CuModArray, src::CuModArray) = (check(ccall((:gffm_mat_copy, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), dst.h, src.h)); dst)
+copyto!(dst::CuModArray, src::CuModArray) = copy!(dst, src)
+copy(A::CuModArray{T,D}) where {T,D} = copy!(_create(T, D, rows(A), cols(A), A.N; ctx=A.ctx), A)
+copy_block!(dst::CuModArray, dr, dc, src::CuModArray, sr, sc, nr, nc) =
+    check(ccall((:gffm_mat_copy_block, libgffm), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Int64, Int64), dst.h, dr - 1, dc - 1, src.h, sr - 1, sc - 1, nr, nc))
+fill!(A::CuModArray, v) = (check(ccall((:gffm_mat_fill, libgffm), Int32, (Ptr{Cvoid}, Int64), A.h, Int64(v))); A)
+zero!(A::CuModArray) = (check(ccall((:gffm_mat_zero, libgffm), Int32, (Ptr{Cvoid},), A.h)); A)
+function change_modulus_no_alloc!(A::CuModArray, N::Integer)   # reference CuModMatrix.jl:745-760
+    check(ccall((:gffm_mat_set_modulus, libgffm), Int32, (Ptr{Cvoid}, UInt64, Int32), A.h, N, 1)); A.N = N; A
+end
+change_modulus(A::CuModArray, N::Integer) = change_modulus_no_alloc!(copy(A), N)   # :726-740
+transpose(A::CuModArray{T,2}) where {T} = (B = _create(T, 2, cols(A), rows(A), A.N; ctx=A.ctx); check(ccall((:gffm_mat_transpose, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), B.h, A.h)); B)
+isequal_device(A::CuModArray, B::CuModArray) = (r = Ref{Int32}(0); check(ccall((:gffm_mat_equal, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Int32}), A.h, B.h, r)); r[] != 0)
+checksum(A::CuModArray) = (r = Ref{UInt64}(0); check(ccall((:gffm_mat_checksum, libgffm), Int32, (Ptr{Cvoid}, Ref{UInt64}), A.h, r)); r[])
+
+# ---- elementwise (reference kernel_ops/*.jl) ----------------------------------------------------------------------
+_ew(op, C, A, B, s, modN) = (check(ccall((:gffm_ewise, libgffm), Int32, (Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, UInt64),
+                                         op, C.h, A.h, B === nothing ? C_NULL : B.h, Int64(s), modN)); C)
+mod_elements!(A::CuModArray, mod_N::Integer=0) = _ew(0, A, A, nothing, 0, mod_N)
+add!(C, A, B, mod_N::Integer=0) = _ew(1, C, A, B, 0, mod_N)
+sub!(C, A, B, mod_N::Integer=0) = _ew(2, C, A, B, 0, mod_N)
+elementwise_multiply!(C, A, B, mod_N::Integer=0) = _ew(3, C, A, B, 0, mod_N)
+scalar_add!(C, A, s::Number, mod_N::Integer=0) = _ew(4, C, A, nothing, s, mod_N)
+scalar_sub!(C, A, s::Number, mod_N::Integer=0) = _ew(5, C, A, nothing, s, mod_N)
+rscalar_sub!(C, A, s::Number, mod_N::Integer=0) = _ew(6, C, A, nothing, s, mod_N)
+negate!(C, A, mod_N::Integer=0) = _ew(6, C, A, nothing, 0, mod_N)
+mul!(C::CuModArray, A::CuModArray, s::Number, mod_N::Integer=0) = _ew(7, C, A, nothing, s, mod_N)
+div!(C, A, s::Number, mod_N::Integer=0) = _ew(8, C, A, nothing, s, mod_N)
+rmul!(A::CuModArray, s::Number) = mul!(A, A, s)
+lmul!(s::Number, A::CuModArray) = mul!(A, A, s)
+_like(A::CuModArray{T,D}) where {T,D} = _create(T, D, rows(A), cols(A), A.N; ctx=A.ctx)
++(A::CuModArray, B::CuModArray) = add!(_like(A), A, B)
+-(A::CuModArray, B::CuModArray) = sub!(_like(A), A, B)
++(A::CuModArray, s::Number) = scalar_add!(_like(A), A, s); +(s::Number, A::CuModArray) = A + s
+-(A::CuModArray, s::Number) = scalar_sub!(_like(A), A, s); -(s::Number, A::CuModArray) = rscalar_sub!(_like(A), A, s)
+-(A::CuModArray) = negate!(_like(A), A)
+*(A::CuModArray, s::Number) = mul!(_like(A), A, s); *(s::Number, A::CuModArray) = A * s
+/(A::CuModArray, s::Number) = div!(_like(A), A, s)
+
+# ---- modular GEMM / GEMV (reference CuModMatrix.jl:767-836, kernel_mul/stripe_mul.jl:82-244) ------------------------------
+# matrix form: M (stripe width) is meaningless here and ignored; N = modulus override.  vector form: R = input bound, P = modulus.
+function mul!(C::CuModArray{T,2}, A::CuModArray{T,2}, B::CuModArray{T,2}; M=nothing, N::Integer=0, mode::Integer=0, algo::Integer=0) where {T}
+    check(ccall((:gffm_gemm, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64, Int32, Int32), C.h, A.h, B.h, 0, N, mode, algo)); C
+end
+mulN!(C, A, B, N::Integer) = mul!(C, A, B; N=N)
+stripe_mul!(C, A, B; kw...) = mul!(C, A, B; kw...)
+function mul!(z::CuModArray{T,1}, A::CuModArray{T,2}, x::CuModArray{T,1}; R::Integer=0, P::Integer=0, maxopsOverride=false) where {T}
+    check(ccall((:gffm_gemv, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64), z.h, A.h, x.h, R, P)); z
+end
+gemm_block!(C, cr, cc, A, ar, ac, B, br, bc, m, n, k; R=0, P=0, mode=0, algo=0) =
+    check(ccall((:gffm_gemm_block, libgffm), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, UInt64, UInt64, Int32, Int32),
+                C.h, cr - 1, cc - 1, A.h, ar - 1, ac - 1, B.h, br - 1, bc - 1, m, n, k, R, P, mode, algo))
+*(A::CuModArray{T,2}, B::CuModArray{T,2}) where {T} = mul!(_create(T, 2, rows(A), cols(B), A.N; ctx=A.ctx), A, B)      # kernel_ops/mul_ops.jl:54-58
+*(A::CuModArray{T,2}, x::CuModArray{T,1}) where {T} = mul!(_create(T, 1, rows(A), 1, A.N; ctx=A.ctx), A, x)
+mat_mul_gpu_type(A, B, mod_N::Integer=0) = mul!(_create(eltype(A), 2, rows(A), cols(B), mod_N == 0 ? A.N : mod_N; ctx=A.ctx), A, B; N=(mod_N == 0 ? A.N : mod_N))
+mat_mul_type_inplace!(C, A, B, mod_N::Integer=0) = mul!(C, A, B; N=(mod_N == 0 ? C.N : mod_N))
+function ^(A::CuModArray{T,2}, n::Integer) where {T}      # reference CuModMatrix.jl:307-329
+    rows(A) == cols(A) || throw(CuModMatrixNotSquareException("power of a non-square matrix"))
+    n < 0 && return inverse(A)^(-n)
+    result = eye(T, rows(A), A.N); base = copy(A)
+    while n > 0
+        (n & 1) == 1 && (result = result * base)
+        n >>= 1
+        n > 0 && (base = base * base)
+    end
+    result
+end
+
+# ---- elimination (reference rref_lu_pluq/*.jl, triangular/*.jl, CuModMatrix.jl:335-502) -----------------------------------
+_tuples(buf, n) = [(Int(buf[2k-1]), Int(buf[2k])) for k in 1:n]
+function pluq_gpu_kernel(A::CuModArray{T,2}; debug::Bool=false, col_pivot_mode::Integer=0) where {T}
+    U = Ref{Ptr{Cvoid}}(C_NULL); L = Ref{Ptr{Cvoid}}(C_NULL)
+    cap = max(rows(A), cols(A), 1)
+    pr = Base.zeros(Int64, 2cap); pc = Base.zeros(Int64, 2cap)
+    npr = Ref{Int64}(0); npc = Ref{Int64}(0); rk = Ref{Int64}(0)
+    check(ccall((:gffm_pluq, libgffm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}, Ptr{Int64}, Ref{Int64}, Ptr{Int64}, Ref{Int64}, Ref{Int64}, Int32),
+                A.h, U, L, pr, npr, pc, npc, rk, col_pivot_mode))
+    (CuModArray{T,2}(U[], A.N, A.ctx), CuModArray{T,2}(L[], A.N, A.ctx), _tuples(pr, npr[]), _tuples(pc, npc[]))
+end
+const pluq = pluq_gpu_kernel
+_setup_PLUQ(A; debug::Bool=false) = pluq_gpu_kernel(A; debug=debug)        # reference CuModMatrix.jl:335-338
+function lu(A::CuModArray{T,2}) where {T}                                # intended lu_gpu_type, test/Experiments/rref_gpu_type.jl:60-103
+    U = Ref{Ptr{Cvoid}}(C_NULL); L = Ref{Ptr{Cvoid}}(C_NULL); cap = max(min(rows(A), cols(A)), 1)
+    pr = Base.zeros(Int64, 2cap); piv = Base.zeros(Int64, cap); npr = Ref{Int64}(0); rk = Ref{Int64}(0)
+    check(ccall((:gffm_lu, libgffm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}, Ptr{Int64}, Ref{Int64}, Ptr{Int64}, Ref{Int64}), A.h, U, L, pr, npr, piv, rk))
+    (CuModArray{T,2}(U[], A.N, A.ctx), CuModArray{T,2}(L[], A.N, A.ctx), _tuples(pr, npr[]))
+end
+function rref(A::CuModArray{T,2}) where {T}                              # intended rref_gpu_type, rref_gpu_type.jl:8-51
+    R = Ref{Ptr{Cvoid}}(C_NULL); cap = max(min(rows(A), cols(A)), 1); piv = Base.zeros(Int64, cap); rk = Ref{Int64}(0)
+    check(ccall((:gffm_rref, libgffm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ptr{Int64}, Ref{Int64}), A.h, R, piv, rk))
+    CuModArray{T,2}(R[], A.N, A.ctx)
+end
+rank(A::CuModArray) = (r = Ref{Int64}(0); check(ccall((:gffm_rank, libgffm), Int32, (Ptr{Cvoid}, Ref{Int64}), A.h, r)); Int(r[]))
+function is_invertible_with_inverse(A::CuModArray{T,2}; debug::Bool=false) where {T}     # reference CuModMatrix.jl:356-422
+    out = Ref{Ptr{Cvoid}}(C_NULL); ok = Ref{Int32}(0)
+    check(ccall((:gffm_inverse, libgffm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Int32}), A.h, out, ok))
+    ok[] == 0 ? (false, nothing) : (true, CuModArray{T,2}(out[], A.N, A.ctx))
+end
+is_invertible(A::CuModArray) = rows(A) == cols(A) && rank(A) == rows(A)                  # :460-465
+function inverse(A::CuModArray; debug::Bool=false)                                       # :480-502
+    ok, inv = is_invertible_with_inverse(A)
+    ok || throw(MatrixNotInvertibleException("matrix is not invertible"))
+    inv
+end
+function _triinv(A::CuModArray{T,2}, upper::Bool) where {T}
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gffm_triinv, libgffm), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), A.h, upper ? 1 : 0, out))
+    CuModArray{T,2}(out[], A.N, A.ctx)
+end
+upper_triangular_inverse_no_copy(A; debug::Bool=false) = _triinv(A, true)    # triangular_inverse_no_copy.jl:197-228
+lower_triangular_inverse_no_copy(A; debug::Bool=false) = _triinv(A, false)   # :450-478
+backward_sub_gpu_type_32(A) = _triinv(A, true)                               # substitution_inplace.jl:51-56
+forward_sub_gpu_type_32(A) = _triinv(A, false)                               # :37-43
+function _perm!(A, P::Vector{Tuple{Int,Int}}, on_cols::Bool, inv::Bool)      # permutations.jl:11-27,73-89
+    flat = Int64[x for t in P for x in t]
+    check(ccall((:gffm_apply_perm, libgffm), Int32, (Ptr{Cvoid}, Ptr{Int64}, Int64, Int32, Int32), A.h, flat, length(P), on_cols ? 1 : 0, inv ? 1 : 0)); A
+end
+apply_col_perm!(P, A) = _perm!(A, P, true, false); apply_col_inv_perm!(P, A) = _perm!(A, P, true, true)
+apply_row_perm!(P, A) = _perm!(A, P, false, false); apply_row_inv_perm!(P, A) = _perm!(A, P, false, true)
+function perm_array_to_matrix(perm::Vector, N::Integer, new_size::Tuple{Int,Int}; perm_stack::Bool=false)   # permutations.jl:141-157
+    n = length(perm)
+    if perm_stack
+        P = Matrix{Int}(I, n, n); for (i, j) in perm; P[i, :], P[j, :] = P[j, :], P[i, :]; end
+    else
+        P = Base.zeros(Int, n, n); for i in 1:n; P[perm[i], i] = 1; end
+    end
+    CuModMatrix(P, N; new_size=new_size)
+end
+function mod_inv(p::Integer, P::Integer)                                      # pluq_kernels.jl:11-31 (batched device kernel)
+    i = UInt64[mod(p, P)]; o = UInt64[0]
+    check(ccall((:gffm_modinv_batch, libgffm), Int32, (Ptr{Cvoid}, Ptr{UInt64}, Ptr{UInt64}, Int64, UInt64), default_context().h, i, o, 1, P)); Int(o[1])
+end
+
+# ---- Karatsuba two-limb matrices (reference src/KaratsubaMatrix/*.jl) --------------------------------------------------
+mutable struct KaratsubaArray{T,D}
+    data1::CuModArray{T,D}; data2::CuModArray{T,D}; plan::Union{Nothing,CuModArray{T,D}}
+    N1::Int; N2::Int; M::Int
+end
+const KaratsubaMatrix{T} = KaratsubaArray{T,2}
+const KaratsubaVector{T} = KaratsubaArray{T,1}
+KaratsubaMatrix(d1::CuModArray{T,2}, d2::CuModArray{T,2}, N1, N2, M=N1 * N2) where {T} = KaratsubaArray{T,2}(d1, d2, nothing, N1, N2, M)
+KaratsubaVector(d1::CuModArray{T,1}, d2::CuModArray{T,1}, N1, N2, M=N1 * N2) where {T} = KaratsubaArray{T,1}(d1, d2, nothing, N1, N2, M)
+function KaratsubaMatrix(::Type{T}, A::AbstractMatrix, N1, N2, M=N1 * N2) where {T}       # KaratsubaMatrix.jl:372-397
+    Am = mod.(A, M); KaratsubaMatrix(CuModMatrix(mod.(Am, N1), N1; elem_type=T), CuModMatrix(div.(Am, N1), N1; elem_type=T), N1, N2, M)
+end
+const MatToKMat = KaratsubaMatrix
+KaratsubaZeros(::Type{T}, r, c, N1, N2, M=N1 * N2) where {T} = KaratsubaMatrix(zeros(T, r, c, N1), zeros(T, r, c, N1), N1, N2, M)   # :404-420
+initialize_plan!(K::KaratsubaArray) = K        # :422-424 -- the limb add is fused into the GEMM prologue, no plan buffer needed
+Array(K::KaratsubaArray) = Int.(Array(K.data1)) .+ K.N1 .* Int.(Array(K.data2))            # :318-336
+function KMatMul!(C::KaratsubaArray, A::KaratsubaArray, B::KaratsubaArray)                 # :133-204 (and KMatMul_gemv! :238-300)
+    (A.M == B.M == C.M) || throw(CuModArrayModulusMismatchException("Karatsuba operands have different moduli"))
+    check(ccall((:gffm_kmat_mul, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64),
+                C.data1.h, C.data2.h, A.data1.h, A.data2.h, B.data1.h, B.data2.h, A.N1, A.N2)); C
+end
+const KMatMul_gemv! = KMatMul!
+_kew(op, C, A, B, s) = (check(ccall((:gffm_kmat_ewise, libgffm), Int32, (Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, UInt64, UInt64),
+    op, C.data1.h, C.data2.h, A.data1.h, A.data2.h, B === nothing ? C_NULL : B.data1.h, B === nothing ? C_NULL : B.data2.h, Int64(s), A.N1, A.N2)); C)
+add!(C::KaratsubaArray, A::KaratsubaArray, B::KaratsubaArray) = _kew(1, C, A, B, 0)       # :505-536
+sub!(C::KaratsubaArray, A::KaratsubaArray, B::KaratsubaArray) = _kew(2, C, A, B, 0)       # :583-629
+scalar_multiply!(C::KaratsubaArray, A::KaratsubaArray, s::Integer) = _kew(7, C, A, nothing, s)   # :631-666
+negate!(C::KaratsubaArray, A::KaratsubaArray) = _kew(6, C, A, nothing, 0)                 # :691-731
+
+export CuModArray, CuModMatrix, CuModVector, rows, cols, unsafe_Array, eye, zeros, rand, zero!, add!, sub!, elementwise_multiply!,
+       negate!, scalar_add!, scalar_sub!, mod_elements!, change_modulus, change_modulus_no_alloc!, mulN!, stripe_mul!,
+       mat_mul_gpu_type, mat_mul_type_inplace!, pluq_gpu_kernel, pluq, lu, rref, rank, inverse, is_invertible, is_invertible_with_inverse,
+       upper_triangular_inverse_no_copy, lower_triangular_inverse_no_copy, forward_sub_gpu_type_32, backward_sub_gpu_type_32,
+       apply_col_perm!, apply_col_inv_perm!, apply_row_perm!, apply_row_inv_perm!, perm_array_to_matrix, mod_inv,
+       KaratsubaArray, KaratsubaMatrix, KaratsubaVector, KaratsubaZeros, MatToKMat, KMatMul!, KMatMul_gemv!, initialize_plan!, scalar_multiply!,
+       CuModArraySizeMismatchException, CuModArrayModulusMismatchException, CuModMatrixTooLargeException, CuModMatrixNotSquareException,
+       CuModMatrixModulusNotPrimeException, InverseOverflowError, InverseNotDefinedException, MatrixNotInvertibleException
+
+end # module

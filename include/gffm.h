@@ -93,7 +93,10 @@ int32_t gffm_destroy(gffm_ctx* ctx);
 int32_t gffm_sync(gffm_ctx* ctx);                         /* CUDA.synchronize / CUDA.@sync */
 int32_t gffm_set_stream(gffm_ctx* ctx, void* cuda_stream); /* adopt an external cudaStream_t (e.g. torch's) */
 int32_t gffm_get_stream(gffm_ctx* ctx, void** cuda_stream);
-/* CUDA-event timings (ms) of the phases of the last gemm/pluq/inverse call; returns how many were written */
+/* phase profiling: when on, gemm calls record CUDA events around their phases on the context stream */
+int32_t gffm_set_profiling(gffm_ctx* ctx, int32_t on);
+/* CUDA-event timings (ms) of the phases of the last profiled gemm call -- RNS: {plane split, tcgen05 GEMM kernel, CRT
+ * kernel}; LIMB: {plane split, tcgen05 GEMM kernel}.  Blocks until the events have completed. */
 int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t capacity, int32_t* n_written);
 /* number of library kernels launched on this context since creation (bench.py's gpu_launches) */
 int32_t gffm_launch_count(gffm_ctx* ctx, int64_t* count);

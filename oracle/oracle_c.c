@@ -1,0 +1,126 @@
+/* oracle_c.c -- C restatement of the reference's CPU ground truth for the hot path.  TEST INFRASTRUCTURE ONLY:
+ * used by tests/ as a second, faster checker and by bench.py as the `cpu_baseline` / `--impl reference` arm.  Never
+ * linked into or called by the product (gpufinitefieldmatrices.jl_b200/).
+ *
+ * The reference's tests compute their expected values with plain host integers, `mod.(A*B, N)` on Matrix{Int}
+ * (/root/reference/test/CuModMatrix/stripe_mul_test.jl:11,26,48; matmul_operations_test.jl:65,107); Julia is not
+ * available in this image, so that computation is restated here: exact uint64 accumulation with a reduction every
+ * `chunk` terms so that no partial sum can overflow, pthreads over row blocks (all host cores).
+ * The elimination follows /root/reference/src/CuModMatrix/rref_lu_pluq/pluq_kernels.jl:46-157 (pivot = maximum
+ * residue, first index; pivot row scaled to 1; L keeps the pivot and the un-normalised sub-column) in its
+ * well-defined echelon form (see oracle.py:echelon).
+ * Parity status: pinned against oracle.py (which is pinned against the reference's literal fixtures) in
+ * tests/test_oracle_golden.py::test_c_oracle_matches_numpy_oracle.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* libgomp is not installed in this image, so the row-block parallelism uses plain pthreads */
+static int g_threads = 0;
+int oracle_num_threads(void) {
+  if (g_threads <= 0) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    g_threads = n < 1 ? 1 : (n > 256 ? 256 : (int)n);
+  }
+  return g_threads;
+}
+void oracle_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+
+typedef struct {
+  const uint32_t *A, *B;
+  uint32_t* C;
+  int64_t lda, ldb, ldc, m, k, n, chunk;
+  uint64_t N;
+  volatile int64_t* next;
+} mm_job;
+
+static void* mm_worker(void* arg) {
+  mm_job* J = (mm_job*)arg;
+  const int64_t IB = 64;
+  uint64_t acc[64];
+  for (;;) {
+    const int64_t i0 = __sync_fetch_and_add(J->next, IB);
+    if (i0 >= J->m) break;
+    const int64_t ib = (J->m - i0) < IB ? (J->m - i0) : IB;
+    for (int64_t j = 0; j < J->n; ++j) {
+      for (int64_t i = 0; i < ib; ++i) acc[i] = 0;
+      for (int64_t k0 = 0; k0 < J->k; k0 += J->chunk) {
+        const int64_t k1 = (k0 + J->chunk < J->k) ? k0 + J->chunk : J->k;
+        for (int64_t kk = k0; kk < k1; ++kk) {
+          const uint64_t b = J->B[j * J->ldb + kk];
+          const uint32_t* a = J->A + kk * J->lda + i0;
+          for (int64_t i = 0; i < ib; ++i) acc[i] += (uint64_t)a[i] * b;
+        }
+        for (int64_t i = 0; i < ib; ++i) acc[i] %= J->N;
+      }
+      for (int64_t i = 0; i < ib; ++i) J->C[j * J->ldc + i0 + i] = (uint32_t)acc[i];
+    }
+  }
+  return NULL;
+}
+
+/* C = A*B mod N; column-major, A m x k (lda), B k x n (ldb), C m x n (ldc); entries < 2^32, N < 2^32 */
+void oracle_matmul_mod(const uint32_t* A, int64_t lda, const uint32_t* B, int64_t ldb, uint32_t* C, int64_t ldc, int64_t m,
+                       int64_t k, int64_t n, uint64_t N, uint64_t in_bound) {
+  /* terms are < in_bound^2; keep partial sums below 2^63 */
+  uint64_t R = in_bound ? in_bound : N;
+  long double r2 = (long double)(R - 1) * (long double)(R - 1);
+  int64_t chunk = r2 < 1 ? k : (int64_t)(9.0e18L / r2);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 4096) chunk = 4096;
+  volatile int64_t next = 0;
+  mm_job job = {A, B, C, lda, ldb, ldc, m, k, n, chunk, N, &next};
+  const int nt = oracle_num_threads();
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nt);
+  for (int t = 1; t < nt; ++t) pthread_create(&th[t], NULL, mm_worker, &job);
+  mm_worker(&job);
+  for (int t = 1; t < nt; ++t) pthread_join(th[t], NULL);
+  free(th);
+}
+
+static uint64_t mod_inv_u64(uint64_t p, uint64_t P) { /* pluq_kernels.jl:11-31 */
+  int64_t inv = 0, new_inv = 1, rem = (int64_t)P, new_rem = (int64_t)(p % P);
+  while (new_rem != 0) {
+    int64_t q = rem / new_rem, t = inv - q * new_inv;
+    inv = new_inv; new_inv = t;
+    t = rem - q * new_rem; rem = new_rem; new_rem = t;
+  }
+  if (inv < 0) inv += (int64_t)P;
+  return (uint64_t)inv;
+}
+
+/* Row echelon elimination in place (W m x n column-major, ld), L m x m (ldl, zero on entry).  Returns the rank;
+ * pivcol[t], swp[t] (0-based row exchanged with row t).  Same conventions as oracle.py:echelon. */
+int64_t oracle_echelon(uint32_t* W, int64_t ld, uint32_t* L, int64_t ldl, int64_t m, int64_t n, uint64_t N, int64_t* pivcol,
+                       int64_t* swp) {
+  int64_t row = 0;
+  for (int64_t col = 0; col < n && row < m; ++col) {
+    uint32_t best = 0; int64_t bi = -1;
+    for (int64_t i = row; i < m; ++i) { uint32_t v = W[col * ld + i]; if (v > best) { best = v; bi = i; } }
+    if (best == 0) continue;
+    const uint64_t pinv = mod_inv_u64(best, N);
+    /* swap rows row <-> bi over all columns of W and L; scale the pivot row */
+    for (int64_t c = 0; c < n; ++c) {
+      uint32_t t = W[c * ld + bi]; W[c * ld + bi] = W[c * ld + row]; W[c * ld + row] = (uint32_t)(((uint64_t)t * pinv) % N);
+    }
+    for (int64_t c = 0; c < m; ++c) { uint32_t t = L[c * ldl + bi]; L[c * ldl + bi] = L[c * ldl + row]; L[c * ldl + row] = t; }
+    L[row * ldl + row] = best;
+    for (int64_t i = row + 1; i < m; ++i) { L[row * ldl + i] = W[col * ld + i]; W[col * ld + i] = 0; }
+    for (int64_t c = col + 1; c < n; ++c) {
+      const uint64_t u = W[c * ld + row];
+      if (u == 0) continue;
+      uint32_t* wc = W + c * ld;
+      const uint32_t* lc = L + row * ldl;
+      for (int64_t i = row + 1; i < m; ++i) {
+        const uint64_t l = lc[i];
+        if (l) wc[i] = (uint32_t)(((uint64_t)wc[i] + N - (l * u) % N) % N);
+      }
+    }
+    pivcol[row] = col; swp[row] = bi;
+    ++row;
+  }
+  return row;
+}

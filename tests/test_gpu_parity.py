@@ -1,0 +1,409 @@
+"""GPU parity tests: every call goes through the C ABI (ctypes mirror == Julia shim) and is compared bit-for-bit
+with the CPU oracle on the same seeded inputs, with the reference's own literal fixtures, and -- at BASELINE sizes --
+through size-independent properties.  Run with `pytest -m gpu` on a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+
+FX = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.json")))
+
+
+@pytest.fixture(scope="module")
+def g():
+    import gffm_b200
+    gffm_b200.default_context()
+    return gffm_b200
+
+
+# ---------------------------------------------------------------- container ----------------------------------------------
+def test_ctor_padding_mod_and_errors(g):
+    A = np.array([[-3, 12], [5, 6], [7, -1]])
+    M = g.CuModMatrix(A, 7)
+    assert M.size() == (3, 2) and M.shape == (3, 2)
+    img = M.unsafe_Array(np.int64)
+    assert img.shape == (35, 34)  # +32 per dimension, CuModMatrix.jl:62
+    assert np.array_equal(img, O.construct(A, 7))
+    assert np.array_equal(M.Array(np.int64), np.mod(A, 7))
+    for dt in (np.float32, np.float64, np.int64, np.int32, np.uint32):
+        Mh = g.CuModMatrix(np.mod(A, 7).astype(dt), 7, elem_type=np.float64)
+        assert np.array_equal(Mh.to_int(), np.mod(A, 7))
+        assert Mh.Array().dtype == np.float64
+    with pytest.raises(g.InexactError):
+        g.CuModMatrix(np.array([[0.5, 1.0]]), 7)
+    with pytest.raises(g.CuModArrayModulusMismatchException):
+        g.CuModMatrix(np.array([[1]]), 2 ** 52 + 1)
+    # mod=false keeps the raw values, new_size pads/crops
+    assert np.array_equal(g.CuModMatrix(np.array([[9, 10]]), 7, mod=False).to_int(), [[9, 10]])
+    assert g.CuModMatrix(np.ones((2, 2)), 7, new_size=(4, 5)).size() == (4, 5)
+    v = g.CuModVector(np.array([1, 2, 15]), 11)
+    assert v.shape == (3,) and np.array_equal(v.to_int(), [1, 2, 4])
+    e = g.CuModMatrix(np.zeros((0, 5)), 7)
+    assert e.Array().shape == (0, 5)
+
+
+def test_basic_3x3_fixture(g):
+    f = FX["basic_3x3"]
+    A = g.CuModMatrix(np.array(f["A"]), f["N"]); B = g.CuModMatrix(np.array(f["B"]), f["N"]); s = f["scalar"]
+    assert np.array_equal((A + B).to_int(), f["add"])
+    assert np.array_equal((A - B).to_int(), f["sub"])
+    assert np.array_equal((A * B).to_int(), f["matmul"])
+    F = g.zeros(np.float32, 3, 3, f["N"]); g.elementwise_multiply_(F, A, B)
+    assert np.array_equal(F.to_int(), f["elementwise_multiply"])
+    assert np.array_equal((s + A).to_int(), f["scalar_add"])
+    assert np.array_equal((A - s).to_int(), f["scalar_sub"])
+    assert np.array_equal((s * A).to_int(), f["scalar_mul"])
+    assert np.array_equal((A * -1).to_int(), f["negate"])
+    assert np.array_equal((A ** 2).to_int(), f["pow2"])
+    assert np.array_equal((A ** 0).to_int(), f["pow0"])
+    assert A[0, 0] == 1 and A[2, 2] == 9
+
+
+def test_matmul_fixtures_and_override_modulus(g):
+    f = FX["matmul_2x3_3x2"]
+    A = g.CuModMatrix(np.array(f["A"]), f["N"]); B = g.CuModMatrix(np.array(f["B"]), f["N"])
+    assert np.array_equal((A * B).to_int(), f["C_mod11"])
+    assert np.array_equal(g.mat_mul_gpu_type(A, B).to_int(), f["C_mod11"])
+    assert np.array_equal(g.mat_mul_gpu_type(A, B, f["override_N"]).to_int(), f["C_mod7"])
+    h = FX["matmul_inplace"]
+    A = g.CuModMatrix(np.array(h["A"]), h["N"]); B = g.CuModMatrix(np.array(h["B"]), h["N"])
+    C = g.zeros(np.float32, 2, 2, h["N"]); g.mat_mul_type_inplace_(C, A, B)
+    assert np.array_equal(C.to_int(), h["C_mod9"])
+    C2 = g.zeros(np.float32, 2, 2, h["override_N"]); g.mat_mul_type_inplace_(C2, A, B, h["override_N"])
+    assert np.array_equal(C2.to_int(), h["C_mod3"])
+    # mul! checks: modulus mismatch before size mismatch (CuModMatrix.jl:769-783)
+    with pytest.raises(g.CuModArrayModulusMismatchException):
+        g.mul_(g.zeros(np.float32, 2, 2, 7), A, B)
+    with pytest.raises(g.CuModArraySizeMismatchException):
+        g.mul_(g.zeros(np.float32, 3, 2, h["N"]), A, B)
+
+
+def test_inplace_ops_and_modulus_override(g):
+    N = 11
+    rng = np.random.default_rng(3)
+    A = rng.integers(0, N, size=(37, 53)); B = rng.integers(0, N, size=(37, 53))
+    Ag, Bg = g.CuModMatrix(A, N), g.CuModMatrix(B, N)
+    C = g.zeros(np.float32, 37, 53, N)
+    assert np.array_equal(g.add_(C, Ag, Bg).to_int(), O.ew_add(A, B, N))
+    assert np.array_equal(g.sub_(C, Ag, Bg).to_int(), O.ew_sub(A, B, N))
+    assert np.array_equal(g.elementwise_multiply_(C, Ag, Bg).to_int(), O.ew_mul(A, B, N))
+    assert np.array_equal(g.negate_(C, Ag).to_int(), O.ew_negate(A, N))
+    assert np.array_equal(g.scalar_add_(C, Ag, 5).to_int(), O.ew_scalar_add(A, 5, N))
+    assert np.array_equal(g.scalar_sub_(C, Ag, 5).to_int(), O.ew_scalar_sub(A, 5, N))
+    assert np.array_equal(g.rscalar_sub_(C, Ag, 5).to_int(), O.ew_rscalar_sub(A, 5, N))
+    assert np.array_equal(g.mul_(C, Ag, 3).to_int(), O.ew_scalar_mul(A, 3, N))
+    assert np.array_equal((Ag / 3).to_int(), O.ew_scalar_div(A, 3, N))
+    # mod_N override on mismatched-modulus operands (inplace_operations_test.jl:125-191)
+    B13 = g.CuModMatrix(B, 13)
+    with pytest.raises(g.CuModArrayModulusMismatchException):
+        g.add_(C, Ag, B13)
+    assert np.array_equal(g.add_(C, Ag, B13, mod_N=5).to_int(), O.ew_add(A, B, 5))
+    # copy!, mod_elements!, fill!, zero!, change_modulus (inplace_operations_test.jl:216-255; basic :232-258)
+    D = g.zeros(np.float32, 37, 53, N); g.copy_(D, Ag)
+    assert D.equals(Ag)
+    f = FX["fill_122_mod_11"]
+    g.fill_(D, f["value"]); assert np.all(D.to_int() == f["expect"])
+    g.zero_(D); assert np.all(D.to_int() == 0)
+    E = g.change_modulus(Ag, 5)
+    assert E.N == 5 and np.array_equal(E.to_int(), np.mod(A, 5)) and Ag.N == N
+    g.change_modulus_no_alloc_(Ag, 3)
+    assert Ag.N == 3 and np.array_equal(Ag.to_int(), np.mod(A, 3))
+    assert np.array_equal(g.eye(np.float32, 5, N).to_int(), np.eye(5, dtype=np.int64))
+    R = g.rand(np.float32, 40, 30, N, seed=7)
+    assert R.to_int().max() < N and R.unsafe_Array(np.int64)[40:, :].sum() == 0  # padding stays zero (unlike CuModMatrix.jl:551-556)
+    assert np.array_equal(g.transpose(Bg).to_int(), B.T)
+    assert np.array_equal(g.synth(33, 17, 65521, 5).to_int(), O.synth_matrix(5, 33, 17, 65521))
+    big = g.CuModMatrix(rng.integers(0, 2 ** 31, size=(9, 9)), 4294967291)
+    assert np.array_equal((big + big).to_int(), O.ew_add(big.to_int(), big.to_int(), 4294967291))
+    assert np.array_equal(g.elementwise_multiply_(g.zeros(np.float64, 9, 9, 4294967291), big, big).to_int(), O.ew_mul(big.to_int(), big.to_int(), 4294967291))
+
+
+def test_permutation_fixture(g):
+    f = FX["permutation_3x3"]
+    P = [tuple(p) for p in f["P"]]
+    A = g.CuModMatrix(np.array(f["A"], dtype=np.float64), f["N"])
+    g.apply_col_perm_(P, A); assert np.array_equal(A.to_int(), f["col_perm"])
+    g.apply_col_inv_perm_(P, A); assert np.array_equal(A.to_int(), f["A"])
+    g.apply_row_perm_(P, A); assert np.array_equal(A.to_int(), f["row_perm"])
+    g.apply_row_inv_perm_(P, A); assert np.array_equal(A.to_int(), f["A"])
+    rng = np.random.default_rng(1)
+    X = rng.integers(0, 11, size=(20, 30))
+    Pl = [(int(a), int(b)) for a, b in rng.integers(1, 21, size=(15, 2))]
+    Xg = g.CuModMatrix(X, 11); g.apply_row_perm_(Pl, Xg)
+    assert np.array_equal(Xg.to_int(), O.apply_row_perm(Pl, X))
+    g.apply_row_inv_perm_(Pl, Xg); assert np.array_equal(Xg.to_int(), X)
+    assert np.array_equal(g.perm_array_to_matrix(Pl, 11, (20, 20), perm_stack=True).to_int(), O.perm_array_to_matrix(Pl, 20, True))
+    assert g.mod_inv(3, 7) == O.mod_inv(3, 7) == 5
+
+
+# ---------------------------------------------------------------- modular GEMM ----------------------------------------------
+CASES = [  # (m, k, n, N)
+    (1, 1, 1, 11), (3, 5, 2, 7), (100, 100, 100, 2 ** 11), (100, 100, 100, 11 ** 3), (129, 257, 255, 11), (300, 515, 700, 251),
+    (257, 1000, 129, 65521), (300, 500, 700, 33554393), (128, 4096, 64, 33554393), (513, 130, 1025, 2 ** 26), (64, 300, 64, 4294967291),
+]
+
+
+@pytest.mark.parametrize("m,k,n,N", CASES)
+def test_gemm_vs_oracle_all_algorithms(g, m, k, n, N):
+    A = O.synth_matrix(11, m, k, N); B = O.synth_matrix(12, k, n, N)
+    want = O.matmul_mod(A, B, N)
+    algos = [g.capi.ALGO_AUTO, g.capi.ALGO_SIMT]
+    if N <= 65536:
+        algos.append(g.capi.ALGO_LIMB)
+    if N <= 2 ** 31:
+        algos.append(g.capi.ALGO_RNS)
+    Ag, Bg = g.CuModMatrix(A, N), g.CuModMatrix(B, N)
+    C0 = O.synth_matrix(13, m, n, N)
+    for algo in algos:
+        C = g.zeros(np.float64, m, n, N)
+        g.mul_(C, Ag, Bg, algo=algo)
+        assert np.array_equal(C.to_int(), want), f"algo {algo}"
+        Cacc = g.CuModMatrix(C0, N); g.mul_(Cacc, Ag, Bg, algo=algo, mode=g.capi.GEMM_ADD)
+        assert np.array_equal(Cacc.to_int(), np.mod(C0 + want, N)), f"algo {algo} add"
+        Csub = g.CuModMatrix(C0, N); g.mul_(Csub, Ag, Bg, algo=algo, mode=g.capi.GEMM_SUB)
+        assert np.array_equal(Csub.to_int(), np.mod(C0 - want, N)), f"algo {algo} sub"
+
+
+@pytest.mark.parametrize("N,algo_name", [(11, "ALGO_LIMB"), (256, "ALGO_LIMB"), (65521, "ALGO_LIMB"), (65536, "ALGO_LIMB"), (33554393, "ALGO_RNS"), (2 ** 26, "ALGO_RNS")])
+def test_gemm_adversarial_all_max(g, N, algo_name):
+    """Exact accumulation budget: every entry N-1, K long enough to need more than one K chunk for L=2."""
+    m, k, n = 130, 20000, 140
+    A = np.full((m, k), N - 1, dtype=np.int64); B = np.full((k, n), N - 1, dtype=np.int64)
+    want = np.full((m, n), (k * (N - 1) * (N - 1)) % N, dtype=np.int64)
+    C = g.zeros(np.float64, m, n, N)
+    g.mul_(C, g.CuModMatrix(A, N), g.CuModMatrix(B, N), algo=getattr(g.capi, algo_name))
+    assert np.array_equal(C.to_int(), want)
+
+
+def test_stripe_mul_cases_from_reference(g):
+    for case in FX["stripe_cases"]["cases"]:
+        n, N = case["n"], case["N"]
+        rng = np.random.default_rng(n * 7 + N)
+        A = rng.integers(case["lo"], case["hi"] + 1, size=(n, n)); B = rng.integers(case["lo"], case["hi"] + 1, size=(n, n))
+        for (i, j, v, which) in case.get("poke", []):
+            (A if which == "A" else B)[i - 1, j - 1] = v
+        C = g.zeros(np.float32, n, n, N)
+        g.stripe_mul_(C, g.CuModMatrix(A, N), g.CuModMatrix(B, N))
+        assert np.array_equal(C.to_int(), O.exact_matmul_mod(A, B, N))
+
+
+def test_baseline_config1_1024_mod_11(g):
+    """BASELINE config 1: 1024x1024 * 1024x1024 mod 11 (seeds 1,2), bit-exact vs the integer oracle; the device-side
+    synthetic generator must agree with the oracle's."""
+    n, N = 1024, 11
+    A = O.synth_matrix(1, n, n, N); B = O.synth_matrix(2, n, n, N)
+    Ag = g.synth(n, n, N, 1); Bg = g.synth(n, n, N, 2)
+    assert np.array_equal(Ag.to_int(), A) and np.array_equal(Bg.to_int(), B)
+    assert np.array_equal((Ag * Bg).to_int(), O.matmul_mod(A, B, N))
+
+
+def test_gemv(g):
+    for (m, k, N) in [(100, 100, 11 ** 3), (500, 333, 33554393), (1, 7, 7), (130, 1, 11)]:
+        A = O.synth_matrix(21, m, k, N); x = O.synth_matrix(22, k, 1, N).reshape(-1)
+        z = g.zeros(np.float64, m, 1, N)
+        g.gemv_(z, g.CuModMatrix(A, N), g.CuModVector(x, N))
+        assert np.array_equal(z.to_int().reshape(-1), O.matvec_mod(A, x, N))
+        z2 = g.CuModMatrix(A, N) * g.CuModVector(x, N)  # mul!(z,A,x) through the GEMM entry
+        assert np.array_equal(z2.to_int().reshape(-1), O.matvec_mod(A, x, N))
+
+
+def _freivalds(g, A, B, C, N, seed=99):
+    """C == A*B (mod N) with probability >= 1 - 1/N per trial, using the independent GEMV kernel: A*(B*x) == C*x."""
+    n = B.cols
+    x = g.synth(n, 1, N, seed)
+    Bx = g.zeros(np.float64, B.rows, 1, N); g.gemv_(Bx, B, x)
+    ABx = g.zeros(np.float64, A.rows, 1, N); g.gemv_(ABx, A, Bx)
+    Cx = g.zeros(np.float64, C.rows, 1, N); g.gemv_(Cx, C, x)
+    return ABx.equals(Cx)
+
+
+@pytest.mark.parametrize("n,N", [(8192, 33554393), (8192, 7), (16384, 65521), (16384, 33554393)])
+def test_gemm_full_size_properties(g, n, N):
+    """BASELINE sizes (configs 2 and the n=16384 metric): Freivalds check with the SIMT GEMV, linearity
+    (A*(B+B') == A*B + A*B'), and all-(N-1) adversarial input with its closed-form answer."""
+    A = g.synth(n, n, N, 5); B = g.synth(n, n, N, 6)
+    C = g.zeros(np.float32, n, n, N); g.mul_(C, A, B)
+    for s in (1, 2, 3):
+        assert _freivalds(g, A, B, C, N, seed=100 + s)
+    B2 = g.synth(n, n, N, 16); Bs = B + B2
+    Cs = g.zeros(np.float32, n, n, N); g.mul_(Cs, A, Bs)
+    g.mul_(C, A, B2, mode=g.capi.GEMM_ADD)
+    assert C.equals(Cs)
+    g.fill_(A, N - 1); g.fill_(B, N - 1); g.mul_(C, A, B)
+    want = (n * (N - 1) * (N - 1)) % N
+    ref = g.zeros(np.float32, n, n, N); g.fill_(ref, want)
+    assert C.equals(ref)
+
+
+# ---------------------------------------------------------------- elimination ----------------------------------------------
+def _check_pluq_invariant(g, Ag, U, L, pr, pc):
+    PA = g.copy(Ag); g.apply_row_perm_(pr, PA); g.apply_col_perm_(pc, PA)
+    return (L * U).equals(PA) if L.cols == U.rows else None
+
+
+@pytest.mark.parametrize("m,n,N,seed", [(1, 1, 7, 1), (10, 10, 7, 1), (33, 33, 2, 2), (100, 100, 65521, 3), (257, 257, 33554393, 4), (300, 200, 65521, 5),
+                                        (200, 300, 11, 6), (1000, 1000, 13, 7), (700, 700, 4294967291, 8)])
+def test_pluq_lu_rref_inverse_vs_oracle(g, m, n, N, seed):
+    A = O.synth_matrix(seed, m, n, N)
+    if min(m, n) > 20 and seed in (5, 6, 7):
+        A[:, 3] = 0; A[:, 11] = (3 * A[:, 1] + A[:, 2]) % N; A[m // 2, :] = A[0, :]
+    Ag = g.CuModMatrix(A, N)
+    U, L, pr, pc, rk = g.pluq_gpu_kernel(Ag, return_rank=True)
+    Uo, Lo, pro, pco, rko = O.pluq(A, N)
+    assert rk == rko and pr == pro and pc == pco
+    assert np.array_equal(U.to_int(), Uo) and np.array_equal(L.to_int(), Lo)
+    assert _check_pluq_invariant(g, Ag, U, L, pr, pc)
+    E, L2, pr2, piv = g.lu(Ag, return_pivots=True)
+    Eo, Lo2, pro2, pivo = O.echelon(A, N)
+    assert np.array_equal(E.to_int(), Eo) and np.array_equal(L2.to_int(), Lo2) and pr2 == pro2 and piv == pivo
+    R, pivr = g.rref(Ag, return_pivots=True)
+    Ro, pivro = O.rref(A, N)
+    assert np.array_equal(R.to_int(), Ro) and pivr == pivro
+    assert g.rank(Ag) == rko
+    if m == n:
+        ok, inv = g.is_invertible_with_inverse(Ag)
+        oko, invo = O.is_invertible_with_inverse(A, N)
+        assert ok == oko == g.is_invertible(Ag)
+        if ok:
+            assert np.array_equal(inv.to_int(), invo)
+            assert (Ag * inv).equals(g.eye(np.float32, n, N))
+        else:
+            with pytest.raises(g.MatrixNotInvertibleException):
+                g.inverse(Ag)
+
+
+def test_pluq_matches_reference_loop_on_full_rank(g):
+    """For full-rank input no column swap occurs, so the blocked path must reproduce the reference's own loop
+    (pluq_kernels.jl:46-157, restated literally in oracle.pluq_reference) bit for bit."""
+    N = 65521
+    A = O.synth_matrix(31, 150, 150, N)
+    U, L, pr, pc = g.pluq_gpu_kernel(g.CuModMatrix(A, N))
+    Uo, Lo, pro, pco = O.pluq_reference(A, N)
+    assert pc == pco == [] and pr == pro
+    assert np.array_equal(U.to_int(), Uo) and np.array_equal(L.to_int(), Lo)
+
+
+def test_pluq_reference_quirk_mode(g):
+    """GFFM_PIVOT_REFERENCE_QUIRK replays the reference's rank-deficient behaviour literally."""
+    N = 7
+    rng = np.random.default_rng(5)
+    A = O.exact_matmul_mod(rng.integers(0, N, size=(30, 9)), rng.integers(0, N, size=(9, 40)), N)
+    A[:, 3] = 0
+    for M_ in (A, A[:, :30], O.synth_matrix(2, 25, 25, N)):
+        U, L, pr, pc = g.pluq_gpu_kernel(g.CuModMatrix(M_, N), col_pivot_mode=g.capi.PIVOT_REFERENCE_QUIRK)
+        Uo, Lo, pro, pco = O.pluq_reference(M_, N)
+        assert pr == pro and pc == pco
+        assert np.array_equal(U.to_int(), Uo) and np.array_equal(L.to_int(), Lo)
+
+
+def test_de_rham_known_answer(g):
+    f = FX["de_rham"]
+    A = g.CuModMatrix(np.array(f["A"]), f["N"])
+    flag, B = g.is_invertible_with_inverse(A)
+    assert flag is True
+    assert np.array_equal((A * B).to_int(), f["A_times_inverse"])
+
+
+def test_triangular_inverse(g):
+    f = FX["triangular_2x2"]
+    for upper, key in ((True, "upper"), (False, "lower")):
+        T = g.CuModMatrix(np.array(f[key], dtype=np.float64), f["N"])
+        Ti = g.upper_triangular_inverse_no_copy(T) if upper else g.lower_triangular_inverse_no_copy(T)
+        assert np.array_equal((T * Ti).to_int(), np.eye(2))
+    I = g.CuModMatrix(np.eye(1000), 2)
+    assert np.array_equal((I * g.upper_triangular_inverse_no_copy(I)).to_int(), np.eye(1000))
+    rng = np.random.default_rng(4)
+    for p in (3, 13, 97):          # triangular_test.jl:82-88 sweep (subset)
+        for n in (33, 47, 64, 65):
+            T = np.tril(rng.integers(1, p, size=(n, n)))
+            Ti = g.lower_triangular_inverse_no_copy(g.CuModMatrix(T, p))
+            assert np.array_equal(Ti.to_int(), O.lower_triangular_inverse(T, p))
+    T = np.triu(rng.integers(1, 13, size=(1000, 1000)))
+    Tg = g.CuModMatrix(T, 13)
+    assert (Tg * g.upper_triangular_inverse_no_copy(Tg)).equals(g.eye(np.float32, 1000, 13))
+    Tw = np.triu(rng.integers(1, 13, size=(200, 500)))   # wide upper: [T^-1; 0] (triangular_test.jl:43-45)
+    Twg = g.CuModMatrix(Tw, 13)
+    Ti = g.upper_triangular_inverse_no_copy(Twg)
+    assert Ti.size() == (500, 200) and np.array_equal(Ti.to_int(), O.upper_triangular_inverse(Tw, 13))
+    assert np.array_equal((Twg * Ti).to_int(), np.eye(200))
+    with pytest.raises(g.InverseNotDefinedException):
+        g.lower_triangular_inverse_no_copy(g.CuModMatrix(np.ones((5, 3)), 13))
+    with pytest.raises(g.MatrixNotInvertibleException):
+        g.lower_triangular_inverse_no_copy(g.CuModMatrix(np.array([[1, 0], [1, 0]]), 13))
+
+
+def test_baseline_config4_lu_inverse_8192_mod_7(g):
+    """BASELINE config 4: A = Pi*(Lo*Up) mod 7, n = 8192; properties A*A^-1 == I and P*A == L*U."""
+    n, N = 8192, 7
+    lo = O.synth_matrix(9, n, n, N); up = O.synth_matrix(10, n, n, N)
+    Lo = np.tril(lo, -1) + np.eye(n, dtype=np.int64)
+    Up = np.triu(up, 1) + np.diag(1 + (np.diag(up) % 6))
+    Ag = g.CuModMatrix(Lo, N) * g.CuModMatrix(Up, N)
+    rot = [(i + 1, ((i + 4097) % n) + 1) for i in range(0, 64)]
+    g.apply_row_perm_(rot, Ag)
+    ok, inv = g.is_invertible_with_inverse(Ag)
+    assert ok and (Ag * inv).equals(g.eye(np.float32, n, N))
+    U, L, pr, pc, rk = g.pluq_gpu_kernel(Ag, return_rank=True)
+    assert rk == n and pc == [] and _check_pluq_invariant(g, Ag, U, L, pr, pc)
+
+
+def test_baseline_config3_rref_pluq_16384_rank_deficient(g):
+    """BASELINE config 3: 16384^2 rank-deficient mod 65521; rank, P*A*Q == L*U, echelon shape, RREF idempotence."""
+    n, N, r = 16384, 65521, 15360
+    X = g.synth(n, r, N, 7); Y = g.synth(r, n, N, 8)
+    Ag = X * Y
+    z = g.zeros(np.float32, n, 1, N)
+    for c in (100, 5000, 16383):
+        g.capi.check(Ag.lib.gffm_mat_copy_block(Ag.h, 0, c, z.h, 0, 0, n, 1))
+    c17 = g.zeros(np.float32, n, 1, N); c42 = g.zeros(np.float32, n, 1, N)
+    g.capi.check(Ag.lib.gffm_mat_copy_block(c17.h, 0, 0, Ag.h, 0, 17, n, 1))
+    g.capi.check(Ag.lib.gffm_mat_copy_block(c42.h, 0, 0, Ag.h, 0, 4242, n, 1))
+    comb = c17 * 3 + c42
+    g.capi.check(Ag.lib.gffm_mat_copy_block(Ag.h, 0, 9000, comb.h, 0, 0, n, 1))
+    U, L, pr, pc, rk = g.pluq_gpu_kernel(Ag, return_rank=True)
+    assert rk <= r and rk >= r - 4
+    assert _check_pluq_invariant(g, Ag, U, L, pr, pc)
+    R, piv = g.rref(Ag, return_pivots=True)
+    assert len(piv) == rk and 100 not in piv and 5000 not in piv and 9000 not in piv
+    R2, piv2 = g.rref(R, return_pivots=True)
+    assert piv2 == piv and R2.equals(R)
+
+
+# ---------------------------------------------------------------- Karatsuba ----------------------------------------------
+@pytest.mark.parametrize("n,cols,N1,N2", [(500, 1, 13 ** 4, 13 ** 3), (500, 500, 13 ** 4, 13 ** 3), (300, 200, 8191, 8191), (200, 64, 11, 11), (130, 130, 2 ** 26, 2 ** 26)])
+def test_karatsuba_matmul(g, n, cols, N1, N2):
+    """test/KaratsubaMatrix/basic_operations_test.jl:75-133 (mat x vec, N1=13^4, N2=13^3, n=500) plus mat x mat."""
+    rng = np.random.default_rng(n + cols)
+    A1 = rng.integers(0, N1, size=(n, n)); A2 = rng.integers(0, N2, size=(n, n))
+    B1 = rng.integers(0, N1, size=(n, cols)); B2 = rng.integers(0, N2, size=(n, cols))
+    AK = g.KaratsubaMatrix(g.CuModMatrix(A1, N1, elem_type=np.float64), g.CuModMatrix(A2, N1, elem_type=np.float64), N1, N2, N1 * N2)
+    BK = g.KaratsubaMatrix(g.CuModMatrix(B1, N1, elem_type=np.float64), g.CuModMatrix(B2, N1, elem_type=np.float64), N1, N2, N1 * N2)
+    CK = g.KaratsubaZeros(np.float64, n, cols, N1, N2)
+    for K in (AK, BK, CK):
+        g.initialize_plan_(K)
+    g.KMatMul_(CK, AK, BK)
+    full = (O.karatsuba_join(A1, A2, N1) @ O.karatsuba_join(B1, B2, N1)) % (N1 * N2)
+    assert np.array_equal(CK.Array(), full)
+    if N1 <= 2 ** 20 and n <= 300:
+        C1, C2 = O.karatsuba_matmul(A1, A2, B1, B2, N1, N2)  # the reference's own kernels, restated
+        assert np.array_equal(CK.data1.to_int(), C1) and np.array_equal(CK.data2.to_int(), C2)
+
+
+def test_karatsuba_elementwise_and_split(g):
+    N1, N2 = 13 ** 4, 13 ** 3
+    M = N1 * N2
+    rng = np.random.default_rng(8)
+    A = rng.integers(0, M, size=(40, 30)); B = rng.integers(0, M, size=(40, 30))
+    AK = g.MatToKMat(A, N1, N2); BK = g.MatToKMat(B, N1, N2)
+    assert np.array_equal(AK.Array(), A)
+    CK = g.KaratsubaZeros(np.float64, 40, 30, N1, N2)
+    K = g.karatsuba
+    assert np.array_equal(K.add_(CK, AK, BK).Array(), (A.astype(object) + B) % M)
+    assert np.array_equal(K.sub_(CK, AK, BK).Array(), (A.astype(object) - B) % M)
+    assert np.array_equal(K.scalar_multiply_(CK, AK, 97).Array(), (A.astype(object) * 97) % M)
+    assert np.array_equal(K.negate_(CK, AK).Array(), (-A.astype(object)) % M)

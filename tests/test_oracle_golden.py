@@ -209,3 +209,15 @@ def test_karatsuba_reference_kernels_equal_direct():
     full = O.karatsuba_join(A1, A2, N1)
     s1, s2 = O.karatsuba_split(full, N1, N2)
     assert np.array_equal(s1, A1) and np.array_equal(s2, A2)
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle import oracle_c as OC
+    for (m, k, n, N) in [(33, 70, 21, 11), (100, 129, 64, 65521), (64, 200, 48, 33554393), (17, 40, 9, 4294967291)]:
+        A = O.synth_matrix(3, m, k, N); B = O.synth_matrix(4, k, n, N)
+        assert np.array_equal(OC.matmul_mod(A, B, N), O.exact_matmul_mod(A, B, N))
+    for (m, n, N) in [(20, 20, 7), (40, 25, 65521), (25, 40, 11)]:
+        A = O.synth_matrix(5, m, n, N); A[:, 3] = 0
+        E, L, pr, piv = OC.echelon(A, N)
+        Eo, Lo, pro, pivo = O.echelon(A, N)
+        assert np.array_equal(E, Eo) and np.array_equal(L, Lo) and pr == pro and piv == pivo
