@@ -71,6 +71,8 @@ extern "C" int32_t gffm_destroy(gffm_ctx* ctx) {
   ws_free(&ctx->ws_eplanes);
   ws_free(&ctx->ws_misc);
   ws_free(&ctx->ws_misc2);
+  ws_free(&ctx->ws_invtab);
+  ws_free(&ctx->ws_scratch);
   if (ctx->ws_pinned.ptr) cudaFreeHost(ctx->ws_pinned.ptr);
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -107,6 +109,10 @@ extern "C" int32_t gffm_set_profiling(gffm_ctx* ctx, int32_t on) {
 extern "C" int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t cap, int32_t* n) {
   if (!ctx) GFFM_FAIL(GFFM_ERR_INVALID, "null ctx");
   ctx->timings.clear();
+  if (ctx->n_ev == 0 && !ctx->elim_timings.empty()) {
+    ctx->timings = ctx->elim_timings;
+    ctx->elim_timings.clear();
+  }
   if (ctx->n_ev >= 2) {
     GFFM_CUDA(cudaEventSynchronize(ctx->ev[ctx->n_ev - 1]));
     for (int i = 0; i + 1 < ctx->n_ev; ++i) {
@@ -781,9 +787,10 @@ int32_t gffm_gemm_views(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t
   const int64_t m = A.rows, k = A.cols, n = B.cols;
   if (algo == GFFM_ALGO_AUTO) {
     const double work = (double)m * (double)n * (double)(k > 0 ? k : 1);
-    if (work < 128.0 * 128.0 * 128.0 || k < 16 || !gffm_tc_available(ctx)) algo = GFFM_ALGO_SIMT;
+    if (work < 2.0 * 128.0 * 128.0 * 128.0 || k < 16 || !gffm_tc_available(ctx)) algo = GFFM_ALGO_SIMT;
     else if (R <= 65536) algo = GFFM_ALGO_LIMB;
-    else algo = GFFM_ALGO_RNS;
+    else if (R < (1ull << 32)) algo = GFFM_ALGO_RNS;
+    else algo = GFFM_ALGO_SIMT;
   }
   switch (algo) {
     case GFFM_ALGO_SIMT: return gffm_gemm_simt(ctx, C, A, B, R, P, mode);

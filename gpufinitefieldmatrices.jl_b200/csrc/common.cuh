@@ -49,8 +49,10 @@ struct gffm_ctx {
   bool own_stream = false;
   int64_t launches = 0;
   // grow-only scratch buffers (stream-ordered reuse)
-  gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned;
+  gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned, ws_invtab, ws_scratch;
+  uint64_t inv_table_N = 0;
   std::vector<double> timings;
+  std::vector<double> elim_timings;  // {inner panels, U12 = L11^-1 A12, trailing GEMM} ms of the last profiled elimination
   bool profile = false;
   int n_ev = 0;  // events recorded by the last profiled call
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -131,6 +133,24 @@ __host__ __device__ inline uint64_t modinv_u64(uint64_t p, uint64_t P) {
   if (rem != 1) return 0;
   if (inv < 0) inv += (int64_t)P;
   return (uint64_t)inv;
+}
+// same algorithm on 32-bit remainders (hardware-friendly division); P < 2^32.  ~10x faster than the 64-bit form on
+// the GPU, where 64-bit integer division is emulated.
+__host__ __device__ inline uint32_t modinv_u32(uint32_t p, uint32_t P) {
+  uint32_t r0 = P, r1 = p % P;
+  long long t0 = 0, t1 = 1;
+  while (r1 != 0) {
+    const uint32_t q = r0 / r1;
+    const uint32_t r2 = r0 - q * r1;
+    const long long t2 = t0 - (long long)q * t1;
+    r0 = r1;
+    r1 = r2;
+    t0 = t1;
+    t1 = t2;
+  }
+  if (r0 != 1) return 0;
+  if (t0 < 0) t0 += (long long)P;
+  return (uint32_t)t0;
 }
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

@@ -35,7 +35,7 @@ struct RnsModDev {
   uint32_t m;    // modulus
   uint32_t mu;   // floor(2^32 / m)
   uint32_t off;  // multiple of m, >= 2^31 : makes the int32 accumulator non-negative
-  uint32_t pad;
+  uint32_t u;    // (M/m)^-1 mod m : CRT pre-scaling applied in the epilogue
 };
 
 struct GemmParams {
@@ -235,19 +235,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < S::NSLOT; ++s) tc::tmem_ld16(acc_base + s * S::BN + c0, v[s]);
         tc::tmem_ld_wait();
         if constexpr (S::EPI == EPI_POS) {
+          // fused C +/-= : all 16 old values are requested before any is used (16 loads in flight per thread)
+          uint32_t old[16];
+          uint32_t* dst0 = p.C + (int64_t)(col0 + c0) * p.ldc + row;
+          if (p.mode != GFFM_GEMM_STORE) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) old[c] = (row_ok && col0 + c0 + c < p.n) ? dst0[(int64_t)c * p.ldc] : 0u;
+          }
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            const int col = col0 + c0 + c;
             uint64_t acc = (uint64_t)v[0][c];
             if constexpr (S::NSLOT == 3) acc += ((uint64_t)v[1][c] << 8) + ((uint64_t)v[2][c] << 16);
             uint32_t r = (uint32_t)mod_u64(acc, p.modP);
-            if (row_ok && col < p.n) {
-              uint32_t* dst = p.C + (int64_t)col * p.ldc + row;
-              if (p.mode == GFFM_GEMM_ADD) r = addmod_u32(*dst, r, (uint32_t)p.modP.P);
-              else if (p.mode == GFFM_GEMM_SUB) r = submod_u32(*dst, r, (uint32_t)p.modP.P);
-              *dst = r;
-            }
+            if (p.mode == GFFM_GEMM_ADD) r = addmod_u32(old[c], r, (uint32_t)p.modP.P);
+            else if (p.mode == GFFM_GEMM_SUB) r = submod_u32(old[c], r, (uint32_t)p.modP.P);
+            old[c] = r;
           }
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (row_ok && col0 + c0 + c < p.n) dst0[(int64_t)c * p.ldc] = old[c];
         } else {
           const RnsModDev md = p.mods[z];
           uint8_t* eplane = p.E + (int64_t)z * p.e_plane_stride;
@@ -256,6 +262,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int col = col0 + c0 + c;
             const uint32_t u = v[0][c] + md.off;  // == acc (mod m), non-negative
             uint32_t e = u - __umulhi(u, md.mu) * md.m;
+            if (e >= md.m) e -= md.m;
+            e *= md.u;  // < 2^16
+            e -= __umulhi(e, md.mu) * md.m;
             if (e >= md.m) e -= md.m;
             if (row_ok && col < p.n) eplane[(int64_t)col * p.lde + row] = (uint8_t)e;
           }
@@ -285,8 +294,10 @@ struct SplitParams {
   int mode;             // 0 = positional limb p -> (x >> 8p) & 255 ; 1 = RNS residues
   uint32_t R;           // RNS: input bound (for balancing), 0 = unbalanced
   uint32_t half;        // RNS: values > half are shifted by -R
-  int is_b;             // RNS: multiply by u_t (B side)
-  uint32_t m[MAX_MODS], mu[MAX_MODS], u[MAX_MODS], Rm[MAX_MODS];
+  uint32_t m[MAX_MODS], mu[MAX_MODS];
+  uint32_t cneg[MAX_MODS];  // (-R) mod m
+  uint32_t h[MAX_MODS];     // (m+1)/2 : residues >= h are stored as r - m
+  uint32_t badj[MAX_MODS];  // 256 - m : low byte of (r - m) is r + 256 - m
 };
 
 __device__ __forceinline__ uint32_t small_mod(uint32_t a, uint32_t m, uint32_t mu) {
@@ -295,84 +306,113 @@ __device__ __forceinline__ uint32_t small_mod(uint32_t a, uint32_t m, uint32_t m
   return r;
 }
 
-__device__ __forceinline__ uint8_t encode_plane(uint32_t x, int pl, const SplitParams& sp) {
-  if (sp.mode == 0) return (uint8_t)((x >> (8 * pl)) & 255u);
+// one 8-bit digit of x for plane pl: positional byte, or balanced residue mod m_pl as two's-complement int8
+__device__ __forceinline__ uint32_t encode_plane(uint32_t x, bool neg, int pl, const SplitParams& sp) {
+  if (sp.mode == 0) return (x >> (8 * pl)) & 255u;
   const uint32_t m = sp.m[pl];
   uint32_t r = small_mod(x, m, sp.mu[pl]);
-  if (sp.R && x > sp.half) {  // x - R
-    const uint32_t Rm = sp.Rm[pl];
-    r = r >= Rm ? r - Rm : r + m - Rm;
+  if (neg) {  // x - R
+    r += sp.cneg[pl];
+    if (r >= m) r -= m;
   }
-  if (sp.is_b) r = small_mod(r * sp.u[pl], m, sp.mu[pl]);
-  // balance into [-floor(m/2), ceil(m/2)-1] and store as two's complement int8
-  if (r >= (m + 1) / 2) r -= m;
-  return (uint8_t)(r & 255u);
+  return (r >= sp.h[pl] ? r + sp.badj[pl] : r) & 255u;
 }
 
-// B operand (k x n column-major, K contiguous already): thread = 4 consecutive k of one column j.
+// B operand (k x n column-major, K contiguous already): thread = 4 consecutive k of one column j; a warp reads
+// 512 contiguous bytes and writes 128 contiguous bytes per plane.
 // Optional second source (Karatsuba prologue fusion, reference KaratsubaKernels.jl:129-139): x = src + src2.
-__global__ void split_b_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2,
-                               int K, int ncols, uint8_t* __restrict__ planes, int64_t Kp, int64_t rowsP,
-                               const __grid_constant__ SplitParams sp) {
+__global__ void __launch_bounds__(128)
+split_b_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2, int K, int ncols,
+               uint8_t* __restrict__ planes, int64_t Kp, int64_t rowsP, const __grid_constant__ SplitParams sp) {
   const int64_t k4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 k
   const int j = blockIdx.y;
   if (k4 * 4 >= Kp || j >= ncols) return;
   uint32_t x[4];
+  const uint32_t* col = src + (int64_t)j * ld + k4 * 4;
+  if (k4 * 4 + 3 < K && ((reinterpret_cast<uintptr_t>(col) & 15) == 0)) {
+    const uint4 v = *reinterpret_cast<const uint4*>(col);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  } else {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int64_t k = k4 * 4 + t;
-    x[t] = 0;
-    if (k < K) {
-      x[t] = src[(int64_t)j * ld + k];
-      if (src2) x[t] += src2[(int64_t)j * ld2 + k];
-    }
+    for (int t = 0; t < 4; ++t) x[t] = (k4 * 4 + t < K) ? col[t] : 0u;
   }
+  if (src2) {
+    const uint32_t* col2 = src2 + (int64_t)j * ld2 + k4 * 4;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (k4 * 4 + t < K) x[t] += col2[t];
+  }
+  bool neg[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) neg[t] = sp.R && x[t] > sp.half;
+  uint8_t* out = planes + (int64_t)j * Kp + k4 * 4;
   for (int pl = 0; pl < sp.nplanes; ++pl) {
     uint32_t w = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) w |= (uint32_t)encode_plane(x[t], pl, sp) << (8 * t);
-    *reinterpret_cast<uint32_t*>(planes + ((int64_t)pl * rowsP + j) * Kp + k4 * 4) = w;
+    for (int t = 0; t < 4; ++t) w |= encode_plane(x[t], neg[t], pl, sp) << (8 * t);
+    *reinterpret_cast<uint32_t*>(out + (int64_t)pl * rowsP * Kp) = w;
   }
 }
 
-// A operand (m x k column-major, M contiguous): 32(i) x 128(k) tile transposed through shared memory.
+// A operand (m x k column-major, M contiguous): 32(i) x 128(k) tile.  Each thread loads 16 elements of one row
+// (coalesced over the warp's 32 rows, 16 loads in flight), encodes them, and the BYTES are transposed through a
+// conflict-free shared tile (row pitch 132 B) so that every warp stores 128 contiguous bytes per plane row.
+constexpr int SPLIT_A_PITCH = 132;
+constexpr int SPLIT_A_GROUP = 4;  // planes per shared-memory pass
+
 __global__ void __launch_bounds__(256)
 split_a_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2, int M, int K,
                uint8_t* __restrict__ planes, int64_t Kp, int64_t rowsP, const __grid_constant__ SplitParams sp) {
-  __shared__ uint32_t tile[128][33];
+  __shared__ __align__(16) uint8_t tile[SPLIT_A_GROUP][32 * SPLIT_A_PITCH];
   const int i0 = blockIdx.x * 32;
   const int k0 = blockIdx.y * 128;
   const int lane = threadIdx.x & 31;
-  const int w = threadIdx.x >> 5;  // 8 warps
-  for (int kk = w; kk < 128; kk += 8) {
-    const int k = k0 + kk, i = i0 + lane;
-    uint32_t x = 0;
-    if (k < K && i < M) {
-      x = src[(int64_t)k * ld + i];
-      if (src2) x += src2[(int64_t)k * ld2 + i];
-    }
-    tile[kk][lane] = x;
-  }
-  __syncthreads();
-  const int i = threadIdx.x >> 3;   // 0..31
-  const int kg = threadIdx.x & 7;   // 16-byte group along k
-  if (i0 + i >= M) return;
+  const int w = threadIdx.x >> 5;  // 8 warps; this thread owns k = k0 + w + 8t of row i0 + lane
   uint32_t x[16];
+  const int i = i0 + lane;
 #pragma unroll
-  for (int t = 0; t < 16; ++t) x[t] = tile[kg * 16 + t][i];
-  for (int pl = 0; pl < sp.nplanes; ++pl) {
-    uint32_t wv[4] = {0, 0, 0, 0};
+  for (int t = 0; t < 16; ++t) {
+    const int k = k0 + w + 8 * t;
+    x[t] = (k < K && i < M) ? src[(int64_t)k * ld + i] : 0u;
+  }
+  if (src2) {
 #pragma unroll
-    for (int t = 0; t < 16; ++t) wv[t >> 2] |= (uint32_t)encode_plane(x[t], pl, sp) << (8 * (t & 3));
-    *reinterpret_cast<uint4*>(planes + ((int64_t)pl * rowsP + (i0 + i)) * Kp + k0 + kg * 16) =
-        make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    for (int t = 0; t < 16; ++t) {
+      const int k = k0 + w + 8 * t;
+      if (k < K && i < M) x[t] += src2[(int64_t)k * ld2 + i];
+    }
+  }
+  uint32_t negmask = 0;
+  if (sp.R) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) negmask |= (x[t] > sp.half ? 1u : 0u) << t;
+  }
+  for (int p0 = 0; p0 < sp.nplanes; p0 += SPLIT_A_GROUP) {
+    const int np = min(SPLIT_A_GROUP, sp.nplanes - p0);
+    for (int q = 0; q < np; ++q) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        tile[q][lane * SPLIT_A_PITCH + w + 8 * t] = (uint8_t)encode_plane(x[t], (negmask >> t) & 1u, p0 + q, sp);
+    }
+    __syncthreads();
+    // write-out: np planes x 32 rows x 32 words; a warp stores one 128-byte row segment per instruction
+    for (int idx = threadIdx.x; idx < np * 1024; idx += 256) {
+      const int q = idx >> 10, row = (idx >> 5) & 31, wc = idx & 31;
+      if (i0 + row < M) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(&tile[q][row * SPLIT_A_PITCH + wc * 4]);
+        *reinterpret_cast<uint32_t*>(planes + ((int64_t)(p0 + q) * rowsP + (i0 + row)) * Kp + k0 + wc * 4) = v;
+      }
+    }
+    __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// CRT epilogue kernel (RNS): e_t = (x * u_t^-1-scaled) mod m_t planes -> x mod P, fused C +/-= and the Karatsuba
+// CRT epilogue kernel (RNS): planes e_t = (x * (M/m_t)^-1) mod m_t  ->  x mod P, fused C +/-= and the Karatsuba
 // carry split (reference KaratsubaKernels.jl:141-158: C1 = cc mod N1, carry = cc div N1).
 //   x = S - round(S/M) * M,  S = sum_t e_t * (M/m_t);   frac(S/M) tracked in 2^-56 fixed point.
+// HBM-bound: each thread handles 4 consecutive rows (one 32-bit load per plane, all planes in flight, one 128-bit
+// store), a warp moves 128 B per plane and 512 B of C per instruction.
 // ---------------------------------------------------------------------------------------------------
 struct CrtParams {
   int s;
@@ -388,31 +428,63 @@ struct CrtParams {
 __global__ void __launch_bounds__(256)
 crt_kernel(const uint8_t* __restrict__ E, int64_t lde, int64_t plane_stride, int m, int n, uint32_t* __restrict__ C,
            int64_t ldc, uint32_t* __restrict__ hi, int64_t ldhi, const __grid_constant__ CrtParams cp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int j = blockIdx.y;
-  if (i >= m || j >= n) return;
-  const uint8_t* e = E + (int64_t)j * lde + i;
-  uint64_t acc = 0, F = 0;
-#pragma unroll 1
-  for (int t = 0; t < cp.s; ++t) {
-    const uint64_t et = e[(int64_t)t * plane_stride];
-    acc += et * cp.w[t];
-    F += et * cp.f[t];
+  if (i4 >= m || j >= n) return;
+  const uint8_t* e = E + (int64_t)j * lde + i4;  // lde is a multiple of 128 and i4 of 4: aligned 32-bit loads
+  uint32_t ew[MAX_MODS];
+#pragma unroll
+  for (int t = 0; t < MAX_MODS; ++t) ew[t] = (t < cp.s) ? *reinterpret_cast<const uint32_t*>(e + (int64_t)t * plane_stride) : 0u;
+  uint64_t acc[4] = {0, 0, 0, 0}, F[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int t = 0; t < MAX_MODS; ++t) {
+    if (t < cp.s) {
+      const uint64_t wt = cp.w[t], ft = cp.f[t];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint64_t et = (ew[t] >> (8 * q)) & 255u;
+        acc[q] += et * wt;
+        F[q] += et * ft;
+      }
+    }
   }
-  const uint64_t qq = cp.balanced ? ((F + (1ull << 55) + (1ull << 12)) >> 56) : ((F + (1ull << 12)) >> 56);
-  const uint64_t t1 = mod_u64(acc, cp.modP);
-  const uint64_t t2 = mod_u64(qq * cp.W, cp.modP);
-  uint64_t r = t1 >= t2 ? t1 - t2 : t1 + cp.modP.P - t2;
-  uint32_t* dst = C + (int64_t)j * ldc + i;
-  if (cp.kara_N1) {
-    hi[(int64_t)j * ldhi + i] = (uint32_t)(r / cp.kara_N1);
-    *dst = (uint32_t)(r % cp.kara_N1);
-    return;
+  uint32_t r32[4];
+  uint32_t* dst = C + (int64_t)j * ldc + i4;
+  const int nv = min(4, m - i4);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint64_t qq = cp.balanced ? ((F[q] + (1ull << 55) + (1ull << 12)) >> 56) : ((F[q] + (1ull << 12)) >> 56);
+    const uint64_t t1 = mod_u64(acc[q], cp.modP);
+    const uint64_t t2 = mod_u64(qq * cp.W, cp.modP);
+    const uint64_t r = t1 >= t2 ? t1 - t2 : t1 + cp.modP.P - t2;
+    if (cp.kara_N1) {
+      if (q < nv) hi[(int64_t)j * ldhi + i4 + q] = (uint32_t)(r / cp.kara_N1);
+      r32[q] = (uint32_t)(r % cp.kara_N1);
+    } else {
+      r32[q] = (uint32_t)r;
+    }
   }
-  uint32_t r32 = (uint32_t)r;
-  if (cp.mode == GFFM_GEMM_ADD) r32 = addmod_u32(*dst, r32, (uint32_t)cp.modP.P);
-  else if (cp.mode == GFFM_GEMM_SUB) r32 = submod_u32(*dst, r32, (uint32_t)cp.modP.P);
-  *dst = r32;
+  const bool vec = nv == 4 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  if (!cp.kara_N1 && cp.mode != GFFM_GEMM_STORE) {
+    uint32_t old[4];
+    if (vec) {
+      const uint4 o = *reinterpret_cast<const uint4*>(dst);
+      old[0] = o.x; old[1] = o.y; old[2] = o.z; old[3] = o.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) old[q] = q < nv ? dst[q] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      r32[q] = cp.mode == GFFM_GEMM_ADD ? addmod_u32(old[q], r32[q], (uint32_t)cp.modP.P) : submod_u32(old[q], r32[q], (uint32_t)cp.modP.P);
+  }
+  if (vec) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(r32[0], r32[1], r32[2], r32[3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < nv) dst[q] = r32[q];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -572,7 +644,7 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
                             uint64_t P, int mode, bool balanced, uint32_t* kara_hi, int64_t ldhi, uint64_t kara_N1) {
   const int64_t m = A.rows, K = A.cols, n = B.cols;
   if (m == 0 || n == 0) return GFFM_OK;
-  if (R == 0 || R > (1ull << 31) || P == 0 || P > (1ull << 52)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "RNS GEMM needs R <= 2^31, P <= 2^52");
+  if (R == 0 || R >= (1ull << 32) || P == 0 || P > (1ull << 52)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "RNS GEMM needs R < 2^32, P <= 2^52");
   if (!kara_hi && P >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "uint32 output needs P < 2^32");
   if (K == 0) {
     if (mode == GFFM_GEMM_STORE && !kara_hi) return gffm_fill_view(ctx, Cv, 0);
@@ -627,16 +699,17 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
       const uint64_t ut = modinv_u64(others_mod_mt, mt);
       spa.m[t] = mt;
       spa.mu[t] = (uint32_t)((1ull << 32) / mt);
-      spa.u[t] = (uint32_t)ut;
-      spa.Rm[t] = (uint32_t)(R % mt);
+      spa.cneg[t] = (uint32_t)((mt - (R % mt)) % mt);
+      spa.h[t] = (mt + 1) / 2;
+      spa.badj[t] = 256 - mt;
+      p.mods[t].u = (uint32_t)ut;
       cp.w[t] = (uint64_t)others_mod_P;
       cp.f[t] = (1ull << 56) / mt;
       p.mods[t].m = mt;
       p.mods[t].mu = (uint32_t)((1ull << 32) / mt);
       p.mods[t].off = (uint32_t)(((1ull << 31) + mt - 1) / mt * mt);
     }
-    SplitParams spb = spa;
-    spb.is_b = 1;
+    const SplitParams& spb = spa;
     uint8_t* pa = (uint8_t*)ctx->ws_planes_a.ptr;
     uint8_t* pb = (uint8_t*)ctx->ws_planes_b.ptr;
     prof_mark(ctx, 0);
@@ -657,7 +730,7 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     p.e_plane_stride = e_plane;
     GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p));
     prof_mark(ctx, 2);
-    dim3 grid((unsigned)ceil_div(m, 256), (unsigned)n);
+    dim3 grid((unsigned)ceil_div(m, 1024), (unsigned)n);
     crt_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, (int)m, (int)n, Cv.p, Cv.ld,
                                               kara_hi, ldhi, cp);
     GFFM_LAUNCH_CHECK(ctx);

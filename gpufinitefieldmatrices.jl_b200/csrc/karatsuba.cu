@@ -215,7 +215,7 @@ pluq_quirk_kernel(uint32_t* __restrict__ W, int64_t ldw, uint32_t* __restrict__ 
       __syncthreads();
       continue;
     }
-    const uint32_t pinv = (uint32_t)modinv_u64(pv, P);
+    const uint32_t pinv = modinv_u32(pv, P);
     // swap_rows_and_mod over all columns
     for (int c = tid; c < cols; c += 1024) {
       const uint32_t tmp = W[(int64_t)c * ldw + prow_i];

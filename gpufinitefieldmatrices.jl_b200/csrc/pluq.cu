@@ -16,6 +16,7 @@
 // reference's swap-with-fixed-last-column quirk is not reproduced by the blocked path).
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -41,30 +42,50 @@ struct PluqBufs {
   int* swp;          // [t] row swapped with row t when pivot t was chosen
   int* g_dst;        // composed gather list of the last panel: W[g_dst[e]] <- old W[g_src[e]]
   int* g_src;
+  const uint32_t* inv_table;  // [x] = x^-1 mod N for N <= 2^20 (batched once per modulus), else nullptr
 };
 
 __device__ __forceinline__ bool better(uint32_t v, int i, uint32_t bv, int bi) { return v > bv || (v == bv && i < bi); }
 
 // ---------------------------------------------------------------------------------------------------
 // panel kernel: columns [j0, j0+w) of W, rows [r, m).  One cluster; CTA c owns rows rb + c*rows_c + [0,rows_c).
+// The panel stays in (distributed) shared memory for all w pivots; the L multipliers of a pivot are kept IN PLACE in
+// its own panel column (below the pivot) so that row swaps move them for free -- no global traffic inside the pivot
+// loop.  Per pivot: local argmax (warp shuffles) + the candidate's modular inverse (table lookup / 32-bit Euclid,
+// computed by every CTA for its own candidate BEFORE the barrier), cluster barrier, DSMEM read of the 8/16
+// candidates, pivot row / current row published in shared memory, cluster barrier, DSMEM read, rank-1 update.
 // ---------------------------------------------------------------------------------------------------
+template <bool SMALL>
+__device__ __forceinline__ uint32_t panel_mulmod(uint32_t a, uint32_t b, const ModP& mp, uint32_t mu32) {
+  if constexpr (SMALL) {  // N <= 2^16: 32-bit product, 32-bit Barrett
+    const uint32_t x = a * b;
+    uint32_t r = x - __umulhi(x, mu32) * (uint32_t)mp.P;
+    if (r >= (uint32_t)mp.P) r -= (uint32_t)mp.P;
+    return r;
+  } else {
+    return mulmod_u32(a, b, mp);
+  }
+}
+
+template <bool SMALL>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, uint32_t* __restrict__ Lm, int64_t ldl,
-                  PluqBufs b, const __grid_constant__ ModP mp) {
+                  PluqBufs b, const __grid_constant__ ModP mp, uint32_t mu32) {
   cg::cluster_group cluster = cg::this_cluster();
   const int cs = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   extern __shared__ uint32_t panel[];  // [w][rows_c]
-  __shared__ uint32_t cand_val[2];
+  __shared__ uint32_t cand_val[2], cand_inv[2];
   __shared__ int cand_idx[2];
   __shared__ uint32_t red_val[32];
   __shared__ int red_idx[32];
-  __shared__ uint32_t sel_val;
+  __shared__ uint32_t sel_val, sel_inv;
   __shared__ int sel_idx;
   __shared__ uint32_t rowbuf_p[PANEL_W_MAX], rowbuf_r[PANEL_W_MAX], u_s[PANEL_W_MAX], oldr_s[PANEL_W_MAX];
-  __shared__ uint32_t pinv_s;
+  __shared__ int colpiv[PANEL_W_MAX];       // panel column -> pivot ordinal within this panel, or -1
+  __shared__ uint32_t pivval[PANEL_W_MAX];  // pivot value of ordinal s
 
   const int rb = b.st->r;
   const int rows_total = m - rb;
@@ -76,6 +97,7 @@ pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, u
 
   for (int c = 0; c < w; ++c)
     for (int q = tid; q < my_n; q += PANEL_THREADS) panel[c * rows_c + q] = W[(int64_t)(j0 + c) * ldw + my_lo + q];
+  if (tid < PANEL_W_MAX) colpiv[tid] = -1;
   cluster.sync();  // everybody has read st->r before anyone can finish and overwrite it
 
   int r = rb;
@@ -122,34 +144,41 @@ pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, u
       if (lane == 0) {
         cand_val[jj & 1] = bv;
         cand_idx[jj & 1] = bi;
+        // inverse of this CTA's candidate, off the post-barrier critical path (batched table when N <= 2^20)
+        cand_inv[jj & 1] = bv ? (b.inv_table ? b.inv_table[bv] : modinv_u32(bv, P)) : 0u;
       }
     }
     cluster.sync();
     // ---- phase B: cluster-wide winner through distributed shared memory
     if (warp == 0) {
-      uint32_t v = 0;
+      uint32_t v = 0, iv = 0;
       int i = 0x7fffffff;
       if (lane < cs) {
         v = *cluster.map_shared_rank(&cand_val[jj & 1], lane);
         i = *cluster.map_shared_rank(&cand_idx[jj & 1], lane);
+        iv = *cluster.map_shared_rank(&cand_inv[jj & 1], lane);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const uint32_t ov = __shfl_xor_sync(0xffffffffu, v, o);
         const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        const uint32_t oiv = __shfl_xor_sync(0xffffffffu, iv, o);
         if (better(ov, oi, v, i)) {
           v = ov;
           i = oi;
+          iv = oiv;
         }
       }
       if (lane == 0) {
         sel_val = v;
         sel_idx = i;
+        sel_inv = iv;
       }
     }
     __syncthreads();
     const uint32_t pv = sel_val;
     const int p = sel_idx;
+    const uint32_t pinv = sel_inv;
     if (pv == 0) continue;  // no pivot in this column (uniform over the cluster): skip it, row stays
     const int owner_p = (p - rb) / rows_c, owner_r = (r - rb) / rows_c;
     if (rank == owner_p && tid < w) rowbuf_p[tid] = panel[tid * rows_c + (p - my_lo)];
@@ -158,52 +187,63 @@ pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, u
     if (tid < w) {
       const uint32_t xp = *cluster.map_shared_rank(&rowbuf_p[tid], owner_p);
       const uint32_t xr = *cluster.map_shared_rank(&rowbuf_r[tid], owner_r);
-      const uint32_t pinv = (uint32_t)modinv_u64(pv, P);  // batched: one inverse per pivot, on the device
-      u_s[tid] = tid >= jj ? mulmod_u32(xp, pinv, mp) : 0u;
+      // new row r = old row p: multipliers of earlier pivots (columns < jj) move with the row, pivot -> 1, rest scaled
+      u_s[tid] = tid > jj ? panel_mulmod<SMALL>(xp, pinv, mp, mu32) : (tid == jj ? 1u % P : xp);
       oldr_s[tid] = xr;
-      if (tid == 0) pinv_s = pinv;
+    }
+    if (tid == 0) {
+      const int s_ord = r - rb;
+      colpiv[jj] = s_ord;
+      pivval[s_ord] = pv;
+      if (rank == 0) {
+        b.pivcol[r] = j0 + jj;
+        b.pinv[r] = pinv;
+        b.swp[r] = p;
+      }
     }
     __syncthreads();
     // ---- phase C: swap rows r <-> p, scale, eliminate (every thread owns fixed rows of the panel)
-    const int t = r;  // pivot number == row of U
     for (int q = tid; q < my_n; q += PANEL_THREADS) {
       const int i = my_lo + q;
       if (i < r) continue;
       if (i == r) {
-        for (int c = jj; c < w; ++c) panel[c * rows_c + q] = u_s[c];
-        Lm[(int64_t)t * ldl + i] = pv;
+        for (int c = 0; c < w; ++c) panel[c * rows_c + q] = u_s[c];
       } else {
         const bool isp = (i == p);
+        if (isp)
+          for (int c = 0; c < jj; ++c) panel[c * rows_c + q] = oldr_s[c];
         const uint32_t l = isp ? oldr_s[jj] : panel[jj * rows_c + q];
-        Lm[(int64_t)t * ldl + i] = l;
-        panel[jj * rows_c + q] = 0;
+        if (isp) panel[jj * rows_c + q] = l;  // the multiplier stays in the pivot column (becomes L[i][t] at store-back)
         if (l != 0 || isp) {
           for (int c = jj + 1; c < w; ++c) {
             const uint32_t a = isp ? oldr_s[c] : panel[c * rows_c + q];
-            panel[c * rows_c + q] = submod_u32(a, mulmod_u32(l, u_s[c], mp), P);
+            panel[c * rows_c + q] = submod_u32(a, panel_mulmod<SMALL>(l, u_s[c], mp, mu32), P);
           }
         }
-      }
-    }
-    if (rank == 0) {
-      // earlier L columns of THIS panel follow the row swap (reference swap_rows on d_L, pluq_kernels.jl:280-289)
-      if (p != r && tid < r - rb) {
-        uint32_t* col = Lm + (int64_t)(rb + tid) * ldl;
-        const uint32_t x = col[r], y = col[p];
-        col[r] = y;
-        col[p] = x;
-      }
-      if (tid == 0) {
-        b.pivcol[t] = j0 + jj;
-        b.pinv[t] = pinv_s;
-        b.swp[t] = p;
       }
     }
     ++r;
   }
   __syncthreads();
-  for (int c = 0; c < w; ++c)
-    for (int q = tid; q < my_n; q += PANEL_THREADS) W[(int64_t)(j0 + c) * ldw + my_lo + q] = panel[c * rows_c + q];
+  // ---- store-back: pivot columns split into U (rows <= pivot row) and L (rows below), everything else is W
+  for (int c = 0; c < w; ++c) {
+    const int s_ord = colpiv[c];
+    const int t = rb + s_ord;
+    for (int q = tid; q < my_n; q += PANEL_THREADS) {
+      const int i = my_lo + q;
+      const uint32_t v = panel[c * rows_c + q];
+      uint32_t* wdst = W + (int64_t)(j0 + c) * ldw + i;
+      if (s_ord < 0 || i < t) {
+        *wdst = v;
+      } else if (i == t) {
+        *wdst = v;  // == 1
+        Lm[(int64_t)t * ldl + i] = pivval[s_ord];
+      } else {
+        *wdst = 0;
+        Lm[(int64_t)t * ldl + i] = v;
+      }
+    }
+  }
 
   // ---- compose this panel's transpositions (rb..r-1) into one gather list (warp 0 of CTA 0)
   if (rank == 0 && warp == 0) {
@@ -386,7 +426,7 @@ triinv_base_kernel(const uint32_t* __restrict__ T, int64_t ldt, uint32_t* __rest
   }
   __syncthreads();
   if (j < nb) {
-    uint32_t d = unit_diag ? 1u : (uint32_t)modinv_u64(sT[j][j], P);
+    uint32_t d = unit_diag ? 1u : modinv_u32(sT[j][j], P);
     if (!unit_diag && d == 0 && P != 1) atomicExch(singular, 1);
     dinv[j] = d;
   }
@@ -452,6 +492,11 @@ __global__ void swap_pairs_kernel(uint32_t* __restrict__ X, int64_t ld, int rows
   }
 }
 
+__global__ void inv_table_kernel(uint32_t* __restrict__ tab, uint32_t N) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < N) tab[x] = x ? modinv_u32(x, N) : 0u;
+}
+
 __global__ void modinv_batch_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
                                     unsigned long long N) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,31 +513,235 @@ struct Elim {
   std::vector<int> pivcol, swp;
 };
 
-int32_t launch_panel(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int rows_c_max, const PluqBufs& b, const ModP& mp) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    GFFM_CUDA(cudaFuncSetAttribute(pluq_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET));
-    attr_set = true;
-  }
+template <bool SMALL>
+int32_t launch_panel_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int rows_c_max, int cluster, const PluqBufs& b,
+                       const ModP& mp) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(PANEL_CLUSTER);
+  cfg.gridDim = dim3(cluster);
   cfg.blockDim = dim3(PANEL_THREADS);
   cfg.dynamicSmemBytes = (size_t)w * rows_c_max * 4;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = PANEL_CLUSTER;
+  at[0].val.clusterDim.x = cluster;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  GFFM_CUDA(cudaLaunchKernelEx(&cfg, pluq_panel_kernel, W->data, W->ld, (int)W->rows, j0, w, L->data, L->ld, b, mp));
+  const uint32_t mu32 = (uint32_t)((1ull << 32) / mp.P);
+  GFFM_CUDA(cudaLaunchKernelEx(&cfg, pluq_panel_kernel<SMALL>, W->data, W->ld, (int)W->rows, j0, w, L->data, L->ld, b, mp, mu32));
   ctx->launches++;
   return GFFM_OK;
 }
 
-int32_t triinv_views(gffm_ctx* ctx, MatView T, MatView X, bool upper, bool unit_diag, uint64_t P, int* singular_dev);
+// cluster size of the panel kernel: 16 CTAs (non-portable size, opt-in) when the device can co-schedule them, else 8
+int panel_cluster_size(gffm_ctx* ctx) {
+  static int chosen = 0;
+  if (chosen) return chosen;
+  chosen = PANEL_CLUSTER;
+  cudaFuncSetAttribute(pluq_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
+  cudaFuncSetAttribute(pluq_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
+  const char* env = getenv("GFFM_PANEL_CLUSTER");
+  const int want = env ? atoi(env) : 16;
+  if (want == 16 && cudaFuncSetAttribute(pluq_panel_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+      cudaFuncSetAttribute(pluq_panel_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(16);
+    cfg.blockDim = dim3(PANEL_THREADS);
+    cfg.dynamicSmemBytes = PANEL_SMEM_BUDGET;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 16;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, pluq_panel_kernel<false>, &cfg) == cudaSuccess && nclusters >= 1) chosen = 16;
+  } else if (want >= 1 && want <= 8) {
+    chosen = want;
+  }
+  cudaGetLastError();
+  (void)ctx;
+  return chosen;
+}
+
+int32_t launch_panel(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int rows_c_max, int cluster, const PluqBufs& b,
+                     const ModP& mp) {
+  if (mp.P <= 65536) return launch_panel_t<true>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
+  return launch_panel_t<false>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
+}
+
+int32_t triinv_views(gffm_ctx* ctx, MatView T, MatView X, bool upper, bool unit_diag, uint64_t P, int* singular_dev,
+                     const MatView* scratch_opt = nullptr);
+
+// ---- recursive blocked elimination -----------------------------------------------------------------------------
+// elim_rec(c_lo, c_hi): columns narrower than NB0 are factorised by cluster panels + SIMT rank-w updates; wider ranges are
+// split in two, and after the left half the right half receives U12 = L11^-1 * A12 and the Schur update
+// A22 -= L21 * U12 through the tensor-core GEMM with K = number of pivots found in the left half (up to n/2), so the
+// modular GEMM runs at large K where it is tensor-bound instead of epilogue/HBM-bound.
+constexpr int NB0 = 256;
+
+struct ElimState {
+  gffm_ctx* ctx;
+  gffm_mat *W, *L;
+  int m, n;
+  uint64_t N;
+  ModP mp;
+  PluqBufs b;
+  int big_mod;
+  int r;  // pivots found so far (host copy, refreshed after every base block)
+  double t_panel = 0, t_u12 = 0, t_trail = 0;
+  // stack allocator over ctx->ws_scratch for the Schur-update temporaries
+  char* sbase = nullptr;
+  size_t scap = 0;
+  // one entry per base block that produced pivots: pivot rows [r_start, r_start+K) and the cached inverse of its
+  // K x K diagonal block of L (leading dimension NB0), reused by every triangular solve above it in the recursion
+  struct Block {
+    int r_start, K;
+    uint32_t* linv;
+  };
+  std::vector<Block> blocks;
+  uint32_t* linv_pool = nullptr;
+};
+
+MatView scratch_view(ElimState& E, size_t& off, int64_t rows, int64_t cols) {
+  const int64_t ld = round_up(std::max<int64_t>(rows, 1), 32);
+  MatView v{reinterpret_cast<uint32_t*>(E.sbase + off), ld, rows, cols};
+  off += (size_t)ld * std::max<int64_t>(cols, 1) * 4;
+  off = (off + 255) & ~(size_t)255;
+  return v;
+}
+
+int32_t base_block(ElimState& E, int c_lo, int c_hi) {
+  gffm_ctx* ctx = E.ctx;
+  gffm_mat *W = E.W, *L = E.L;
+  const int m = E.m, n = E.n, r0 = E.r;
+  const bool prof = ctx->profile;
+  if (prof) cudaEventRecord(ctx->ev[4], ctx->stream);
+  const int cluster = panel_cluster_size(ctx);
+  const int rows_c_max = (int)ceil_div(m - r0, cluster);
+  int w = PANEL_SMEM_BUDGET / (4 * std::max(rows_c_max, 1));
+  static const int w_cap = getenv("GFFM_PANEL_W") ? std::max(1, std::min(PANEL_W_MAX, atoi(getenv("GFFM_PANEL_W")))) : 16;
+  w = std::min(w, w_cap);
+  if (w < 1) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "matrix has too many rows (%d) for the panel kernel", m);
+  for (int j0 = c_lo; j0 < c_hi; j0 += w) {
+    const int wj = std::min(w, c_hi - j0);
+    GFFM_TRY(launch_panel(ctx, W, L, j0, wj, rows_c_max, cluster, E.b, E.mp));
+    // row swaps of this panel: W columns right of the panel, all earlier L columns [0, rb)
+    if (j0 + wj < n) {
+      const int ncol = n - (j0 + wj);
+      gather_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(ncol, 8), 4 * ctx->num_sms), 256, 0, ctx->stream>>>(
+          W->data, W->ld, j0 + wj, n, nullptr, E.b);
+      GFFM_LAUNCH_CHECK(ctx);
+    }
+    if (j0 > 0) {
+      gather_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(std::max(std::min(j0, m), 1), 8), 4 * ctx->num_sms), 256, 0, ctx->stream>>>(
+          L->data, L->ld, 0, 0, &E.b.st->rb, E.b);
+      GFFM_LAUNCH_CHECK(ctx);
+    }
+    // rest of the base block: U12' = L11'^-1 W12', W22' -= L21' U12'
+    const int lo = j0 + wj;
+    if (lo < c_hi) {
+      trsm_small_kernel<<<(unsigned)ceil_div(c_hi - lo, 8), 256, 0, ctx->stream>>>(W->data, W->ld, lo, c_hi, L->data, L->ld, E.b, E.mp);
+      GFFM_LAUNCH_CHECK(ctx);
+      dim3 grid((unsigned)ceil_div(m - r0, 128), (unsigned)std::min<int64_t>(ceil_div(c_hi - lo, 32), 8));
+      update_small_kernel<<<grid, 256, 0, ctx->stream>>>(W->data, W->ld, m, lo, c_hi, L->data, L->ld, E.b, E.big_mod, E.mp);
+      GFFM_LAUNCH_CHECK(ctx);
+    }
+  }
+  if (prof) cudaEventRecord(ctx->ev[5], ctx->stream);
+  PluqState hs;
+  GFFM_CUDA(cudaMemcpyAsync(&hs, E.b.st, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+  GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  E.r = hs.r;
+  if (prof) {
+    float a = 0;
+    cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
+    E.t_panel += a;
+  }
+  const int K = E.r - r0;
+  if (K > 0 && E.linv_pool) {
+    ElimState::Block blk{r0, K, E.linv_pool + (size_t)E.blocks.size() * NB0 * NB0};
+    MatView X{blk.linv, NB0, K, K};
+    GFFM_TRY(gffm_fill_view(ctx, X, 0));
+    size_t off = 0;
+    MatView tsc = scratch_view(E, off, NB0 / 2, NB0 / 2);
+    GFFM_TRY(triinv_views(ctx, sub_view(view_of(L), r0, r0, K, K), X, /*upper=*/false, false, E.N, nullptr, &tsc));
+    E.blocks.push_back(blk);
+  }
+  return GFFM_OK;
+}
+
+// W[rows of blocks b_lo..b_hi, c1..c2) <- L11^-1 * (same rows), L11 = the unit-free lower-triangular block of L spanned by
+// those blocks.  Recursive over the block list: diagonal blocks use their cached inverses, off-diagonal parts are GEMMs
+// whose K is the pivot count of the left part.
+int32_t trsm_blocks(ElimState& E, int b_lo, int b_hi, int c1, int c2) {
+  gffm_ctx* ctx = E.ctx;
+  MatView Wv = view_of(E.W), Lv = view_of(E.L);
+  const int nc = c2 - c1;
+  if (b_hi - b_lo == 1) {
+    const ElimState::Block& blk = E.blocks[b_lo];
+    size_t off = 0;
+    MatView tmp = scratch_view(E, off, blk.K, nc);
+    if (off > E.scap) GFFM_FAIL(GFFM_ERR_OOM, "elimination scratch too small");
+    MatView X{blk.linv, NB0, blk.K, blk.K};
+    MatView rows = sub_view(Wv, blk.r_start, c1, blk.K, nc);
+    GFFM_TRY(gffm_gemm_views(ctx, tmp, X, rows, E.N, E.N, GFFM_GEMM_STORE, GFFM_ALGO_AUTO));
+    return gffm_copy_views(ctx, rows, tmp);
+  }
+  const int mid = (b_lo + b_hi) / 2;
+  GFFM_TRY(trsm_blocks(E, b_lo, mid, c1, c2));
+  const int r_lo = E.blocks[b_lo].r_start, r_mid = E.blocks[mid].r_start;
+  const int r_hi = E.blocks[b_hi - 1].r_start + E.blocks[b_hi - 1].K;
+  GFFM_TRY(gffm_gemm_views(ctx, sub_view(Wv, r_mid, c1, r_hi - r_mid, nc), sub_view(Lv, r_mid, r_lo, r_hi - r_mid, r_mid - r_lo),
+                           sub_view(Wv, r_lo, c1, r_mid - r_lo, nc), E.N, E.N, GFFM_GEMM_SUB, GFFM_ALGO_AUTO));
+  return trsm_blocks(E, mid, b_hi, c1, c2);
+}
+
+// columns [c1, c2): rows r0..r0+K become U12 = L11^-1 * W12, rows below get W22 -= L21 * U12
+int32_t schur_update(ElimState& E, int r0, int K, int c1, int c2) {
+  gffm_ctx* ctx = E.ctx;
+  const bool prof = ctx->profile;
+  const int nc = c2 - c1;
+  if (prof) cudaEventRecord(ctx->ev[5], ctx->stream);
+  MatView Wv = view_of(E.W), Lv = view_of(E.L);
+  // blocks covering pivot rows [r0, r0+K)
+  int b_lo = -1, b_hi = -1;
+  for (int i = 0; i < (int)E.blocks.size(); ++i) {
+    if (E.blocks[i].r_start == r0) b_lo = i;
+    if (E.blocks[i].r_start + E.blocks[i].K == r0 + K) b_hi = i + 1;
+  }
+  if (b_lo < 0 || b_hi <= b_lo) GFFM_FAIL(GFFM_ERR_INVALID, "internal: pivot blocks do not tile [%d,%d)", r0, r0 + K);
+  GFFM_TRY(trsm_blocks(E, b_lo, b_hi, c1, c2));
+  if (prof) cudaEventRecord(ctx->ev[6], ctx->stream);
+  if (r0 + K < E.m)
+    GFFM_TRY(gffm_gemm_views(ctx, sub_view(Wv, r0 + K, c1, E.m - r0 - K, nc), sub_view(Lv, r0 + K, r0, E.m - r0 - K, K),
+                             sub_view(Wv, r0, c1, K, nc), E.N, E.N, GFFM_GEMM_SUB, GFFM_ALGO_AUTO));
+  if (prof) {
+    cudaEventRecord(ctx->ev[7], ctx->stream);
+    cudaEventSynchronize(ctx->ev[7]);
+    float a = 0, b2 = 0;
+    cudaEventElapsedTime(&a, ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&b2, ctx->ev[6], ctx->ev[7]);
+    E.t_u12 += a;
+    E.t_trail += b2;
+  }
+  return GFFM_OK;
+}
+
+int32_t elim_rec(ElimState& E, int c_lo, int c_hi) {
+  if (E.r >= E.m || c_lo >= c_hi) return GFFM_OK;
+  if (c_hi - c_lo <= NB0) return base_block(E, c_lo, c_hi);
+  const int mid = c_lo + (int)round_up((c_hi - c_lo + 1) / 2, NB0);
+  const int r_before = E.r;
+  GFFM_TRY(elim_rec(E, c_lo, mid));
+  const int K = E.r - r_before;
+  if (K > 0 && mid < c_hi) GFFM_TRY(schur_update(E, r_before, K, mid, c_hi));
+  return elim_rec(E, mid, c_hi);
+}
 
 // Row-echelon elimination of A (copy) with L; leaves everything on the device, returns rank/pivots on the host.
 int32_t eliminate(gffm_mat* A, Elim* out) {
@@ -502,18 +751,28 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
   if (N >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "elimination needs N < 2^32");
   gffm_mat *W = nullptr, *L = nullptr;
   GFFM_TRY(gffm_mat_create(ctx, m, n, N, A->pad, &W));
-  GFFM_TRY(gffm_mat_create(ctx, m, m, N, A->pad, &L));
   out->W = W;
+  GFFM_TRY(gffm_mat_create(ctx, m, m, N, A->pad, &L));
   out->L = L;
   GFFM_TRY(gffm_copy_views(ctx, view_of(W), view_of(A)));
   const int maxr = std::min(m, n);
   out->rank = 0;
   if (maxr == 0) return GFFM_OK;
+  ElimState E;
+  E.ctx = ctx;
+  E.W = W;
+  E.L = L;
+  E.m = m;
+  E.n = n;
+  E.N = N;
+  E.mp = make_modp(N);
+  E.big_mod = N > (1ull << 29) ? 1 : 0;
+  E.r = 0;
   // device bookkeeping
   const size_t need = sizeof(PluqState) + (size_t)maxr * (sizeof(int) * 2 + sizeof(uint32_t)) + 2 * 64 * sizeof(int) + 256;
   GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_misc2, need));
   char* base = (char*)ctx->ws_misc2.ptr;
-  PluqBufs b;
+  PluqBufs& b = E.b;
   b.st = (PluqState*)base;
   b.pivcol = (int*)(base + 64);
   b.swp = b.pivcol + maxr;
@@ -521,65 +780,31 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
   b.g_dst = (int*)(b.pinv + maxr);
   b.g_src = b.g_dst + 64;
   GFFM_CUDA(cudaMemsetAsync(base, 0, need, ctx->stream));
-  const ModP mp = make_modp(N);
-  const int big_mod = N > (1ull << 29) ? 1 : 0;
-  const int NB = 256;
-  int r0 = 0;
-  for (int c0 = 0; c0 < n && r0 < m; c0 += NB) {
-    const int nbc = std::min(NB, n - c0);
-    const int rows_c_max = (int)ceil_div(m - r0, PANEL_CLUSTER);
-    int w = PANEL_SMEM_BUDGET / (4 * std::max(rows_c_max, 1));
-    w = std::min(w, 16);
-    if (w < 1) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "matrix has too many rows (%d) for the panel kernel", m);
-    for (int j0 = c0; j0 < c0 + nbc; j0 += w) {
-      const int wj = std::min(w, c0 + nbc - j0);
-      GFFM_TRY(launch_panel(ctx, W, L, j0, wj, rows_c_max, b, mp));
-      // row swaps of this panel: W columns right of the panel, all earlier L columns [0, rb)
-      if (j0 + wj < n) {
-        const int ncol = n - (j0 + wj);
-        gather_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(ncol, 8), 4 * ctx->num_sms), 256, 0, ctx->stream>>>(
-            W->data, W->ld, j0 + wj, n, nullptr, b);
-        GFFM_LAUNCH_CHECK(ctx);
-      }
-      if (r0 > 0 || j0 > c0) {
-        gather_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(std::max(j0, 1), 8), 4 * ctx->num_sms), 256, 0, ctx->stream>>>(
-            L->data, L->ld, 0, 0, &b.st->rb, b);
-        GFFM_LAUNCH_CHECK(ctx);
-      }
-      // rest of the outer block: U12' = L11'^-1 W12', W22' -= L21' U12'
-      const int c_lo = j0 + wj, c_hi = c0 + nbc;
-      if (c_lo < c_hi) {
-        trsm_small_kernel<<<(unsigned)ceil_div(c_hi - c_lo, 8), 256, 0, ctx->stream>>>(W->data, W->ld, c_lo, c_hi, L->data, L->ld, b, mp);
-        GFFM_LAUNCH_CHECK(ctx);
-        dim3 grid((unsigned)ceil_div(m - r0, 128), (unsigned)std::min<int64_t>(ceil_div(c_hi - c_lo, 32), 8));
-        update_small_kernel<<<grid, 256, 0, ctx->stream>>>(W->data, W->ld, m, c_lo, c_hi, L->data, L->ld, b, big_mod, mp);
-        GFFM_LAUNCH_CHECK(ctx);
-      }
+  b.inv_table = nullptr;
+  if (N <= (1u << 20)) {  // batched modular inverses: one kernel computes every inverse mod N, cached per context
+    if (ctx->inv_table_N != N) {
+      GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_invtab, (size_t)N * 4));
+      inv_table_kernel<<<(unsigned)ceil_div((int64_t)N, 256), 256, 0, ctx->stream>>>((uint32_t*)ctx->ws_invtab.ptr, (uint32_t)N);
+      GFFM_LAUNCH_CHECK(ctx);
+      ctx->inv_table_N = N;
     }
-    // pivots found in this outer block
-    PluqState hs;
-    GFFM_CUDA(cudaMemcpyAsync(&hs, b.st, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
-    GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int K = hs.r - r0;
-    const int c1 = c0 + nbc;
-    if (K > 0 && c1 < n) {
-      // U12 = L11^-1 * W[r0..r0+K, c1..n)
-      gffm_mat* Linv = nullptr;
-      GFFM_TRY(gffm_mat_create(ctx, K, K, N, 0, &Linv));
-      int32_t st = triinv_views(ctx, sub_view(view_of(L), r0, r0, K, K), view_of(Linv), /*upper=*/false, false, N, nullptr);
-      gffm_mat* tmp = nullptr;
-      if (st == GFFM_OK) st = gffm_mat_create(ctx, K, n - c1, N, 0, &tmp);
-      if (st == GFFM_OK) st = gffm_gemm_views(ctx, view_of(tmp), view_of(Linv), sub_view(view_of(W), r0, c1, K, n - c1), N, N, GFFM_GEMM_STORE, GFFM_ALGO_AUTO);
-      if (st == GFFM_OK) st = gffm_copy_views(ctx, sub_view(view_of(W), r0, c1, K, n - c1), view_of(tmp));
-      // W22 -= L21 * U12
-      if (st == GFFM_OK && hs.r < m)
-        st = gffm_gemm_views(ctx, sub_view(view_of(W), hs.r, c1, m - hs.r, n - c1), sub_view(view_of(L), hs.r, r0, m - hs.r, K),
-                             sub_view(view_of(W), r0, c1, K, n - c1), N, N, GFFM_GEMM_SUB, GFFM_ALGO_AUTO);
-      gffm_mat_destroy(Linv);
-      if (tmp) gffm_mat_destroy(tmp);
-      GFFM_TRY(st);
-    }
-    r0 = hs.r;
+    b.inv_table = (const uint32_t*)ctx->ws_invtab.ptr;
+  }
+  // scratch: one NB0 x n tile for the triangular solves (+ the 128 x 128 scratch of the block inversions) and the pool
+  // of cached NB0 x NB0 diagonal-block inverses
+  if (n > NB0) {
+    const size_t nblk = (size_t)ceil_div(n, NB0) + 1;
+    const size_t tmp_bytes = 4 * ((size_t)NB0 * n + (size_t)NB0 * NB0) + 8192;
+    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_scratch, tmp_bytes + nblk * NB0 * NB0 * 4));
+    E.sbase = (char*)ctx->ws_scratch.ptr;
+    E.scap = tmp_bytes;
+    E.linv_pool = reinterpret_cast<uint32_t*>(E.sbase + tmp_bytes);
+  }
+  GFFM_TRY(elim_rec(E, 0, n));
+  const int r0 = E.r;
+  if (ctx->profile) {
+    ctx->n_ev = 0;
+    ctx->elim_timings = {E.t_panel, E.t_u12, E.t_trail};
   }
   out->rank = r0;
   out->pivcol.resize(r0);
@@ -596,7 +821,7 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
 // half must be zero on entry).  Recursive halving at multiples of TRI_B; combine with two GEMMs:
 //   lower: X21 = -X22 * T21 * X11        upper: X12 = -X11 * T12 * X22
 // (reference triangular_inverse_no_copy.jl:153-157,182-186,406-410,435-439 -- there with unguarded cuBLAS float GEMM)
-int32_t triinv_rec(gffm_ctx* ctx, MatView T, MatView X, bool upper, uint64_t P, int lo, int hi, gffm_mat* scratch) {
+int32_t triinv_rec(gffm_ctx* ctx, MatView T, MatView X, bool upper, uint64_t P, int lo, int hi, const MatView& scratch) {
   const int len = hi - lo;
   if (len <= TRI_B) return GFFM_OK;  // base blocks were inverted in one batched launch
   const int half = (int)round_up((len + 1) / 2, TRI_B);
@@ -607,14 +832,14 @@ int32_t triinv_rec(gffm_ctx* ctx, MatView T, MatView X, bool upper, uint64_t P, 
   if (!upper) {
     MatView T21 = sub_view(T, mid, lo, n2, n1), X11 = sub_view(X, lo, lo, n1, n1), X22 = sub_view(X, mid, mid, n2, n2),
             X21 = sub_view(X, mid, lo, n2, n1);
-    MatView tmp = sub_view(view_of(scratch), 0, 0, n2, n1);
+    MatView tmp = sub_view(scratch, 0, 0, n2, n1);
     GFFM_TRY(gffm_gemm_views(ctx, tmp, T21, X11, P, P, GFFM_GEMM_STORE, GFFM_ALGO_AUTO));
     GFFM_TRY(gffm_fill_view(ctx, X21, 0));
     GFFM_TRY(gffm_gemm_views(ctx, X21, X22, tmp, P, P, GFFM_GEMM_SUB, GFFM_ALGO_AUTO));
   } else {
     MatView T12 = sub_view(T, lo, mid, n1, n2), X11 = sub_view(X, lo, lo, n1, n1), X22 = sub_view(X, mid, mid, n2, n2),
             X12 = sub_view(X, lo, mid, n1, n2);
-    MatView tmp = sub_view(view_of(scratch), 0, 0, n1, n2);
+    MatView tmp = sub_view(scratch, 0, 0, n1, n2);
     GFFM_TRY(gffm_gemm_views(ctx, tmp, T12, X22, P, P, GFFM_GEMM_STORE, GFFM_ALGO_AUTO));
     GFFM_TRY(gffm_fill_view(ctx, X12, 0));
     GFFM_TRY(gffm_gemm_views(ctx, X12, X11, tmp, P, P, GFFM_GEMM_SUB, GFFM_ALGO_AUTO));
@@ -622,7 +847,8 @@ int32_t triinv_rec(gffm_ctx* ctx, MatView T, MatView X, bool upper, uint64_t P, 
   return GFFM_OK;
 }
 
-int32_t triinv_views(gffm_ctx* ctx, MatView T, MatView X, bool upper, bool unit_diag, uint64_t P, int* singular_dev) {
+int32_t triinv_views(gffm_ctx* ctx, MatView T, MatView X, bool upper, bool unit_diag, uint64_t P, int* singular_dev,
+                     const MatView* scratch_opt) {
   const int n = (int)T.rows;
   if (T.cols != n || X.rows != n || X.cols != n) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "triinv: square views expected");
   if (n == 0) return GFFM_OK;
@@ -636,10 +862,14 @@ int32_t triinv_views(gffm_ctx* ctx, MatView T, MatView X, bool upper, bool unit_
                                                                                sing, make_modp(P));
   GFFM_LAUNCH_CHECK(ctx);
   if (n <= TRI_B) return GFFM_OK;
-  gffm_mat* scratch = nullptr;
   const int half = (int)round_up((n + 1) / 2, TRI_B);
+  if (scratch_opt) {
+    if (scratch_opt->rows < half || scratch_opt->cols < half) GFFM_FAIL(GFFM_ERR_INVALID, "triinv scratch too small");
+    return triinv_rec(ctx, T, X, upper, P, 0, n, *scratch_opt);
+  }
+  gffm_mat* scratch = nullptr;
   GFFM_TRY(gffm_mat_create(ctx, half, half, P, 0, &scratch));
-  int32_t st = triinv_rec(ctx, T, X, upper, P, 0, n, scratch);
+  int32_t st = triinv_rec(ctx, T, X, upper, P, 0, n, view_of(scratch));
   gffm_mat_destroy(scratch);
   return st;
 }
