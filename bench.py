@@ -181,8 +181,7 @@ def main():
 
     with torch.cuda.stream(stream):
         # ---- resident inputs: A row block of this rank, B (broadcast from rank 0 each step when world > 1) -----------
-        rows_per = (n + world - 1) // world
-        r0, r1 = rank * rows_per, min(n, (rank + 1) * rows_per)
+        r0, r1 = g.multigpu.row_block(n, world, rank)
         mloc = r1 - r0
         if world == 1:
             A = g.synth(n, n, N, SEED_A, ctx=ctx)
@@ -201,21 +200,19 @@ def main():
             ctx.sync()
             del Bs
         C = g.zeros(np.float32, mloc, n, N, ctx=ctx)
-        npan = max(1, args.panels) if world > 1 else 1
-        pan = (n + npan - 1) // npan
+        panels = g.multigpu.col_panels(n, args.panels if world > 1 else 1)
+        npan = len(panels)
+        pan = panels[0][1] - panels[0][0]
+
+        def gemm_panel(c0, c1):
+            g.capi.check(C.lib.gffm_gemm_block(C.h, 0, c0, A.h, 0, 0, B.h, 0, c0, mloc, c1 - c0, n, 0, 0, g.capi.GEMM_STORE, g.capi.ALGO_AUTO))
 
         def step():
+            A.touch()  # every step is a FRESH product: the cached 8-bit planes of A are rebuilt (B is external memory, never cached)
             if world == 1:
                 g.mul_(C, A, B)
-                return
-            works = []
-            for p in range(npan):
-                c0, c1 = p * pan, min(n, (p + 1) * pan)
-                works.append(dist.broadcast(Bt[c0:c1], src=0, async_op=True))
-            for p in range(npan):
-                c0, c1 = p * pan, min(n, (p + 1) * pan)
-                works[p].wait()  # stream-level dependency: the GEMM of panel p overlaps the broadcast of panel p+1
-                g.capi.check(C.lib.gffm_gemm_block(C.h, 0, c0, A.h, 0, 0, B.h, 0, c0, mloc, c1 - c0, n, 0, 0, g.capi.GEMM_STORE, g.capi.ALGO_AUTO))
+            else:  # NCCL broadcast of B in column panels, GEMM of panel p overlaps the broadcast of panel p+1
+                g.multigpu.pipelined_broadcast_matmul(dist, Bt, panels, gemm_panel, src=0)
 
         for _ in range(W):
             step()
@@ -332,6 +329,7 @@ def main():
                 a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
                 a0.record(stream)
                 for _ in range(5):
+                    A_.touch(); B_.touch()  # fresh product each time (no cached planes)
                     g.mul_(C_, A_, B_)
                 a1.record(stream); torch.cuda.synchronize()
                 t_ = a0.elapsed_time(a1) / 5

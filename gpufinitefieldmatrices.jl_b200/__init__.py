@@ -7,6 +7,7 @@ from .capi import (CuModArrayModulusMismatchException, CuModArraySizeMismatchExc
 from .cumodmatrix import *  # noqa: F401,F403
 from .cumodmatrix import Context, CuModMatrix, CuModVector, default_context
 from . import karatsuba
+from . import multigpu
 from .karatsuba import KaratsubaMatrix, KaratsubaVector, KaratsubaZeros, KMatMul_, KMatMul_gemv_, MatToKMat, initialize_plan_
 
 __all__ = [n for n in dir() if not n.startswith("_")]

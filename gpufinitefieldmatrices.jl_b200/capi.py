@@ -79,6 +79,8 @@ SIGNATURES = {
     "gffm_mat_create": [_vp, _i64, _i64, _u64, _i32, _pvp],
     "gffm_mat_wrap": [_vp, _vp, _i64, _i64, _i64, _u64, _pvp],
     "gffm_mat_destroy": [_vp],
+    "gffm_mat_drop_cache": [_vp],
+    "gffm_mat_touch": [_vp],
     "gffm_mat_upload": [_vp, _vp, _i32, _i64, _i32],
     "gffm_mat_download": [_vp, _vp, _i32, _i64, _i32],
     "gffm_mat_rows": [_vp, _pi64],

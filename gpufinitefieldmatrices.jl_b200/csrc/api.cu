@@ -220,8 +220,34 @@ extern "C" int32_t gffm_mat_wrap(gffm_ctx* ctx, void* dptr, int64_t rows, int64_
   return GFFM_OK;
 }
 
+static void free_plane_caches(gffm_mat* m) {
+  for (int r = 0; r < 2; ++r) {
+    if (m->cache[r].ptr) cudaFree(m->cache[r].ptr);
+    m->cache[r] = gffm_plane_cache();
+  }
+}
+
+extern "C" int32_t gffm_mat_touch(gffm_mat* m) {
+  if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  gffm_touch(m);
+  return GFFM_OK;
+}
+
+extern "C" int32_t gffm_mat_drop_cache(gffm_mat* m) {
+  if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  free_plane_caches(m);
+  return GFFM_OK;
+}
+
 extern "C" int32_t gffm_mat_destroy(gffm_mat* m) {
   if (!m) return GFFM_OK;
+  if (m->cache[0].ptr || m->cache[1].ptr) {
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    free_plane_caches(m);
+  }
   if (m->owned && m->data) {
     // stream-ordered: wait for queued work that may still use the buffer (safe from a finalizer thread)
     cudaSetDevice(m->ctx->device);
@@ -314,6 +340,7 @@ extern "C" int32_t gffm_mat_upload(gffm_mat* m, const void* host, int32_t dtype,
   if (!es) GFFM_FAIL(GFFM_ERR_INVALID, "bad dtype %d", dtype);
   if (ld < m->rows) GFFM_FAIL(GFFM_ERR_INVALID, "ld < rows");
   if (m->rows == 0 || m->cols == 0) return GFFM_OK;
+  gffm_touch(m);
   gffm_ctx* ctx = m->ctx;
   cudaSetDevice(ctx->device);
   if (dtype == GFFM_U32) {
@@ -464,6 +491,7 @@ int32_t gffm_ew_views(gffm_ctx* ctx, int op, MatView C, MatView A, const MatView
 extern "C" int32_t gffm_ewise(int32_t op, gffm_mat* C, gffm_mat* A, gffm_mat* B, int64_t scalar, uint64_t mod_override) {
   if (!C || !A) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (op < GFFM_EW_MOD || op > GFFM_EW_SDIV) GFFM_FAIL(GFFM_ERR_INVALID, "bad op");
+  gffm_touch(C);
   const uint64_t P = mod_override ? mod_override : C->N;
   if (!mod_override) {  // reference checks moduli unless mod_N is given (CuModMatrix.jl add!/sub! preambles)
     if (A->N != C->N || (B && B->N != C->N)) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "operands have different moduli");
@@ -534,6 +562,7 @@ int32_t gffm_fill_view(gffm_ctx* ctx, MatView dst, uint32_t value) {
 extern "C" int32_t gffm_mat_copy(gffm_mat* dst, gffm_mat* src) {
   if (!dst || !src) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (dst->rows != src->rows || dst->cols != src->cols) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "copy!: sizes differ");
+  gffm_touch(dst);
   return gffm_copy_views(dst->ctx, view_of(dst), view_of(src));
 }
 extern "C" int32_t gffm_mat_copy_block(gffm_mat* dst, int64_t dr0, int64_t dc0, gffm_mat* src, int64_t sr0, int64_t sc0, int64_t nr, int64_t nc) {
@@ -541,16 +570,19 @@ extern "C" int32_t gffm_mat_copy_block(gffm_mat* dst, int64_t dr0, int64_t dc0, 
   if (dr0 < 0 || dc0 < 0 || sr0 < 0 || sc0 < 0 || nr < 0 || nc < 0 || dr0 + nr > dst->rows || dc0 + nc > dst->cols ||
       sr0 + nr > src->rows || sc0 + nc > src->cols)
     GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "block out of range");
+  gffm_touch(dst);
   return gffm_copy_views(dst->ctx, sub_view(view_of(dst), dr0, dc0, nr, nc), sub_view(view_of(src), sr0, sc0, nr, nc));
 }
 extern "C" int32_t gffm_mat_fill(gffm_mat* m, int64_t value) {
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  gffm_touch(m);
   return gffm_fill_view(m->ctx, view_of(m), scalar_residue(value, m->N));
 }
 extern "C" int32_t gffm_mat_zero(gffm_mat* m) { return gffm_mat_fill(m, 0); }
 extern "C" int32_t gffm_mat_eye(gffm_mat* m) {
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (m->rows * m->cols == 0) return GFFM_OK;
+  gffm_touch(m);
   fill_kernel<<<grid_for(m->ctx, m->rows * m->cols), 256, 0, m->ctx->stream>>>(m->data, m->ld, m->rows, m->cols, scalar_residue(1, m->N), 1);
   GFFM_LAUNCH_CHECK(m->ctx);
   return GFFM_OK;
@@ -558,6 +590,7 @@ extern "C" int32_t gffm_mat_eye(gffm_mat* m) {
 extern "C" int32_t gffm_mat_synth(gffm_mat* m, uint64_t seed) {
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (m->rows * m->cols == 0) return GFFM_OK;
+  gffm_touch(m);
   synth_kernel<<<grid_for(m->ctx, m->rows * m->cols), 256, 0, m->ctx->stream>>>(m->data, m->ld, m->rows, m->cols, seed, m->N);
   GFFM_LAUNCH_CHECK(m->ctx);
   return GFFM_OK;
@@ -570,6 +603,7 @@ extern "C" int32_t gffm_mat_set_modulus(gffm_mat* m, uint64_t N, int32_t reduce)
   if (N > (1ull << 52)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "Modulus is bigger than 2^52");
   if (N > (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "moduli above 2^32 need wide storage");
   m->N = N;
+  gffm_touch(m);
   if (reduce && N < (1ull << 32)) return gffm_ew_views(m->ctx, GFFM_EW_MOD, view_of(m), view_of(m), nullptr, 0, N);
   return GFFM_OK;
 }
@@ -586,12 +620,14 @@ extern "C" int32_t gffm_mat_get_elem(gffm_mat* m, int64_t i, int64_t j, int64_t*
 extern "C" int32_t gffm_mat_set_elem(gffm_mat* m, int64_t i, int64_t j, int64_t value) {
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (i < 0 || j < 0 || i >= m->rows || j >= m->cols) GFFM_FAIL(GFFM_ERR_INVALID, "BoundsError");
+  gffm_touch(m);
   return gffm_fill_view(m->ctx, sub_view(view_of(m), i, j, 1, 1), scalar_residue(value, m->N));
 }
 extern "C" int32_t gffm_mat_transpose(gffm_mat* dst, gffm_mat* src) {
   if (!dst || !src) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (dst->rows != src->cols || dst->cols != src->rows) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "transpose: sizes differ");
   if (src->rows * src->cols == 0) return GFFM_OK;
+  gffm_touch(dst);
   dim3 grid((unsigned)ceil_div(src->rows, 32), (unsigned)ceil_div(src->cols, 32));
   if (grid.y > 65535) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "transpose: too many columns");
   transpose_kernel<<<grid, dim3(32, 8), 0, src->ctx->stream>>>(dst->data, dst->ld, src->data, src->ld, src->rows, src->cols);
@@ -769,6 +805,7 @@ extern "C" int32_t gffm_gemv(gffm_mat* z, gffm_mat* A, gffm_mat* x, uint64_t R, 
   }
   if (P >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "gemv needs P < 2^32");
   if (A->rows == 0) return GFFM_OK;
+  gffm_touch(z);
   gffm_ctx* ctx = A->ctx;
   gemv_kernel<<<(unsigned)ceil_div(A->rows, 128), 256, 0, ctx->stream>>>(z->data, A->data, A->ld, x->data, (int)A->rows, (int)A->cols, make_modp(P));
   GFFM_LAUNCH_CHECK(ctx);
@@ -812,8 +849,11 @@ extern "C" int32_t gffm_gemm_block(gffm_mat* C, int64_t cr0, int64_t cc0, gffm_m
     P = C->N;
   }
   if (!R) R = A->N > B->N ? A->N : B->N;
-  return gffm_gemm_views(C->ctx, sub_view(view_of(C), cr0, cc0, m, n), sub_view(view_of(A), ar0, ac0, m, k),
-                         sub_view(view_of(B), br0, bc0, k, n), R, P, mode, algo);
+  gffm_touch(C);
+  // operands may reuse their cached 8-bit planes (C is excluded: it is being written, and may alias neither input)
+  MatView av = (A != C) ? cached_view_of(A) : view_of(A), bv = (B != C) ? cached_view_of(B) : view_of(B);
+  return gffm_gemm_views(C->ctx, sub_view(view_of(C), cr0, cc0, m, n), sub_view(av, ar0, ac0, m, k), sub_view(bv, br0, bc0, k, n), R, P,
+                         mode, algo);
 }
 
 extern "C" int32_t gffm_gemm(gffm_mat* C, gffm_mat* A, gffm_mat* B, uint64_t R, uint64_t P, int32_t mode, int32_t algo) {

@@ -58,6 +58,18 @@ struct gffm_ctx {
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+// Cached 8-bit operand planes of a matrix (built lazily by the first GEMM that needs them, reused while the
+// matrix is unchanged -- every writer bumps `version`).  One entry per operand role.
+struct gffm_plane_cache {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  bool valid = false;
+  uint64_t version = 0;
+  int mode = 0, nplanes = 0, balanced = 0;
+  uint64_t R = 0;
+  int64_t r0 = 0, c0 = 0, rows = 0, cols = 0, k0 = 0, kc = 0, Kp = 0, rowsP = 0;
+};
+
 struct gffm_mat {
   gffm_ctx* ctx = nullptr;
   uint32_t* data = nullptr;  // column-major, element (i,j) at data[j*ld + i]
@@ -67,7 +79,10 @@ struct gffm_mat {
   int32_t pad = GFFM_REF_PAD;
   uint64_t N = 0;
   bool owned = true;
+  uint64_t version = 1;         // bumped by every API call that writes the matrix
+  gffm_plane_cache cache[2];    // [0] = as A operand (transposed planes), [1] = as B operand
 };
+static inline void gffm_touch(gffm_mat* m) { m->version++; }
 
 int32_t gffm_ws_reserve(gffm_ctx* ctx, gffm_workspace* ws, size_t bytes);
 int32_t gffm_pinned_reserve(gffm_ctx* ctx, size_t bytes);
@@ -169,10 +184,18 @@ struct MatView {  // a sub-block of a column-major uint32 matrix
   uint32_t* p;
   int64_t ld;
   int64_t rows, cols;
+  gffm_mat* owner = nullptr;  // set only by the public GEMM entry points: enables the operand-plane cache
+  int64_t r0 = 0, c0 = 0;     // offset of this view inside owner
 };
 static inline MatView view_of(gffm_mat* m) { return MatView{m->data, m->ld, m->rows, m->cols}; }
 static inline MatView sub_view(const MatView& v, int64_t r0, int64_t c0, int64_t nr, int64_t nc) {
-  return MatView{v.p + c0 * v.ld + r0, v.ld, nr, nc};
+  return MatView{v.p + c0 * v.ld + r0, v.ld, nr, nc, v.owner, v.r0 + r0, v.c0 + c0};
+}
+// view that may use the plane cache of m (owned matrices only: external memory can change behind our back)
+static inline MatView cached_view_of(gffm_mat* m) {
+  MatView v = view_of(m);
+  if (m->owned) v.owner = m;
+  return v;
 }
 
 // C (op)= A*B mod P on views; inputs < R.  algo as in gffm.h.

@@ -556,6 +556,52 @@ int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2,
   return GFFM_OK;
 }
 
+// Returns the plane buffer for operand X (role 0 = A, 1 = B) and runs the split unless a valid cached copy exists.
+int32_t acquire_planes(gffm_ctx* ctx, int role, const MatView& X, const MatView* X2, int64_t k0, int64_t kc, int64_t Kp, int64_t rowsP,
+                       const SplitParams& sp, int balanced, uint64_t R, gffm_workspace* ws, uint8_t** out) {
+  const size_t bytes = (size_t)sp.nplanes * rowsP * Kp;
+  gffm_mat* own = X2 ? nullptr : X.owner;
+  if (own) {
+    gffm_plane_cache& c = own->cache[role];
+    const bool hit = c.valid && c.version == own->version && c.mode == sp.mode && c.nplanes == sp.nplanes && c.balanced == balanced &&
+                     c.R == R && c.r0 == X.r0 && c.c0 == X.c0 && c.rows == X.rows && c.cols == X.cols && c.k0 == k0 && c.kc == kc &&
+                     c.Kp == Kp && c.rowsP == rowsP;
+    if (hit) {
+      *out = (uint8_t*)c.ptr;
+      return GFFM_OK;
+    }
+    if (c.bytes < bytes) {
+      if (c.ptr) {
+        GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(c.ptr);
+        c.ptr = nullptr;
+        c.bytes = 0;
+      }
+      if (cudaMalloc(&c.ptr, bytes) != cudaSuccess) {  // no memory for a cache: fall back to the shared workspace
+        cudaGetLastError();
+        c.ptr = nullptr;
+        own = nullptr;
+      } else {
+        c.bytes = bytes;
+      }
+    }
+    if (own) {
+      c.valid = false;
+      GFFM_TRY(run_split(ctx, role == 0, X, X2, k0, kc, (uint8_t*)c.ptr, Kp, rowsP, sp));
+      c.valid = true;
+      c.version = own->version;
+      c.mode = sp.mode; c.nplanes = sp.nplanes; c.balanced = balanced; c.R = R;
+      c.r0 = X.r0; c.c0 = X.c0; c.rows = X.rows; c.cols = X.cols; c.k0 = k0; c.kc = kc; c.Kp = Kp; c.rowsP = rowsP;
+      *out = (uint8_t*)c.ptr;
+      return GFFM_OK;
+    }
+  }
+  GFFM_TRY(gffm_ws_reserve(ctx, ws, bytes));
+  GFFM_TRY(run_split(ctx, role == 0, X, X2, k0, kc, (uint8_t*)ws->ptr, Kp, rowsP, sp));
+  *out = (uint8_t*)ws->ptr;
+  return GFFM_OK;
+}
+
 inline void prof_mark(gffm_ctx* ctx, int idx) {
   if (ctx->profile && idx < 8) {
     cudaEventRecord(ctx->ev[idx], ctx->stream);
@@ -592,8 +638,7 @@ int32_t gffm_gemm_tc_limb_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView
   if (kmax > (1 << 20)) kmax = 1 << 20;
   const int64_t rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
   const int64_t kchunk_max = K < kmax ? round_up(K > 0 ? K : 1, 128) : kmax;
-  GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_planes_a, (size_t)L * rowsPA * kchunk_max));
-  GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_planes_b, (size_t)L * rowsPB * kchunk_max));
+  (void)kchunk_max;
   SplitParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.nplanes = L;
@@ -605,11 +650,10 @@ int32_t gffm_gemm_tc_limb_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView
   for (int64_t k0 = 0; k0 < K; k0 += kmax) {
     const int64_t kc = (K - k0) < kmax ? (K - k0) : kmax;
     const int64_t Kp = round_up(kc, 128);
-    uint8_t* pa = (uint8_t*)ctx->ws_planes_a.ptr;
-    uint8_t* pb = (uint8_t*)ctx->ws_planes_b.ptr;
+    uint8_t *pa = nullptr, *pb = nullptr;
     prof_mark(ctx, 0);
-    GFFM_TRY(run_split(ctx, true, A, A2, k0, kc, pa, Kp, rowsPA, sp));
-    GFFM_TRY(run_split(ctx, false, B, B2, k0, kc, pb, Kp, rowsPB, sp));
+    GFFM_TRY(acquire_planes(ctx, 0, A, A2, k0, kc, Kp, rowsPA, sp, 0, R, &ctx->ws_planes_a, &pa));
+    GFFM_TRY(acquire_planes(ctx, 1, B, B2, k0, kc, Kp, rowsPB, sp, 0, R, &ctx->ws_planes_b, &pb));
     prof_mark(ctx, 1);
     CUtensorMap tmA, tmB;
     GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, L, BM));
@@ -665,8 +709,6 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
       if (s >= MAX_MODS) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "dynamic range exceeds %d moduli", MAX_MODS);
       Mprod *= kModuli[s++];
     }
-    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_planes_a, (size_t)s * rowsPA * Kp));
-    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_planes_b, (size_t)s * rowsPB * Kp));
     const int64_t lde = round_up(m, 128);
     const int64_t e_plane = lde * n;
     GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_eplanes, (size_t)s * e_plane));
@@ -710,11 +752,10 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
       p.mods[t].off = (uint32_t)(((1ull << 31) + mt - 1) / mt * mt);
     }
     const SplitParams& spb = spa;
-    uint8_t* pa = (uint8_t*)ctx->ws_planes_a.ptr;
-    uint8_t* pb = (uint8_t*)ctx->ws_planes_b.ptr;
+    uint8_t *pa = nullptr, *pb = nullptr;
     prof_mark(ctx, 0);
-    GFFM_TRY(run_split(ctx, true, A, A2, k0, kc, pa, Kp, rowsPA, spa));
-    GFFM_TRY(run_split(ctx, false, B, B2, k0, kc, pb, Kp, rowsPB, spb));
+    GFFM_TRY(acquire_planes(ctx, 0, A, A2, k0, kc, Kp, rowsPA, spa, balanced ? 1 : 0, R, &ctx->ws_planes_a, &pa));
+    GFFM_TRY(acquire_planes(ctx, 1, B, B2, k0, kc, Kp, rowsPB, spb, balanced ? 1 : 0, R, &ctx->ws_planes_b, &pb));
     prof_mark(ctx, 1);
     CUtensorMap tmA, tmB;
     GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, s, BM));

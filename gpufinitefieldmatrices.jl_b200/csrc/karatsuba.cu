@@ -82,6 +82,8 @@ extern "C" int32_t gffm_kmat_mul(gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_
     GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "KMatMul!: inconsistent sizes");
   gffm_ctx* ctx = A1->ctx;
   if (m == 0 || n == 0) return GFFM_OK;
+  gffm_touch(C1);
+  gffm_touch(C2);
   if (k > 65536) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "KMatMul! with inner dimension above 65536");
   // temporaries: carry, P2, P3 (m x n, same leading dimension)
   const int64_t ldt = round_up(m, 32);
@@ -119,6 +121,8 @@ extern "C" int32_t gffm_kmat_ewise(int32_t op, gffm_mat* C1, gffm_mat* C2, gffm_
     GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "Karatsuba elementwise: sizes differ");
   if (C1->ld != C2->ld || A1->ld != A2->ld || (B1 && B1->ld != B2->ld)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "limb pairs must share a leading dimension");
   if (m * n == 0) return GFFM_OK;
+  gffm_touch(C1);
+  gffm_touch(C2);
   gffm_ctx* ctx = A1->ctx;
   const unsigned long long M = N1 * N2;
   long long sv = scalar % (long long)M;

@@ -1083,6 +1083,7 @@ extern "C" int32_t gffm_triinv(gffm_mat* A, int32_t upper, gffm_mat** out) {
 extern "C" int32_t gffm_apply_perm(gffm_mat* A, const int64_t* pairs, int64_t n_pairs, int32_t on_cols, int32_t inverse) {
   if (!A || (n_pairs > 0 && !pairs)) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (n_pairs <= 0) return GFFM_OK;
+  gffm_touch(A);
   gffm_ctx* ctx = A->ctx;
   const int64_t lim = on_cols ? A->cols : A->rows;
   for (int64_t e = 0; e < 2 * n_pairs; ++e)

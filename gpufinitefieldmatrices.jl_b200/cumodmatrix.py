@@ -235,6 +235,14 @@ class CuModMatrix:
     def __repr__(self):
         return f"{self.rows}x{self.cols} CuModMatrix{{{self.elem_type.name}}} modulo {self.N}"
 
+    def drop_cache(self):
+        """Frees the cached 8-bit operand planes (they are rebuilt by the next product that needs them)."""
+        capi.check(self.lib.gffm_mat_drop_cache(self.h))
+
+    def touch(self):
+        """Declare a modification made through the raw device pointer (invalidates the cached operand planes)."""
+        capi.check(self.lib.gffm_mat_touch(self.h))
+
     def checksum(self) -> int:
         v = C.c_uint64(0)
         capi.check(self.lib.gffm_mat_checksum(self.h, C.byref(v)))

@@ -161,6 +161,8 @@ end
 change_modulus(A::CuModArray, N::Integer) = change_modulus_no_alloc!(copy(A), N)   # :726-740
 transpose(A::CuModArray{T,2}) where {T} = (B = _create(T, 2, cols(A), rows(A), A.N; ctx=A.ctx); check(ccall((:gffm_mat_transpose, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), B.h, A.h)); B)
 isequal_device(A::CuModArray, B::CuModArray) = (r = Ref{Int32}(0); check(ccall((:gffm_mat_equal, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Int32}), A.h, B.h, r)); r[] != 0)
+touch!(A::CuModArray) = (check(ccall((:gffm_mat_touch, libgffm), Int32, (Ptr{Cvoid},), A.h)); A)
+drop_cache!(A::CuModArray) = (check(ccall((:gffm_mat_drop_cache, libgffm), Int32, (Ptr{Cvoid},), A.h)); A)
 checksum(A::CuModArray) = (r = Ref{UInt64}(0); check(ccall((:gffm_mat_checksum, libgffm), Int32, (Ptr{Cvoid}, Ref{UInt64}), A.h, r)); r[])
 
 # ---- elementwise (reference kernel_ops/*.jl) ----------------------------------------------------------------------

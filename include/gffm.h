@@ -108,6 +108,11 @@ int32_t gffm_mat_create(gffm_ctx* ctx, int64_t rows, int64_t cols, uint64_t N, i
  * device memory (not owned, no padding assumed) */
 int32_t gffm_mat_wrap(gffm_ctx* ctx, void* device_u32, int64_t rows, int64_t cols, int64_t ld, uint64_t N,
                       gffm_mat** out);
+/* A matrix used as a GEMM operand keeps its 8-bit operand planes cached until it is written; this frees them early
+ * (and makes the next product rebuild them -- bench.py uses it so that every timed step is a fresh product). */
+int32_t gffm_mat_drop_cache(gffm_mat* m);
+/* declare that the matrix was modified through its raw device pointer (gffm_mat_device_ptr): invalidates cached planes */
+int32_t gffm_mat_touch(gffm_mat* m);
 int32_t gffm_mat_destroy(gffm_mat* m); /* safe from a Julia finalizer thread: stream-ordered free, no callbacks */
 /* host ctor CuModMatrix(A, N; mod) (CuModMatrix.jl:53-99): convert (exactness checked -> GFFM_ERR_INEXACT),
  * copy into the top-left corner, floored mod when do_mod != 0 */

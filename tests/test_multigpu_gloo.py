@@ -1,0 +1,66 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: row-block sharding of A/C, pipelined column-panel
+broadcast of B.  The per-panel compute is injected (here: the CPU oracle, test-only) -- on GPUs it is gffm_gemm_block."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as O
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, m, k, n, N, npan, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import gffm_b200 as g
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mg = g.multigpu
+    r0, r1 = mg.row_block(m, world, rank)
+    A = O.synth_matrix(11, m, k, N)
+    A_shard = A[r0:r1]
+    ld = ((k + 31) // 32) * 32
+    Bt = torch.zeros((n, ld), dtype=torch.int32)          # column-major k x n, row j = column j
+    if rank == 0:
+        Bt[:, :k] = torch.from_numpy(O.synth_matrix(12, k, n, N).T.astype(np.int32).copy())
+    C_shard = np.zeros((r1 - r0, n), dtype=np.int64)
+
+    def gemm_panel(c0, c1):
+        Bp = Bt[c0:c1, :k].numpy().T.astype(np.int64)
+        C_shard[:, c0:c1] = O.matmul_mod(A_shard, Bp, N)
+
+    mg.pipelined_broadcast_matmul(dist, Bt, mg.col_panels(n, npan), gemm_panel, src=0)
+    np.save(os.path.join(out_dir, f"c_{rank}.npy"), C_shard)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m,k,n,N,npan", [(70, 50, 90, 33554393, 4), (5, 9, 3, 11, 8)])
+def test_sharded_matmul_world2(tmp_path, m, k, n, N, npan):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, m, k, n, N, npan, str(tmp_path)), nprocs=world, join=True)
+    C = np.concatenate([np.load(tmp_path / f"c_{r}.npy") for r in range(world)], axis=0)
+    A = O.synth_matrix(11, m, k, N); B = O.synth_matrix(12, k, n, N)
+    assert np.array_equal(C, O.matmul_mod(A, B, N))
+
+
+def test_partition_helpers():
+    import gffm_b200 as g
+    mg = g.multigpu
+    for m in (0, 1, 7, 16384, 16385):
+        for world in (1, 2, 3, 8):
+            blocks = [mg.row_block(m, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == m
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+    for n in (1, 5, 16384):
+        for p in (1, 3, 8, 100):
+            pans = mg.col_panels(n, p)
+            assert pans[0][0] == 0 and pans[-1][1] == n and all(a[1] == b[0] for a, b in zip(pans, pans[1:]))
