@@ -291,13 +291,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------
 struct SplitParams {
   int nplanes;          // planes written per call
-  int mode;             // 0 = positional limb p -> (x >> 8p) & 255 ; 1 = RNS residues
+  int mode;             // 0 = positional limb p -> (x >> 8p) & 255 ; 1 = RNS residues (generic) ; 2 = RNS fast path (R <= 2^27)
   uint32_t R;           // RNS: input bound (for balancing), 0 = unbalanced
   uint32_t half;        // RNS: values > half are shifted by -R
   uint32_t m[MAX_MODS], mu[MAX_MODS];
   uint32_t cneg[MAX_MODS];  // (-R) mod m
-  uint32_t h[MAX_MODS];     // (m+1)/2 : residues >= h are stored as r - m
-  uint32_t badj[MAX_MODS];  // 256 - m : low byte of (r - m) is r + 256 - m
+  // fast path: v = (hi << 13) + lo (hi arithmetic), y = hi*c13 + lo + off in [0, 2^24) -> exact magic division
+  uint32_t c13[MAX_MODS];   // 2^13 mod m
+  uint32_t off[MAX_MODS];   // multiple of m, >= 2^14 * 256
+  uint32_t mu1[MAX_MODS];   // floor(2^32/m) + 1
 };
 
 __device__ __forceinline__ uint32_t small_mod(uint32_t a, uint32_t m, uint32_t mu) {
@@ -306,7 +308,8 @@ __device__ __forceinline__ uint32_t small_mod(uint32_t a, uint32_t m, uint32_t m
   return r;
 }
 
-// one 8-bit digit of x for plane pl: positional byte, or balanced residue mod m_pl as two's-complement int8
+// one 8-bit digit of x for plane pl: positional byte, or a residue mod m_pl as two's-complement int8 in [-128, 127]
+// (any representative of the class in that range is valid for the signed-int8 MMA; |b| <= 128 either way)
 __device__ __forceinline__ uint32_t encode_plane(uint32_t x, bool neg, int pl, const SplitParams& sp) {
   if (sp.mode == 0) return (x >> (8 * pl)) & 255u;
   const uint32_t m = sp.m[pl];
@@ -315,42 +318,69 @@ __device__ __forceinline__ uint32_t encode_plane(uint32_t x, bool neg, int pl, c
     r += sp.cneg[pl];
     if (r >= m) r -= m;
   }
-  return (r >= sp.h[pl] ? r + sp.badj[pl] : r) & 255u;
+  return (r >= 128u ? r - m : r) & 255u;
 }
 
-// B operand (k x n column-major, K contiguous already): thread = 4 consecutive k of one column j; a warp reads
-// 512 contiguous bytes and writes 128 contiguous bytes per plane.
+// fast RNS digit: v = x or x - R as a signed 32-bit value with |v| <= 2^27, pre-split as hi = v >> 13, lo = v & 8191
+__device__ __forceinline__ uint32_t encode_fast(int hi, uint32_t lo, uint32_t c13, uint32_t off, uint32_t mu1, uint32_t m) {
+  const uint32_t y = (uint32_t)(hi * (int)c13) + (lo + off);   // in [0, 2^24)
+  const uint32_t r = y - __umulhi(y, mu1) * m;                // exact: r in [0, m)
+  return (r >= 128u ? r - m : r) & 255u;
+}
+
+// B operand (k x n column-major, K contiguous already): thread = 8 consecutive k of one column j; a warp reads 1 KiB
+// and writes 256 contiguous bytes per plane.
 // Optional second source (Karatsuba prologue fusion, reference KaratsubaKernels.jl:129-139): x = src + src2.
 __global__ void __launch_bounds__(128)
 split_b_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2, int K, int ncols,
                uint8_t* __restrict__ planes, int64_t Kp, int64_t rowsP, const __grid_constant__ SplitParams sp) {
-  const int64_t k4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 k
+  const int64_t k8 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const int j = blockIdx.y;
-  if (k4 * 4 >= Kp || j >= ncols) return;
-  uint32_t x[4];
-  const uint32_t* col = src + (int64_t)j * ld + k4 * 4;
-  if (k4 * 4 + 3 < K && ((reinterpret_cast<uintptr_t>(col) & 15) == 0)) {
-    const uint4 v = *reinterpret_cast<const uint4*>(col);
-    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  if (k8 >= Kp || j >= ncols) return;
+  uint32_t x[8];
+  const uint32_t* col = src + (int64_t)j * ld + k8;
+  if (k8 + 7 < K && ((reinterpret_cast<uintptr_t>(col) & 15) == 0)) {
+    const uint4 v0 = reinterpret_cast<const uint4*>(col)[0], v1 = reinterpret_cast<const uint4*>(col)[1];
+    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
   } else {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) x[t] = (k4 * 4 + t < K) ? col[t] : 0u;
+    for (int t = 0; t < 8; ++t) x[t] = (k8 + t < K) ? col[t] : 0u;
   }
   if (src2) {
-    const uint32_t* col2 = src2 + (int64_t)j * ld2 + k4 * 4;
+    const uint32_t* col2 = src2 + (int64_t)j * ld2 + k8;
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-      if (k4 * 4 + t < K) x[t] += col2[t];
+    for (int t = 0; t < 8; ++t)
+      if (k8 + t < K) x[t] += col2[t];
   }
-  bool neg[4];
+  uint8_t* out = planes + (int64_t)j * Kp + k8;
+  const int64_t pstride = rowsP * Kp;
+  if (sp.mode == 2) {
+    int hi[8];
+    uint32_t lo[8];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) neg[t] = sp.R && x[t] > sp.half;
-  uint8_t* out = planes + (int64_t)j * Kp + k4 * 4;
-  for (int pl = 0; pl < sp.nplanes; ++pl) {
-    uint32_t w = 0;
+    for (int t = 0; t < 8; ++t) {
+      const int v = (sp.R && x[t] > sp.half) ? (int)(x[t] - sp.R) : (int)x[t];
+      hi[t] = v >> 13;
+      lo[t] = (uint32_t)v & 8191u;
+    }
+    for (int pl = 0; pl < sp.nplanes; ++pl) {
+      const uint32_t c13 = sp.c13[pl], off = sp.off[pl], mu1 = sp.mu1[pl], m = sp.m[pl];
+      uint32_t w0 = 0, w1 = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) w |= encode_plane(x[t], neg[t], pl, sp) << (8 * t);
-    *reinterpret_cast<uint32_t*>(out + (int64_t)pl * rowsP * Kp) = w;
+      for (int t = 0; t < 4; ++t) w0 |= encode_fast(hi[t], lo[t], c13, off, mu1, m) << (8 * t);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) w1 |= encode_fast(hi[4 + t], lo[4 + t], c13, off, mu1, m) << (8 * t);
+      *reinterpret_cast<uint2*>(out + pl * pstride) = make_uint2(w0, w1);
+    }
+  } else {
+    for (int pl = 0; pl < sp.nplanes; ++pl) {
+      uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) w0 |= encode_plane(x[t], sp.R && x[t] > sp.half, pl, sp) << (8 * t);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) w1 |= encode_plane(x[4 + t], sp.R && x[4 + t] > sp.half, pl, sp) << (8 * t);
+      *reinterpret_cast<uint2*>(out + pl * pstride) = make_uint2(w0, w1);
+    }
   }
 }
 
@@ -387,12 +417,24 @@ split_a_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ sr
 #pragma unroll
     for (int t = 0; t < 16; ++t) negmask |= (x[t] > sp.half ? 1u : 0u) << t;
   }
+  if (sp.mode == 2) {  // pre-split once per element: x[t] <- lo | hi << 13 is just v; keep v and derive hi/lo on the fly
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if ((negmask >> t) & 1u) x[t] -= sp.R;
+  }
+  uint8_t* tbase = &tile[0][lane * SPLIT_A_PITCH + w];
   for (int p0 = 0; p0 < sp.nplanes; p0 += SPLIT_A_GROUP) {
     const int np = min(SPLIT_A_GROUP, sp.nplanes - p0);
     for (int q = 0; q < np; ++q) {
+      uint8_t* tq = tbase + q * (32 * SPLIT_A_PITCH);
+      if (sp.mode == 2) {
+        const uint32_t c13 = sp.c13[p0 + q], off = sp.off[p0 + q], mu1 = sp.mu1[p0 + q], m = sp.m[p0 + q];
 #pragma unroll
-      for (int t = 0; t < 16; ++t)
-        tile[q][lane * SPLIT_A_PITCH + w + 8 * t] = (uint8_t)encode_plane(x[t], (negmask >> t) & 1u, p0 + q, sp);
+        for (int t = 0; t < 16; ++t) tq[8 * t] = (uint8_t)encode_fast((int)x[t] >> 13, x[t] & 8191u, c13, off, mu1, m);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) tq[8 * t] = (uint8_t)encode_plane(x[t], (negmask >> t) & 1u, p0 + q, sp);
+      }
     }
     __syncthreads();
     // write-out: np planes x 32 rows x 32 words; a warp stores one 128-byte row segment per instruction
@@ -410,21 +452,23 @@ split_a_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ sr
 // ---------------------------------------------------------------------------------------------------
 // CRT epilogue kernel (RNS): planes e_t = (x * (M/m_t)^-1) mod m_t  ->  x mod P, fused C +/-= and the Karatsuba
 // carry split (reference KaratsubaKernels.jl:141-158: C1 = cc mod N1, carry = cc div N1).
-//   x = S - round(S/M) * M,  S = sum_t e_t * (M/m_t);   frac(S/M) tracked in 2^-56 fixed point.
-// HBM-bound: each thread handles 4 consecutive rows (one 32-bit load per plane, all planes in flight, one 128-bit
-// store), a warp moves 128 B per plane and 512 B of C per instruction.
+//   x = S - round(S/M) * M,  S = sum_t e_t * (M/m_t);  frac(S/M) = sum_t e_t / m_t tracked in 2^-32 fixed point
+//   (the moduli are chosen with |x|/M < 1/2 - 2^-7, so 20 bits of fraction are ample).
+// HBM-bound by design: each thread handles 4 consecutive rows (one 32-bit load per plane, all planes in flight, one
+// 128-bit store); per (element, modulus) the work is one byte extract and two 32x32+64 multiply-adds.
 // ---------------------------------------------------------------------------------------------------
 struct CrtParams {
   int s;
   int mode;
   int balanced;
   ModP modP;
-  uint64_t w[MAX_MODS];  // (M/m_t) mod P
-  uint64_t f[MAX_MODS];  // floor(2^56 / m_t)
-  uint64_t W;            // M mod P
-  uint64_t kara_N1;      // != 0: C <- (x mod P) mod N1, hi <- (x mod P) div N1
+  uint64_t w[MAX_MODS];   // (M/m_t) mod P
+  uint32_t f[MAX_MODS];   // floor(2^32 / m_t)  (m_t >= 2)
+  uint64_t Wq[MAX_MODS + 2];  // (-q * M) mod P for q = 0..s
+  uint64_t kara_N1;       // != 0: C <- (x mod P) mod N1, hi <- (x mod P) div N1
 };
 
+template <bool WIDE>  // WIDE: P >= 2^32 (Karatsuba P1), 64-bit weights
 __global__ void __launch_bounds__(256)
 crt_kernel(const uint8_t* __restrict__ E, int64_t lde, int64_t plane_stride, int m, int n, uint32_t* __restrict__ C,
            int64_t ldc, uint32_t* __restrict__ hi, int64_t ldhi, const __grid_constant__ CrtParams cp) {
@@ -439,24 +483,32 @@ crt_kernel(const uint8_t* __restrict__ E, int64_t lde, int64_t plane_stride, int
 #pragma unroll
   for (int t = 0; t < MAX_MODS; ++t) {
     if (t < cp.s) {
-      const uint64_t wt = cp.w[t], ft = cp.f[t];
+      const uint32_t ft = cp.f[t];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint64_t et = (ew[t] >> (8 * q)) & 255u;
-        acc[q] += et * wt;
-        F[q] += et * ft;
+        const uint32_t et = __byte_perm(ew[t], 0, 0x4440 + q);
+        if constexpr (WIDE) acc[q] += (uint64_t)et * cp.w[t];
+        else acc[q] += (uint64_t)et * (uint32_t)cp.w[t];
+        F[q] += (uint64_t)et * ft;
       }
     }
   }
   uint32_t r32[4];
   uint32_t* dst = C + (int64_t)j * ldc + i4;
   const int nv = min(4, m - i4);
+  const uint64_t rnd = cp.balanced ? ((1ull << 31) + (1ull << 12)) : (1ull << 12);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const uint64_t qq = cp.balanced ? ((F[q] + (1ull << 55) + (1ull << 12)) >> 56) : ((F[q] + (1ull << 12)) >> 56);
-    const uint64_t t1 = mod_u64(acc[q], cp.modP);
-    const uint64_t t2 = mod_u64(qq * cp.W, cp.modP);
-    const uint64_t r = t1 >= t2 ? t1 - t2 : t1 + cp.modP.P - t2;
+    const uint32_t qq = (uint32_t)((F[q] + rnd) >> 32);
+    uint64_t r;
+    if constexpr (WIDE) {
+      const uint64_t t1 = mod_u64(acc[q], cp.modP);
+      const uint64_t t2 = cp.Wq[qq];
+      r = t1 + t2;
+      if (r >= cp.modP.P) r -= cp.modP.P;
+    } else {
+      r = mod_u64(acc[q] + cp.Wq[qq], cp.modP);
+    }
     if (cp.kara_N1) {
       if (q < nv) hi[(int64_t)j * ldhi + i4 + q] = (uint32_t)(r / cp.kara_N1);
       r32[q] = (uint32_t)(r % cp.kara_N1);
@@ -549,7 +601,7 @@ int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2,
     // B is K x n: K along rows of the view
     const uint32_t* s = X.p + k_off;
     const uint32_t* s2 = X2 ? X2->p + k_off : nullptr;
-    dim3 grid((unsigned)ceil_div(Kp / 4, 128), (unsigned)X.cols);
+    dim3 grid((unsigned)ceil_div(Kp / 8, 128), (unsigned)X.cols);
     split_b_kernel<<<grid, 128, 0, ctx->stream>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)X.cols, planes, Kp, rowsP, sp);
   }
   GFFM_LAUNCH_CHECK(ctx);
@@ -702,7 +754,7 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     const int64_t Kp = round_up(kc, 128);
     // number of moduli: M > 2*X*(1+2^-16) (balanced, |x| <= X = kc*floor(R/2)^2) or M > X*(1+2^-16) (X = kc*(R-1)^2)
     unsigned __int128 X = balanced ? (unsigned __int128)kc * (R / 2) * (R / 2) * 2 : (unsigned __int128)kc * (R - 1) * (R - 1);
-    X += (X >> 16) + 2;
+    X += (X >> 6) + 2;  // |x|/M < 1/2 - 2^-7: the CRT rounding decision has a wide margin
     unsigned __int128 Mprod = 1;
     int s = 0;
     while (Mprod <= X) {
@@ -719,6 +771,7 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     spa.mode = 1;
     spa.R = balanced ? (uint32_t)R : 0;
     spa.half = (uint32_t)(R / 2);
+    if (R <= (1ull << 27)) spa.mode = 2;  // fast residue path: |v| <= 2^27, y < 2^24
     CrtParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.s = s;
@@ -726,7 +779,10 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     cp.balanced = balanced ? 1 : 0;
     cp.modP = make_modp(P);
     cp.kara_N1 = kara_hi ? kara_N1 : 0;
-    cp.W = (uint64_t)(Mprod % P);
+    {
+      const uint64_t Wm = (uint64_t)(Mprod % P);
+      for (int q = 0; q <= s + 1 && q < MAX_MODS + 2; ++q) cp.Wq[q] = (uint64_t)((P - (uint64_t)(((unsigned __int128)q * Wm) % P)) % P);
+    }
     GemmParams p;
     memset(&p, 0, sizeof(p));
     for (int t = 0; t < s; ++t) {
@@ -742,11 +798,12 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
       spa.m[t] = mt;
       spa.mu[t] = (uint32_t)((1ull << 32) / mt);
       spa.cneg[t] = (uint32_t)((mt - (R % mt)) % mt);
-      spa.h[t] = (mt + 1) / 2;
-      spa.badj[t] = 256 - mt;
+      spa.c13[t] = 8192u % mt;
+      spa.off[t] = (uint32_t)((((1u << 22) + mt - 1) / mt) * mt);
+      spa.mu1[t] = (uint32_t)((1ull << 32) / mt) + 1u;
       p.mods[t].u = (uint32_t)ut;
       cp.w[t] = (uint64_t)others_mod_P;
-      cp.f[t] = (1ull << 56) / mt;
+      cp.f[t] = (uint32_t)((1ull << 32) / mt);
       p.mods[t].m = mt;
       p.mods[t].mu = (uint32_t)((1ull << 32) / mt);
       p.mods[t].off = (uint32_t)(((1ull << 31) + mt - 1) / mt * mt);
@@ -772,8 +829,12 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p));
     prof_mark(ctx, 2);
     dim3 grid((unsigned)ceil_div(m, 1024), (unsigned)n);
-    crt_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, (int)m, (int)n, Cv.p, Cv.ld,
-                                              kara_hi, ldhi, cp);
+    if (P >= (1ull << 32))
+      crt_kernel<true><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, (int)m, (int)n, Cv.p, Cv.ld,
+                                                      kara_hi, ldhi, cp);
+    else
+      crt_kernel<false><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, (int)m, (int)n, Cv.p, Cv.ld,
+                                                       kara_hi, ldhi, cp);
     GFFM_LAUNCH_CHECK(ctx);
     prof_mark(ctx, 3);
     if (kara_hi && K > kmax) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "Karatsuba carry split with K > 65536");
