@@ -73,6 +73,9 @@ extern "C" int32_t gffm_destroy(gffm_ctx* ctx) {
   ws_free(&ctx->ws_misc2);
   ws_free(&ctx->ws_invtab);
   ws_free(&ctx->ws_scratch);
+  ws_free(&ctx->ws_host);
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   if (ctx->ws_pinned.ptr) cudaFreeHost(ctx->ws_pinned.ptr);
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

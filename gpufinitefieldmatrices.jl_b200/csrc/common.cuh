@@ -49,7 +49,8 @@ struct gffm_ctx {
   bool own_stream = false;
   int64_t launches = 0;
   // grow-only scratch buffers (stream-ordered reuse)
-  gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned, ws_invtab, ws_scratch;
+  gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned, ws_invtab, ws_scratch, ws_host;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of the pipelined host GEMM
   uint64_t inv_table_N = 0;
   std::vector<double> timings;
   std::vector<double> elim_timings;  // {inner panels, U12 = L11^-1 A12, trailing GEMM} ms of the last profiled elimination

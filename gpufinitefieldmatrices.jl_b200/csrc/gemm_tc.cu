@@ -42,6 +42,7 @@ struct GemmParams {
   int m, n;
   int num_kb;
   int num_m_blk, num_n_blk, batches;
+  int mb0, nb0;  // tile offsets (in blocks) into the operand planes: sub-problems of a larger plane set (pipelined host GEMM)
   // positional epilogue
   uint32_t* C;
   int64_t ldc;
@@ -154,10 +155,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* st = smem + stage * C::STAGE_BYTES;
 #pragma unroll
           for (int a = 0; a < S::PA; ++a)
-            tc::tma_load_3d(st + a * C::A_TILE, &tmA, &full_bar[stage], kb * BK_BYTES, mb * BM, z * S::PA + a);
+            tc::tma_load_3d(st + a * C::A_TILE, &tmA, &full_bar[stage], kb * BK_BYTES, (mb + p.mb0) * BM, z * S::PA + a);
 #pragma unroll
           for (int b = 0; b < S::PB; ++b)
-            tc::tma_load_3d(st + S::PA * C::A_TILE + b * C::B_TILE, &tmB, &full_bar[stage], kb * BK_BYTES, nb * S::BN,
+            tc::tma_load_3d(st + S::PA * C::A_TILE + b * C::B_TILE, &tmB, &full_bar[stage], kb * BK_BYTES, (nb + p.nb0) * S::BN,
                             z * S::PB + b);
           if (++stage == S::STAGES) {
             stage = 0;
@@ -575,7 +576,7 @@ int32_t make_plane_tmap(CUtensorMap* tm, void* planes, int64_t Kp, int64_t rowsP
 }
 
 template <class S>
-int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st = nullptr) {
   using C = Cfg<S>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -584,7 +585,7 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   }
   const int total = p.batches * p.num_m_blk * p.num_n_blk;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  gemm_tc_kernel<S><<<grid, 192, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<S><<<grid, 192, C::SMEM_BYTES, st ? st : ctx->stream>>>(tmA, tmB, p);
   GFFM_LAUNCH_CHECK(ctx);
   return GFFM_OK;
 }
@@ -663,6 +664,93 @@ inline void prof_mark(gffm_ctx* ctx, int idx) {
 
 const uint32_t kModuli[MAX_MODS] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197};
 
+// All per-modulus constants of one RNS product with inner dimension kc (<= 65536), inputs < R, result mod P.
+struct RnsPlan {
+  int s = 0;
+  SplitParams sp;
+  CrtParams cp;
+  RnsModDev mods[MAX_MODS];
+};
+
+int32_t make_rns_plan(int64_t kc, uint64_t R, uint64_t P, bool balanced, int crt_mode, uint64_t kara_N1, RnsPlan* plan) {
+  // number of moduli: M > 2*X (balanced, |x| <= X = kc*floor(R/2)^2) or M > X (X = kc*(R-1)^2), with margin
+  unsigned __int128 X = balanced ? (unsigned __int128)kc * (R / 2) * (R / 2) * 2 : (unsigned __int128)kc * (R - 1) * (R - 1);
+  X += (X >> 6) + 2;  // |x|/M < 1/2 - 2^-7: the CRT rounding decision has a wide margin
+  unsigned __int128 Mprod = 1;
+  int s = 0;
+  while (Mprod <= X) {
+    if (s >= MAX_MODS) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "dynamic range exceeds %d moduli", MAX_MODS);
+    Mprod *= kModuli[s++];
+  }
+  plan->s = s;
+  SplitParams& spa = plan->sp;
+  memset(&spa, 0, sizeof(spa));
+  spa.nplanes = s;
+  spa.mode = 1;
+  spa.R = balanced ? (uint32_t)R : 0;
+  spa.half = (uint32_t)(R / 2);
+  if (R <= (1ull << 27)) spa.mode = 2;  // fast residue path: |v| <= 2^27, y < 2^24
+  CrtParams& cp = plan->cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.s = s;
+  cp.mode = crt_mode;
+  cp.balanced = balanced ? 1 : 0;
+  cp.modP = make_modp(P);
+  cp.kara_N1 = kara_N1;
+  {
+    const uint64_t Wm = (uint64_t)(Mprod % P);
+    for (int q = 0; q <= s + 1 && q < MAX_MODS + 2; ++q) cp.Wq[q] = (uint64_t)((P - (uint64_t)(((unsigned __int128)q * Wm) % P)) % P);
+  }
+  memset(plan->mods, 0, sizeof(plan->mods));
+  for (int t = 0; t < s; ++t) {
+    const uint32_t mt = kModuli[t];
+    uint64_t others_mod_mt = 1;
+    unsigned __int128 others_mod_P = 1;
+    for (int u = 0; u < s; ++u) {
+      if (u == t) continue;
+      others_mod_mt = (others_mod_mt * (kModuli[u] % mt)) % mt;
+      others_mod_P = (others_mod_P * kModuli[u]) % P;
+    }
+    const uint64_t ut = modinv_u64(others_mod_mt, mt);
+    spa.m[t] = mt;
+    spa.mu[t] = (uint32_t)((1ull << 32) / mt);
+    spa.cneg[t] = (uint32_t)((mt - (R % mt)) % mt);
+    spa.c13[t] = 8192u % mt;
+    spa.off[t] = (uint32_t)((((1u << 22) + mt - 1) / mt) * mt);
+    spa.mu1[t] = (uint32_t)((1ull << 32) / mt) + 1u;
+    cp.w[t] = (uint64_t)others_mod_P;
+    cp.f[t] = (uint32_t)((1ull << 32) / mt);
+    plan->mods[t].m = mt;
+    plan->mods[t].mu = (uint32_t)((1ull << 32) / mt);
+    plan->mods[t].off = (uint32_t)(((1ull << 31) + mt - 1) / mt * mt);
+    plan->mods[t].u = (uint32_t)ut;
+  }
+  return GFFM_OK;
+}
+
+int32_t launch_crt(gffm_ctx* ctx, cudaStream_t st, const CrtParams& cp, const uint8_t* E, int64_t lde, int64_t e_plane, int64_t m, int64_t n,
+                   uint32_t* C, int64_t ldc, uint32_t* hi, int64_t ldhi) {
+  dim3 grid((unsigned)ceil_div(m, 1024), (unsigned)n);
+  if (cp.modP.P >= (1ull << 32)) crt_kernel<true><<<grid, 256, 0, st>>>(E, lde, e_plane, (int)m, (int)n, C, ldc, hi, ldhi, cp);
+  else crt_kernel<false><<<grid, 256, 0, st>>>(E, lde, e_plane, (int)m, (int)n, C, ldc, hi, ldhi, cp);
+  GFFM_LAUNCH_CHECK(ctx);
+  return GFFM_OK;
+}
+
+// largest K of one limb launch such that no int32 accumulator can exceed 2^31 (exactness budget)
+int64_t limb_kmax(uint64_t R) {
+  const int L = R <= 256 ? 1 : 2;
+  const uint64_t top = (R - 1) >> (8 * (L - 1));
+  const uint64_t lo = L == 1 ? 0 : 255;
+  uint64_t worst = L == 1 ? top * top : (2 * lo * top > lo * lo ? 2 * lo * top : lo * lo);
+  if (L == 2 && top * top > worst) worst = top * top;
+  if (worst == 0) worst = 1;
+  int64_t kmax = (int64_t)(((1ull << 31) - 1) / worst);
+  kmax = kmax / 128 * 128;
+  if (kmax > (1 << 20)) kmax = 1 << 20;
+  return kmax;
+}
+
 }  // namespace
 
 bool gffm_tc_available(gffm_ctx* ctx) {
@@ -678,16 +766,8 @@ int32_t gffm_gemm_tc_limb_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView
   if (R > 65536 || P >= (1ull << 32) || P == 0) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "limb GEMM needs R <= 2^16 and P < 2^32");
   const int L = R <= 256 ? 1 : 2;
   const int BN = L == 1 ? SchemeL1::BN : SchemeL2::BN;
-  // largest K chunk whose worst accumulator stays below 2^31 (exactness budget)
-  const uint64_t top = (R - 1) >> (8 * (L - 1));
-  const uint64_t lo = L == 1 ? 0 : 255;
-  uint64_t worst = L == 1 ? top * top : (2 * lo * top > lo * lo ? 2 * lo * top : lo * lo);
-  if (L == 2 && top * top > worst) worst = top * top;
-  if (worst == 0) worst = 1;
-  int64_t kmax = (int64_t)(((1ull << 31) - 1) / worst);
-  kmax = kmax / 128 * 128;
+  const int64_t kmax = limb_kmax(R);
   if (kmax < 128) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "accumulator budget");
-  if (kmax > (1 << 20)) kmax = 1 << 20;
   const int64_t rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
   const int64_t kchunk_max = K < kmax ? round_up(K > 0 ? K : 1, 128) : kmax;
   (void)kchunk_max;
@@ -752,62 +832,18 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
   for (int64_t k0 = 0; k0 < K; k0 += kmax) {
     const int64_t kc = (K - k0) < kmax ? (K - k0) : kmax;
     const int64_t Kp = round_up(kc, 128);
-    // number of moduli: M > 2*X*(1+2^-16) (balanced, |x| <= X = kc*floor(R/2)^2) or M > X*(1+2^-16) (X = kc*(R-1)^2)
-    unsigned __int128 X = balanced ? (unsigned __int128)kc * (R / 2) * (R / 2) * 2 : (unsigned __int128)kc * (R - 1) * (R - 1);
-    X += (X >> 6) + 2;  // |x|/M < 1/2 - 2^-7: the CRT rounding decision has a wide margin
-    unsigned __int128 Mprod = 1;
-    int s = 0;
-    while (Mprod <= X) {
-      if (s >= MAX_MODS) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "dynamic range exceeds %d moduli", MAX_MODS);
-      Mprod *= kModuli[s++];
-    }
+    RnsPlan plan;
+    GFFM_TRY(make_rns_plan(kc, R, P, balanced, (k0 == 0) ? mode : (mode == GFFM_GEMM_SUB ? GFFM_GEMM_SUB : GFFM_GEMM_ADD), kara_hi ? kara_N1 : 0,
+                           &plan));
+    const int s = plan.s;
+    const SplitParams& spa = plan.sp;
+    const CrtParams& cp = plan.cp;
     const int64_t lde = round_up(m, 128);
     const int64_t e_plane = lde * n;
     GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_eplanes, (size_t)s * e_plane));
-    // per-modulus constants
-    SplitParams spa;
-    memset(&spa, 0, sizeof(spa));
-    spa.nplanes = s;
-    spa.mode = 1;
-    spa.R = balanced ? (uint32_t)R : 0;
-    spa.half = (uint32_t)(R / 2);
-    if (R <= (1ull << 27)) spa.mode = 2;  // fast residue path: |v| <= 2^27, y < 2^24
-    CrtParams cp;
-    memset(&cp, 0, sizeof(cp));
-    cp.s = s;
-    cp.mode = (k0 == 0) ? mode : (mode == GFFM_GEMM_SUB ? GFFM_GEMM_SUB : GFFM_GEMM_ADD);
-    cp.balanced = balanced ? 1 : 0;
-    cp.modP = make_modp(P);
-    cp.kara_N1 = kara_hi ? kara_N1 : 0;
-    {
-      const uint64_t Wm = (uint64_t)(Mprod % P);
-      for (int q = 0; q <= s + 1 && q < MAX_MODS + 2; ++q) cp.Wq[q] = (uint64_t)((P - (uint64_t)(((unsigned __int128)q * Wm) % P)) % P);
-    }
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    for (int t = 0; t < s; ++t) {
-      const uint32_t mt = kModuli[t];
-      uint64_t others_mod_mt = 1;
-      unsigned __int128 others_mod_P = 1;
-      for (int u = 0; u < s; ++u) {
-        if (u == t) continue;
-        others_mod_mt = (others_mod_mt * (kModuli[u] % mt)) % mt;
-        others_mod_P = (others_mod_P * kModuli[u]) % P;
-      }
-      const uint64_t ut = modinv_u64(others_mod_mt, mt);
-      spa.m[t] = mt;
-      spa.mu[t] = (uint32_t)((1ull << 32) / mt);
-      spa.cneg[t] = (uint32_t)((mt - (R % mt)) % mt);
-      spa.c13[t] = 8192u % mt;
-      spa.off[t] = (uint32_t)((((1u << 22) + mt - 1) / mt) * mt);
-      spa.mu1[t] = (uint32_t)((1ull << 32) / mt) + 1u;
-      p.mods[t].u = (uint32_t)ut;
-      cp.w[t] = (uint64_t)others_mod_P;
-      cp.f[t] = (uint32_t)((1ull << 32) / mt);
-      p.mods[t].m = mt;
-      p.mods[t].mu = (uint32_t)((1ull << 32) / mt);
-      p.mods[t].off = (uint32_t)(((1ull << 31) + mt - 1) / mt * mt);
-    }
+    memcpy(p.mods, plan.mods, sizeof(p.mods));
     const SplitParams& spb = spa;
     uint8_t *pa = nullptr, *pb = nullptr;
     prof_mark(ctx, 0);
@@ -828,14 +864,7 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     p.e_plane_stride = e_plane;
     GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p));
     prof_mark(ctx, 2);
-    dim3 grid((unsigned)ceil_div(m, 1024), (unsigned)n);
-    if (P >= (1ull << 32))
-      crt_kernel<true><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, (int)m, (int)n, Cv.p, Cv.ld,
-                                                      kara_hi, ldhi, cp);
-    else
-      crt_kernel<false><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, (int)m, (int)n, Cv.p, Cv.ld,
-                                                       kara_hi, ldhi, cp);
-    GFFM_LAUNCH_CHECK(ctx);
+    GFFM_TRY(launch_crt(ctx, ctx->stream, cp, (const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, m, n, Cv.p, Cv.ld, kara_hi, ldhi));
     prof_mark(ctx, 3);
     if (kara_hi && K > kmax) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "Karatsuba carry split with K > 65536");
   }
@@ -845,4 +874,185 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
 int32_t gffm_gemm_tc_rns(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode, bool balanced,
                          uint32_t* kara_hi, uint64_t kara_N1) {
   return gffm_gemm_tc_rns_ex(ctx, C, A, nullptr, B, nullptr, R, P, mode, balanced, kara_hi, C.ld, kara_N1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gffm_gemm_host: C_host = A_host * B_host mod N straight from / to HOST buffers, fully pipelined.
+// Replaces the reference sequence CuModMatrix(A) ; CuModMatrix(B) ; mul!(C,A,B) ; Array(C)
+// (reference CuModMatrix.jl:53-99, :767-787, :256-261), where the three transfers and the product are serialised.
+// A is cut into row blocks and B into column panels; three streams run concurrently:
+//   H2D     A0 B0 B1 A1 B2 A2 ...                       (PCIe, one direction)
+//   compute mod + 8-bit plane split of each block as it lands, then every C tile (i,j) whose A_i and B_j are present:
+//           tcgen05 GEMM on the tile's sub-range of the plane set (+ CRT kernel for the RNS encoding)
+//   D2H     C tiles as they complete                    (PCIe, other direction)
+// so the host-visible time approaches max(H2D bytes / PCIe, GEMM time) instead of their sum.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+mod_inplace_kernel(uint32_t* __restrict__ X, int64_t ld, int64_t rows, int64_t cols, const __grid_constant__ ModP mp) {
+  const int64_t total = rows * cols;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = idx / rows, i = idx - j * rows;
+    uint32_t v = X[j * ld + i];
+    if (v >= mp.P) X[j * ld + i] = (uint32_t)mod_u64(v, mp);
+  }
+}
+}  // namespace
+
+extern "C" int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, const void* A_host, int64_t lda, const void* B_host,
+                                  int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t dtype, uint64_t N) {
+  if (!ctx || !C_host || !A_host || !B_host) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  if (m <= 0 || n <= 0 || k <= 0) GFFM_FAIL(GFFM_ERR_INVALID, "empty product");
+  if (lda < m || ldb < k || ldc < m) GFFM_FAIL(GFFM_ERR_INVALID, "leading dimension too small");
+  if (dtype != GFFM_U32) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "gffm_gemm_host takes uint32 residues (use upload/gemm/download for other host types)");
+  if (N < 2 || N >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "2 <= N < 2^32 required");
+  if (!gffm_tc_available(ctx)) GFFM_FAIL(GFFM_ERR_CUDA, "tensor-map encoder unavailable");
+  cudaSetDevice(ctx->device);
+  const bool rns = N > 65536;
+  const int L = N <= 256 ? 1 : 2;
+  const int64_t kmax = rns ? 65536 : limb_kmax(N);
+  if (k > kmax) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "inner dimension %lld exceeds one accumulation chunk (%lld) of the pipelined host GEMM", (long long)k, (long long)kmax);
+  const int BN = rns ? SchemeRNS::BN : (L == 1 ? SchemeL1::BN : SchemeL2::BN);
+  RnsPlan plan;
+  SplitParams sp;
+  int nplanes;
+  if (rns) {
+    GFFM_TRY(make_rns_plan(k, N, N, /*balanced=*/true, GFFM_GEMM_STORE, 0, &plan));
+    sp = plan.sp;
+    nplanes = plan.s;
+  } else {
+    memset(&sp, 0, sizeof(sp));
+    sp.nplanes = nplanes = L;
+    sp.mode = 0;
+  }
+  // block sizes: ~4x4 tiling for large products, single block for small ones
+  auto pick = [](int64_t extent, int64_t align) {
+    if (extent <= 2048) return round_up(extent, align);
+    int64_t b = round_up(ceil_div(extent, 4), align);
+    return b;
+  };
+  const int64_t bm = pick(m, BM), bn = pick(n, BN);
+  const int nbA = (int)ceil_div(m, bm), nbB = (int)ceil_div(n, bn);
+  const int64_t Kp = round_up(k, 128), rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
+  const int64_t ldA = round_up(m, 32), ldB = round_up(k, 32), ldC = round_up(m, 32), lde = round_up(m, 128);
+  const int64_t e_plane = lde * n;
+  // one workspace carved into dA, dB, dC, planesA, planesB, E
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off = (off + bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t oA = carve((size_t)ldA * k * 4), oB = carve((size_t)ldB * n * 4), oC = carve((size_t)ldC * n * 4);
+  const size_t oPA = carve((size_t)nplanes * rowsPA * Kp), oPB = carve((size_t)nplanes * rowsPB * Kp);
+  const size_t oE = rns ? carve((size_t)nplanes * e_plane) : 0;
+  GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_host, off));
+  char* base = (char*)ctx->ws_host.ptr;
+  uint32_t *dA = (uint32_t*)(base + oA), *dB = (uint32_t*)(base + oB), *dC = (uint32_t*)(base + oC);
+  uint8_t *pA = (uint8_t*)(base + oPA), *pB = (uint8_t*)(base + oPB), *E = (uint8_t*)(base + oE);
+  if (!ctx->s_h2d) {
+    GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+  }
+  cudaStream_t sc = ctx->stream, sh = ctx->s_h2d, sd = ctx->s_d2h;
+  std::vector<cudaEvent_t> evA(nbA), evB(nbB), evC((size_t)nbA * nbB);
+  for (auto& e : evA) GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : evB) GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : evC) GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaEvent_t ev0;
+  GFFM_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+  GFFM_CUDA(cudaEventRecord(ev0, sc));  // the workspace may still be in use by earlier work on the compute stream
+  GFFM_CUDA(cudaStreamWaitEvent(sh, ev0, 0));
+  GFFM_CUDA(cudaStreamWaitEvent(sd, ev0, 0));
+  CUtensorMap tmA, tmB;
+  GFFM_TRY(make_plane_tmap(&tmA, pA, Kp, rowsPA, nplanes, BM));
+  GFFM_TRY(make_plane_tmap(&tmB, pB, Kp, rowsPB, nplanes, BN));
+  const ModP mp = make_modp(N);
+  const int nblk_mod = ctx->num_sms * 8;
+  int32_t st = GFFM_OK;
+
+  auto upload_a = [&](int i) -> int32_t {
+    const int64_t i0 = i * bm, mi = std::min(bm, m - i0);
+    GFFM_CUDA(cudaMemcpy2DAsync(dA + i0, (size_t)ldA * 4, (const uint32_t*)A_host + i0, (size_t)lda * 4, (size_t)mi * 4, (size_t)k,
+                                cudaMemcpyHostToDevice, sh));
+    GFFM_CUDA(cudaEventRecord(evA[i], sh));
+    GFFM_CUDA(cudaStreamWaitEvent(sc, evA[i], 0));
+    mod_inplace_kernel<<<nblk_mod, 256, 0, sc>>>(dA + i0, ldA, mi, k, mp);
+    GFFM_LAUNCH_CHECK(ctx);
+    MatView v{dA + i0, ldA, mi, k};
+    return run_split(ctx, true, v, nullptr, 0, k, pA + i0 * Kp, Kp, rowsPA, sp);
+  };
+  auto upload_b = [&](int j) -> int32_t {
+    const int64_t j0 = j * bn, nj = std::min(bn, n - j0);
+    GFFM_CUDA(cudaMemcpy2DAsync(dB + j0 * ldB, (size_t)ldB * 4, (const uint32_t*)B_host + j0 * ldb, (size_t)ldb * 4, (size_t)k * 4, (size_t)nj,
+                                cudaMemcpyHostToDevice, sh));
+    GFFM_CUDA(cudaEventRecord(evB[j], sh));
+    GFFM_CUDA(cudaStreamWaitEvent(sc, evB[j], 0));
+    mod_inplace_kernel<<<nblk_mod, 256, 0, sc>>>(dB + j0 * ldB, ldB, k, nj, mp);
+    GFFM_LAUNCH_CHECK(ctx);
+    MatView v{dB + j0 * ldB, ldB, k, nj};
+    return run_split(ctx, false, v, nullptr, 0, k, pB + j0 * Kp, Kp, rowsPB, sp);
+  };
+  auto tile = [&](int i, int j) -> int32_t {
+    const int64_t i0 = i * bm, mi = std::min(bm, m - i0), j0 = j * bn, nj = std::min(bn, n - j0);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.m = (int)mi;
+    p.n = (int)nj;
+    p.num_kb = (int)(Kp / 128);
+    p.num_m_blk = (int)ceil_div(mi, BM);
+    p.num_n_blk = (int)ceil_div(nj, BN);
+    p.mb0 = (int)(i0 / BM);
+    p.nb0 = (int)(j0 / BN);
+    uint32_t* ctile = dC + j0 * ldC + i0;
+    if (rns) {
+      memcpy(p.mods, plan.mods, sizeof(p.mods));
+      p.batches = plan.s;
+      p.E = E + j0 * lde + i0;
+      p.lde = lde;
+      p.e_plane_stride = e_plane;
+      GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p));
+      GFFM_TRY(launch_crt(ctx, sc, plan.cp, E + j0 * lde + i0, lde, e_plane, mi, nj, ctile, ldC, nullptr, 0));
+    } else {
+      p.batches = 1;
+      p.C = ctile;
+      p.ldc = ldC;
+      p.mode = GFFM_GEMM_STORE;
+      p.modP = mp;
+      if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p));
+      else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p));
+    }
+    cudaEvent_t e = evC[(size_t)i * nbB + j];
+    GFFM_CUDA(cudaEventRecord(e, sc));
+    GFFM_CUDA(cudaStreamWaitEvent(sd, e, 0));
+    GFFM_CUDA(cudaMemcpy2DAsync((uint32_t*)C_host + j0 * ldc + i0, (size_t)ldc * 4, ctile, (size_t)ldC * 4, (size_t)mi * 4, (size_t)nj,
+                                cudaMemcpyDeviceToHost, sd));
+    return GFFM_OK;
+  };
+
+  const int steps = std::max(nbA, nbB);
+  for (int t = 0; t < steps && st == GFFM_OK; ++t) {
+    if (t == 0) {
+      st = upload_a(0);
+      if (st == GFFM_OK) st = upload_b(0);
+    } else {
+      if (t < nbB && st == GFFM_OK) st = upload_b(t);
+      if (t < nbA && st == GFFM_OK) st = upload_a(t);
+    }
+    // every tile whose last missing operand block arrived in this step
+    for (int i = 0; i < std::min(t, nbA) && st == GFFM_OK; ++i)
+      if (t < nbB) st = tile(i, t);
+    for (int j = 0; j < std::min(t, nbB) && st == GFFM_OK; ++j)
+      if (t < nbA) st = tile(t, j);
+    if (t < nbA && t < nbB && st == GFFM_OK) st = tile(t, t);
+  }
+  cudaStreamSynchronize(sd);
+  cudaStreamSynchronize(sc);
+  cudaStreamSynchronize(sh);
+  for (auto& e : evA) cudaEventDestroy(e);
+  for (auto& e : evB) cudaEventDestroy(e);
+  for (auto& e : evC) cudaEventDestroy(e);
+  cudaEventDestroy(ev0);
+  if (st == GFFM_OK) GFFM_CUDA(cudaGetLastError());
+  return st;
 }

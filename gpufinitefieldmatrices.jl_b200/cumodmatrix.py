@@ -392,6 +392,22 @@ stripe_mul_ = mul_   # stripe_mul!(C,A,B) (kernel_mul/stripe_mul.jl:175-244): sa
 mulN_ = mul_         # CuModMatrix.jl:789-809
 
 
+def matmul_host(A, B, N, out=None, ctx: Context = None):
+    """`mod.(A*B, N)` for HOST matrices in one pipelined call (gffm_gemm_host): H2D copies, 8-bit plane split, tcgen05
+    GEMM tiles and D2H copies overlap on three streams.  A, B: integer arrays with entries in [0, 2^32); returns uint32."""
+    ctx = ctx or default_context()
+    Ah = np.asfortranarray(np.asarray(A, dtype=np.uint32))
+    Bh = np.asfortranarray(np.asarray(B, dtype=np.uint32))
+    m, k = Ah.shape
+    k2, n = Bh.shape
+    if k != k2:
+        raise capi.CuModArraySizeMismatchException(capi.ERR_SIZE_MISMATCH, "inner dimensions differ")
+    Ch = out if out is not None else np.zeros((m, n), dtype=np.uint32, order="F")
+    capi.check(ctx.lib.gffm_gemm_host(ctx.h, Ch.ctypes.data_as(C.c_void_p), m, Ah.ctypes.data_as(C.c_void_p), m, Bh.ctypes.data_as(C.c_void_p), k,
+                                      m, n, k, capi.U32, int(N)))
+    return Ch
+
+
 def gemv_(z, A, x, R=None, P=None):
     capi.check(z.lib.gffm_gemv(z.h, A.h, x.h, int(R or 0), int(P or 0)))
     return z

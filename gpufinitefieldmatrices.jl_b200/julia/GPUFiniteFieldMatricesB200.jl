@@ -199,6 +199,12 @@ stripe_mul!(C, A, B; kw...) = mul!(C, A, B; kw...)
 function mul!(z::CuModArray{T,1}, A::CuModArray{T,2}, x::CuModArray{T,1}; R::Integer=0, P::Integer=0, maxopsOverride=false) where {T}
     check(ccall((:gffm_gemv, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64), z.h, A.h, x.h, R, P)); z
 end
+# host-to-host pipelined product (uint32 residues): one call instead of CuModMatrix(A); CuModMatrix(B); mul!; Array
+function mul_host!(C::Matrix{UInt32}, A::Matrix{UInt32}, B::Matrix{UInt32}, N::Integer; ctx=default_context())
+    m, k = size(A); n = size(B, 2)
+    check(ccall((:gffm_gemm_host, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int32, UInt64),
+                ctx.h, C, size(C, 1), A, m, B, k, m, n, k, 3, N)); C
+end
 gemm_block!(C, cr, cc, A, ar, ac, B, br, bc, m, n, k; R=0, P=0, mode=0, algo=0) =
     check(ccall((:gffm_gemm_block, libgffm), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, UInt64, UInt64, Int32, Int32),
                 C.h, cr - 1, cc - 1, A.h, ar - 1, ac - 1, B.h, br - 1, bc - 1, m, n, k, R, P, mode, algo))

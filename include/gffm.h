@@ -156,6 +156,12 @@ int32_t gffm_gemm(gffm_mat* C, gffm_mat* A, gffm_mat* B, uint64_t in_bound_R, ui
 int32_t gffm_gemm_block(gffm_mat* C, int64_t cr0, int64_t cc0, gffm_mat* A, int64_t ar0, int64_t ac0,
                         gffm_mat* B, int64_t br0, int64_t bc0, int64_t m, int64_t n, int64_t k,
                         uint64_t in_bound_R, uint64_t mod_P, int32_t mode, int32_t algo);
+/* C_host = A_host * B_host mod N directly between HOST buffers (column-major uint32 residues, leading dimensions in
+ * elements; pinned memory gives full overlap).  One call replaces CuModMatrix(A); CuModMatrix(B); mul!(C,A,B); Array(C)
+ * (CuModMatrix.jl:53-99, :767-787, :256-261) and pipelines H2D copies, plane split, tcgen05 GEMM tiles and D2H copies on
+ * three streams.  Blocks until C_host is complete. */
+int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, const void* A_host, int64_t lda, const void* B_host, int64_t ldb,
+                       int64_t m, int64_t n, int64_t k, int32_t dtype, uint64_t N);
 /* mul!(z,A,x;R,P) (CuModMatrix.jl:816-836, stripe_mul.jl:82-168): z = A*x mod P, x and z are n x 1 matrices */
 int32_t gffm_gemv(gffm_mat* z, gffm_mat* A, gffm_mat* x, uint64_t in_bound_R, uint64_t mod_P);
 

@@ -407,3 +407,19 @@ def test_karatsuba_elementwise_and_split(g):
     assert np.array_equal(K.sub_(CK, AK, BK).Array(), (A.astype(object) - B) % M)
     assert np.array_equal(K.scalar_multiply_(CK, AK, 97).Array(), (A.astype(object) * 97) % M)
     assert np.array_equal(K.negate_(CK, AK).Array(), (-A.astype(object)) % M)
+
+
+# ---------------------------------------------------------------- pipelined host-to-host GEMM ----------------------------------------------
+@pytest.mark.parametrize("m,k,n,N", [(100, 100, 100, 11), (700, 900, 1100, 33554393), (3000, 2500, 4100, 33554393), (2600, 3000, 2100, 65521), (4500, 1000, 2300, 251)])
+def test_gemm_host_pipelined(g, m, k, n, N):
+    """gffm_gemm_host (H2D / split / tcgen05 tiles / D2H on three streams) == the plain upload-mul-download sequence."""
+    A = O.synth_matrix(41, m, k, N); B = O.synth_matrix(42, k, n, N)
+    C = g.matmul_host(A, B, N)
+    ref = (g.CuModMatrix(A, N) * g.CuModMatrix(B, N)).to_int()
+    assert C.dtype == np.uint32 and np.array_equal(C.astype(np.int64), ref)
+    if m * k * n <= 2 ** 30:
+        assert np.array_equal(ref, O.matmul_mod(A, B, N))
+    # unreduced inputs are reduced on the device (constructor semantics mod=true)
+    if N < 2 ** 31:
+        C2 = g.matmul_host(A + N, B, N)
+        assert np.array_equal(C2, C)
