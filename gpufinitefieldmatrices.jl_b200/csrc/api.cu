@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include <algorithm>
+#include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 
@@ -76,6 +77,9 @@ extern "C" int32_t gffm_destroy(gffm_ctx* ctx) {
   ws_free(&ctx->ws_host);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+  if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  for (auto e : ctx->tile_events) cudaEventDestroy(e);
   if (ctx->ws_pinned.ptr) cudaFreeHost(ctx->ws_pinned.ptr);
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -115,6 +119,17 @@ extern "C" int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t cap, int
   if (ctx->n_ev == 0 && !ctx->elim_timings.empty()) {
     ctx->timings = ctx->elim_timings;
     ctx->elim_timings.clear();
+  }
+  if (ctx->n_ev == 0 && !ctx->tile_events.empty()) {
+    // tiled product: {0, sum of the GEMM launch durations, number of launches}
+    double sum = 0;
+    GFFM_CUDA(cudaEventSynchronize(ctx->tile_events.back()));
+    for (size_t i = 0; i + 1 < ctx->tile_events.size(); i += 2) {
+      float t = 0.f;
+      GFFM_CUDA(cudaEventElapsedTime(&t, ctx->tile_events[i], ctx->tile_events[i + 1]));
+      sum += t;
+    }
+    ctx->timings = {0.0, sum, (double)(ctx->tile_events.size() / 2)};
   }
   if (ctx->n_ev >= 2) {
     GFFM_CUDA(cudaEventSynchronize(ctx->ev[ctx->n_ev - 1]));
@@ -831,6 +846,16 @@ int32_t gffm_gemm_views(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t
     else if (R <= 65536) algo = GFFM_ALGO_LIMB;
     else if (R < (1ull << 32)) algo = GFFM_ALGO_RNS;
     else algo = GFFM_ALGO_SIMT;
+  }
+  // large products whose K fits one accumulation chunk can take the tiled multi-stream path (split / CRT concurrent with the
+  // GEMM).  Opt-in (GFFM_TILED=1): measured on B200 it gains nothing for resident operands -- the issue-bound helper kernels
+  // take issue slots from the single MMA-issuing warp and the GEMM slows by what the helpers save (profiles/r01_notes.md).
+  if ((algo == GFFM_ALGO_LIMB || algo == GFFM_ALGO_RNS) && getenv("GFFM_TILED") != nullptr) {
+    const bool rns = algo == GFFM_ALGO_RNS;
+    const bool ok_enc = rns ? (R > 65536 && R < (1ull << 32)) : (R <= 65536);
+    const int64_t kchunk = gffm_gemm_kchunk(R, rns);
+    if (ok_enc && k <= kchunk && m >= 4096 && n >= 4096 && k >= 1024)
+      return gffm_gemm_tiled(ctx, C, A, B, R, P, mode, rns && (R % P) == 0);
   }
   switch (algo) {
     case GFFM_ALGO_SIMT: return gffm_gemm_simt(ctx, C, A, B, R, P, mode);

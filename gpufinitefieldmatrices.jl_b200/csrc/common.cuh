@@ -50,7 +50,9 @@ struct gffm_ctx {
   int64_t launches = 0;
   // grow-only scratch buffers (stream-ordered reuse)
   gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned, ws_invtab, ws_scratch, ws_host;
-  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of the pipelined host GEMM
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;  // copy / helper streams of the tiled GEMM
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<cudaEvent_t> tile_events;  // (start, end) pairs around the GEMM launches of the last profiled tiled product
   uint64_t inv_table_N = 0;
   std::vector<double> timings;
   std::vector<double> elim_timings;  // {inner panels, U12 = L11^-1 A12, trailing GEMM} ms of the last profiled elimination
@@ -208,6 +210,8 @@ int32_t gffm_gemm_tc_limb(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64
 int32_t gffm_gemm_tc_rns(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode,
                          bool balanced, uint32_t* kara_hi, uint64_t kara_N1);
 bool gffm_tc_available(gffm_ctx* ctx);
+int64_t gffm_gemm_kchunk(uint64_t R, bool rns);
+int32_t gffm_gemm_tiled(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode, bool balanced);
 
 int32_t gffm_ew_views(gffm_ctx* ctx, int op, MatView C, MatView A, const MatView* B, int64_t scalar, uint64_t P);
 int32_t gffm_copy_views(gffm_ctx* ctx, MatView dst, MatView src);

@@ -591,19 +591,20 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
 }
 
 int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2, int64_t k_off, int64_t kc, uint8_t* planes,
-                  int64_t Kp, int64_t rowsP, const SplitParams& sp) {
+                  int64_t Kp, int64_t rowsP, const SplitParams& sp, cudaStream_t st = nullptr) {
+  if (!st) st = ctx->stream;
   if (is_a) {
     // A is m x K: rows = i, K along columns of the view
     const uint32_t* s = X.p + k_off * X.ld;
     const uint32_t* s2 = X2 ? X2->p + k_off * X2->ld : nullptr;
     dim3 grid((unsigned)ceil_div(X.rows, 32), (unsigned)(Kp / 128));
-    split_a_kernel<<<grid, 256, 0, ctx->stream>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)X.rows, (int)kc, planes, Kp, rowsP, sp);
+    split_a_kernel<<<grid, 256, 0, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)X.rows, (int)kc, planes, Kp, rowsP, sp);
   } else {
     // B is K x n: K along rows of the view
     const uint32_t* s = X.p + k_off;
     const uint32_t* s2 = X2 ? X2->p + k_off : nullptr;
     dim3 grid((unsigned)ceil_div(Kp / 8, 128), (unsigned)X.cols);
-    split_b_kernel<<<grid, 128, 0, ctx->stream>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)X.cols, planes, Kp, rowsP, sp);
+    split_b_kernel<<<grid, 128, 0, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)X.cols, planes, Kp, rowsP, sp);
   }
   GFFM_LAUNCH_CHECK(ctx);
   return GFFM_OK;
@@ -877,15 +878,15 @@ int32_t gffm_gemm_tc_rns(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// gffm_gemm_host: C_host = A_host * B_host mod N straight from / to HOST buffers, fully pipelined.
-// Replaces the reference sequence CuModMatrix(A) ; CuModMatrix(B) ; mul!(C,A,B) ; Array(C)
-// (reference CuModMatrix.jl:53-99, :767-787, :256-261), where the three transfers and the product are serialised.
-// A is cut into row blocks and B into column panels; three streams run concurrently:
-//   H2D     A0 B0 B1 A1 B2 A2 ...                       (PCIe, one direction)
-//   compute mod + 8-bit plane split of each block as it lands, then every C tile (i,j) whose A_i and B_j are present:
-//           tcgen05 GEMM on the tile's sub-range of the plane set (+ CRT kernel for the RNS encoding)
-//   D2H     C tiles as they complete                    (PCIe, other direction)
-// so the host-visible time approaches max(H2D bytes / PCIe, GEMM time) instead of their sum.
+// Tiled, multi-stream modular GEMM.  A is cut into row blocks and B into column panels; the 8-bit plane split of block
+// t+1 and the CRT of the tiles of step t run on an auxiliary stream WHILE the tensor-core GEMM of step t occupies the
+// compute stream (the GEMM is tensor-bound and leaves the CUDA cores almost idle, the helpers are issue-bound), so
+// only the first split and the last CRT are exposed.  Two front ends:
+//   device mode : operands are resident views (gffm_gemm on large shapes)
+//   host mode   : gffm_gemm_host -- blocks arrive by H2D copies on a third stream and C tiles leave by D2H copies on
+//                 a fourth, replacing the reference sequence CuModMatrix(A); CuModMatrix(B); mul!(C,A,B); Array(C)
+//                 (reference CuModMatrix.jl:53-99, :767-787, :256-261) whose transfers and product are serialised.
+// Tile (i,j) is issued in the step t = max(i,j) in which its last operand block becomes available.
 // ---------------------------------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(256)
@@ -897,27 +898,70 @@ mod_inplace_kernel(uint32_t* __restrict__ X, int64_t ld, int64_t rows, int64_t c
     if (v >= mp.P) X[j * ld + i] = (uint32_t)mod_u64(v, mp);
   }
 }
-}  // namespace
 
-extern "C" int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, const void* A_host, int64_t lda, const void* B_host,
-                                  int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t dtype, uint64_t N) {
-  if (!ctx || !C_host || !A_host || !B_host) GFFM_FAIL(GFFM_ERR_INVALID, "null");
-  if (m <= 0 || n <= 0 || k <= 0) GFFM_FAIL(GFFM_ERR_INVALID, "empty product");
-  if (lda < m || ldb < k || ldc < m) GFFM_FAIL(GFFM_ERR_INVALID, "leading dimension too small");
-  if (dtype != GFFM_U32) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "gffm_gemm_host takes uint32 residues (use upload/gemm/download for other host types)");
-  if (N < 2 || N >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "2 <= N < 2^32 required");
-  if (!gffm_tc_available(ctx)) GFFM_FAIL(GFFM_ERR_CUDA, "tensor-map encoder unavailable");
-  cudaSetDevice(ctx->device);
-  const bool rns = N > 65536;
-  const int L = N <= 256 ? 1 : 2;
-  const int64_t kmax = rns ? 65536 : limb_kmax(N);
-  if (k > kmax) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "inner dimension %lld exceeds one accumulation chunk (%lld) of the pipelined host GEMM", (long long)k, (long long)kmax);
+struct HostIO {  // host mode only
+  const uint32_t* A = nullptr;
+  int64_t lda = 0;
+  const uint32_t* B = nullptr;
+  int64_t ldb = 0;
+  uint32_t* C = nullptr;
+  int64_t ldc = 0;
+};
+
+// returns true when the planes of X are already cached (no split needed); otherwise *out points to the buffer to fill
+// (the owner's cache buffer, (re)allocated here, or the shared workspace) and *fill_cache says whether to validate it
+int32_t plane_buffer(gffm_ctx* ctx, int role, const MatView& X, int64_t k, int64_t Kp, int64_t rowsP, const SplitParams& sp,
+                     int balanced, uint64_t R, gffm_workspace* ws, uint8_t** out, bool* hit, gffm_plane_cache** fill_cache) {
+  const size_t bytes = (size_t)sp.nplanes * rowsP * Kp;
+  *hit = false;
+  *fill_cache = nullptr;
+  gffm_mat* own = X.owner;
+  if (own) {
+    gffm_plane_cache& c = own->cache[role];
+    if (c.valid && c.version == own->version && c.mode == sp.mode && c.nplanes == sp.nplanes && c.balanced == balanced && c.R == R &&
+        c.r0 == X.r0 && c.c0 == X.c0 && c.rows == X.rows && c.cols == X.cols && c.k0 == 0 && c.kc == k && c.Kp == Kp && c.rowsP == rowsP) {
+      *out = (uint8_t*)c.ptr;
+      *hit = true;
+      return GFFM_OK;
+    }
+    if (c.bytes < bytes) {
+      if (c.ptr) {
+        GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(c.ptr);
+        c.ptr = nullptr;
+        c.bytes = 0;
+      }
+      if (cudaMalloc(&c.ptr, bytes) == cudaSuccess) c.bytes = bytes;
+      else {
+        cudaGetLastError();
+        c.ptr = nullptr;
+      }
+    }
+    if (c.ptr) {
+      c.valid = false;
+      c.mode = sp.mode; c.nplanes = sp.nplanes; c.balanced = balanced; c.R = R;
+      c.r0 = X.r0; c.c0 = X.c0; c.rows = X.rows; c.cols = X.cols; c.k0 = 0; c.kc = k; c.Kp = Kp; c.rowsP = rowsP;
+      *out = (uint8_t*)c.ptr;
+      *fill_cache = &c;
+      return GFFM_OK;
+    }
+  }
+  GFFM_TRY(gffm_ws_reserve(ctx, ws, bytes));
+  *out = (uint8_t*)ws->ptr;
+  return GFFM_OK;
+}
+
+int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO* io, int64_t m, int64_t n, int64_t k, uint64_t R, uint64_t P,
+                   int mode, bool balanced) {
+  const bool host = io != nullptr;
+  const bool rns = R > 65536;
+  const int L = R <= 256 ? 1 : 2;
   const int BN = rns ? SchemeRNS::BN : (L == 1 ? SchemeL1::BN : SchemeL2::BN);
   RnsPlan plan;
   SplitParams sp;
   int nplanes;
   if (rns) {
-    GFFM_TRY(make_rns_plan(k, N, N, /*balanced=*/true, GFFM_GEMM_STORE, 0, &plan));
+    GFFM_TRY(make_rns_plan(k, R, P, balanced, mode, 0, &plan));
     sp = plan.sp;
     nplanes = plan.s;
   } else {
@@ -925,75 +969,115 @@ extern "C" int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, cons
     sp.nplanes = nplanes = L;
     sp.mode = 0;
   }
-  // block sizes: ~4x4 tiling for large products, single block for small ones
-  auto pick = [](int64_t extent, int64_t align) {
-    if (extent <= 2048) return round_up(extent, align);
-    int64_t b = round_up(ceil_div(extent, 4), align);
-    return b;
+  // block sizes: host mode up to 8x8 tiles (short tail after the last upload), device mode up to 4x4 (fewer launches)
+  const int64_t max_blocks = host ? 8 : 4, min_block = host ? 1024 : 2048;
+  auto pick = [&](int64_t extent, int64_t align) {
+    if (extent < 2 * min_block) return round_up(extent, align);
+    const int64_t nb = std::min<int64_t>(max_blocks, extent / min_block);
+    return round_up(ceil_div(extent, nb), align);
   };
   const int64_t bm = pick(m, BM), bn = pick(n, BN);
   const int nbA = (int)ceil_div(m, bm), nbB = (int)ceil_div(n, bn);
   const int64_t Kp = round_up(k, 128), rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
-  const int64_t ldA = round_up(m, 32), ldB = round_up(k, 32), ldC = round_up(m, 32), lde = round_up(m, 128);
-  const int64_t e_plane = lde * n;
-  // one workspace carved into dA, dB, dC, planesA, planesB, E
-  size_t off = 0;
-  auto carve = [&](size_t bytes) {
-    size_t o = off;
-    off = (off + bytes + 255) & ~(size_t)255;
-    return o;
-  };
-  const size_t oA = carve((size_t)ldA * k * 4), oB = carve((size_t)ldB * n * 4), oC = carve((size_t)ldC * n * 4);
-  const size_t oPA = carve((size_t)nplanes * rowsPA * Kp), oPB = carve((size_t)nplanes * rowsPB * Kp);
-  const size_t oE = rns ? carve((size_t)nplanes * e_plane) : 0;
-  GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_host, off));
-  char* base = (char*)ctx->ws_host.ptr;
-  uint32_t *dA = (uint32_t*)(base + oA), *dB = (uint32_t*)(base + oB), *dC = (uint32_t*)(base + oC);
-  uint8_t *pA = (uint8_t*)(base + oPA), *pB = (uint8_t*)(base + oPB), *E = (uint8_t*)(base + oE);
-  if (!ctx->s_h2d) {
+  const int64_t lde = round_up(m, 128), e_plane = lde * n;
+  // buffers
+  uint32_t *dA = A.p, *dB = B.p, *dC = Cv.p;
+  int64_t ldA = A.ld, ldB = B.ld, ldC = Cv.ld;
+  uint8_t *pA = nullptr, *pB = nullptr, *E = nullptr;
+  bool hitA = false, hitB = false;
+  gffm_plane_cache *fillA = nullptr, *fillB = nullptr;
+  if (host) {
+    ldA = round_up(m, 32); ldB = round_up(k, 32); ldC = round_up(m, 32);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+      size_t o = off;
+      off = (off + bytes + 255) & ~(size_t)255;
+      return o;
+    };
+    const size_t oA = carve((size_t)ldA * k * 4), oB = carve((size_t)ldB * n * 4), oC = carve((size_t)ldC * n * 4);
+    const size_t oPA = carve((size_t)nplanes * rowsPA * Kp), oPB = carve((size_t)nplanes * rowsPB * Kp);
+    const size_t oE = rns ? carve((size_t)nplanes * e_plane) : 0;
+    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_host, off));
+    char* base = (char*)ctx->ws_host.ptr;
+    dA = (uint32_t*)(base + oA); dB = (uint32_t*)(base + oB); dC = (uint32_t*)(base + oC);
+    pA = (uint8_t*)(base + oPA); pB = (uint8_t*)(base + oPB); E = (uint8_t*)(base + oE);
+  } else {
+    GFFM_TRY(plane_buffer(ctx, 0, A, k, Kp, rowsPA, sp, balanced ? 1 : 0, R, &ctx->ws_planes_a, &pA, &hitA, &fillA));
+    GFFM_TRY(plane_buffer(ctx, 1, B, k, Kp, rowsPB, sp, balanced ? 1 : 0, R, &ctx->ws_planes_b, &pB, &hitB, &fillB));
+    if (rns) {
+      GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_eplanes, (size_t)nplanes * e_plane));
+      E = (uint8_t*)ctx->ws_eplanes.ptr;
+    }
+  }
+  if (!ctx->s_aux) GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+  if (host && !ctx->s_h2d) {
     GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
   }
-  cudaStream_t sc = ctx->stream, sh = ctx->s_h2d, sd = ctx->s_d2h;
-  std::vector<cudaEvent_t> evA(nbA), evB(nbB), evC((size_t)nbA * nbB);
-  for (auto& e : evA) GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto& e : evB) GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto& e : evC) GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  cudaEvent_t ev0;
-  GFFM_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
-  GFFM_CUDA(cudaEventRecord(ev0, sc));  // the workspace may still be in use by earlier work on the compute stream
-  GFFM_CUDA(cudaStreamWaitEvent(sh, ev0, 0));
-  GFFM_CUDA(cudaStreamWaitEvent(sd, ev0, 0));
+  cudaStream_t sc = ctx->stream, sx = ctx->s_aux, sh = ctx->s_h2d, sd = ctx->s_d2h;
+  const int steps = std::max(nbA, nbB);
+  // events: pool owned by the context (grow-only)
+  const size_t need_ev = 2 + 3 * (size_t)steps + 2 * (size_t)nbA * nbB;
+  while (ctx->ev_pool.size() < need_ev) {
+    cudaEvent_t e;
+    GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ev_pool.push_back(e);
+  }
+  size_t evi = 0;
+  auto next_ev = [&]() { return ctx->ev_pool[evi++]; };
+  cudaEvent_t ev0 = next_ev(), ev_end = next_ev();
+  GFFM_CUDA(cudaEventRecord(ev0, sc));  // inputs / workspaces may still be in use by earlier work on the compute stream
+  GFFM_CUDA(cudaStreamWaitEvent(sx, ev0, 0));
+  if (host) {
+    GFFM_CUDA(cudaStreamWaitEvent(sh, ev0, 0));
+    GFFM_CUDA(cudaStreamWaitEvent(sd, ev0, 0));
+  }
   CUtensorMap tmA, tmB;
   GFFM_TRY(make_plane_tmap(&tmA, pA, Kp, rowsPA, nplanes, BM));
   GFFM_TRY(make_plane_tmap(&tmB, pB, Kp, rowsPB, nplanes, BN));
-  const ModP mp = make_modp(N);
+  const ModP mpR = make_modp(R), mpP = make_modp(P);
   const int nblk_mod = ctx->num_sms * 8;
-  int32_t st = GFFM_OK;
+  std::vector<cudaEvent_t> ev_split(steps);
 
-  auto upload_a = [&](int i) -> int32_t {
-    const int64_t i0 = i * bm, mi = std::min(bm, m - i0);
-    GFFM_CUDA(cudaMemcpy2DAsync(dA + i0, (size_t)ldA * 4, (const uint32_t*)A_host + i0, (size_t)lda * 4, (size_t)mi * 4, (size_t)k,
-                                cudaMemcpyHostToDevice, sh));
-    GFFM_CUDA(cudaEventRecord(evA[i], sh));
-    GFFM_CUDA(cudaStreamWaitEvent(sc, evA[i], 0));
-    mod_inplace_kernel<<<nblk_mod, 256, 0, sc>>>(dA + i0, ldA, mi, k, mp);
-    GFFM_LAUNCH_CHECK(ctx);
-    MatView v{dA + i0, ldA, mi, k};
-    return run_split(ctx, true, v, nullptr, 0, k, pA + i0 * Kp, Kp, rowsPA, sp);
+  // step t: make block t of A and of B available as planes (aux stream), one step ahead of the GEMM
+  auto prepare = [&](int t) -> int32_t {
+    if (t < nbA && !hitA) {
+      const int64_t i0 = t * bm, mi = std::min(bm, m - i0);
+      if (host) {
+        GFFM_CUDA(cudaMemcpy2DAsync(dA + i0, (size_t)ldA * 4, io->A + i0, (size_t)io->lda * 4, (size_t)mi * 4, (size_t)k, cudaMemcpyHostToDevice, sh));
+        cudaEvent_t e = next_ev();
+        GFFM_CUDA(cudaEventRecord(e, sh));
+        GFFM_CUDA(cudaStreamWaitEvent(sx, e, 0));
+        mod_inplace_kernel<<<nblk_mod, 256, 0, sx>>>(dA + i0, ldA, mi, k, mpR);
+        GFFM_LAUNCH_CHECK(ctx);
+      }
+      MatView v{dA + i0, ldA, mi, k};
+      GFFM_TRY(run_split(ctx, true, v, nullptr, 0, k, pA + i0 * Kp, Kp, rowsPA, sp, sx));
+    }
+    if (t < nbB && !hitB) {
+      const int64_t j0 = t * bn, nj = std::min(bn, n - j0);
+      if (host) {
+        GFFM_CUDA(cudaMemcpy2DAsync(dB + j0 * ldB, (size_t)ldB * 4, io->B + j0 * io->ldb, (size_t)io->ldb * 4, (size_t)k * 4, (size_t)nj,
+                                    cudaMemcpyHostToDevice, sh));
+        cudaEvent_t e = next_ev();
+        GFFM_CUDA(cudaEventRecord(e, sh));
+        GFFM_CUDA(cudaStreamWaitEvent(sx, e, 0));
+        mod_inplace_kernel<<<nblk_mod, 256, 0, sx>>>(dB + j0 * ldB, ldB, k, nj, mpR);
+        GFFM_LAUNCH_CHECK(ctx);
+      }
+      MatView v{dB + j0 * ldB, ldB, k, nj};
+      GFFM_TRY(run_split(ctx, false, v, nullptr, 0, k, pB + j0 * Kp, Kp, rowsPB, sp, sx));
+    }
+    ev_split[t] = next_ev();
+    GFFM_CUDA(cudaEventRecord(ev_split[t], sx));
+    return GFFM_OK;
   };
-  auto upload_b = [&](int j) -> int32_t {
-    const int64_t j0 = j * bn, nj = std::min(bn, n - j0);
-    GFFM_CUDA(cudaMemcpy2DAsync(dB + j0 * ldB, (size_t)ldB * 4, (const uint32_t*)B_host + j0 * ldb, (size_t)ldb * 4, (size_t)k * 4, (size_t)nj,
-                                cudaMemcpyHostToDevice, sh));
-    GFFM_CUDA(cudaEventRecord(evB[j], sh));
-    GFFM_CUDA(cudaStreamWaitEvent(sc, evB[j], 0));
-    mod_inplace_kernel<<<nblk_mod, 256, 0, sc>>>(dB + j0 * ldB, ldB, k, nj, mp);
-    GFFM_LAUNCH_CHECK(ctx);
-    MatView v{dB + j0 * ldB, ldB, k, nj};
-    return run_split(ctx, false, v, nullptr, 0, k, pB + j0 * Kp, Kp, rowsPB, sp);
+  struct Pending {
+    int i, j;
+    cudaEvent_t done;
   };
-  auto tile = [&](int i, int j) -> int32_t {
+  std::vector<Pending> pending;
+  auto gemm_tile = [&](int i, int j) -> int32_t {
     const int64_t i0 = i * bm, mi = std::min(bm, m - i0), j0 = j * bn, nj = std::min(bn, n - j0);
     GemmParams p;
     memset(&p, 0, sizeof(p));
@@ -1004,55 +1088,123 @@ extern "C" int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, cons
     p.num_n_blk = (int)ceil_div(nj, BN);
     p.mb0 = (int)(i0 / BM);
     p.nb0 = (int)(j0 / BN);
-    uint32_t* ctile = dC + j0 * ldC + i0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ctx->profile) {  // kernel-only duration of every GEMM launch (the compute stream carries nothing else)
+      GFFM_CUDA(cudaEventCreate(&t0));
+      GFFM_CUDA(cudaEventCreate(&t1));
+      GFFM_CUDA(cudaEventRecord(t0, sc));
+    }
     if (rns) {
       memcpy(p.mods, plan.mods, sizeof(p.mods));
       p.batches = plan.s;
       p.E = E + j0 * lde + i0;
       p.lde = lde;
       p.e_plane_stride = e_plane;
-      GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p));
-      GFFM_TRY(launch_crt(ctx, sc, plan.cp, E + j0 * lde + i0, lde, e_plane, mi, nj, ctile, ldC, nullptr, 0));
+      GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p, sc));
     } else {
       p.batches = 1;
-      p.C = ctile;
+      p.C = dC + j0 * ldC + i0;
       p.ldc = ldC;
-      p.mode = GFFM_GEMM_STORE;
-      p.modP = mp;
-      if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p));
-      else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p));
+      p.mode = mode;
+      p.modP = mpP;
+      if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p, sc));
+      else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p, sc));
     }
-    cudaEvent_t e = evC[(size_t)i * nbB + j];
+    if (ctx->profile) {
+      GFFM_CUDA(cudaEventRecord(t1, sc));
+      ctx->tile_events.push_back(t0);
+      ctx->tile_events.push_back(t1);
+    }
+    cudaEvent_t e = next_ev();
     GFFM_CUDA(cudaEventRecord(e, sc));
-    GFFM_CUDA(cudaStreamWaitEvent(sd, e, 0));
-    GFFM_CUDA(cudaMemcpy2DAsync((uint32_t*)C_host + j0 * ldc + i0, (size_t)ldc * 4, ctile, (size_t)ldC * 4, (size_t)mi * 4, (size_t)nj,
-                                cudaMemcpyDeviceToHost, sd));
+    pending.push_back(Pending{i, j, e});
+    return GFFM_OK;
+  };
+  // after the GEMM of a tile: CRT (aux stream) and, in host mode, the D2H copy of the finished C tile
+  auto finish_tiles = [&]() -> int32_t {
+    for (const Pending& t : pending) {
+      const int64_t i0 = t.i * bm, mi = std::min(bm, m - i0), j0 = t.j * bn, nj = std::min(bn, n - j0);
+      cudaEvent_t ready = t.done;
+      if (rns) {
+        GFFM_CUDA(cudaStreamWaitEvent(sx, t.done, 0));
+        GFFM_TRY(launch_crt(ctx, sx, plan.cp, E + j0 * lde + i0, lde, e_plane, mi, nj, dC + j0 * ldC + i0, ldC, nullptr, 0));
+        ready = next_ev();
+        GFFM_CUDA(cudaEventRecord(ready, sx));
+      }
+      if (host) {
+        GFFM_CUDA(cudaStreamWaitEvent(sd, ready, 0));
+        GFFM_CUDA(cudaMemcpy2DAsync(io->C + j0 * io->ldc + i0, (size_t)io->ldc * 4, dC + j0 * ldC + i0, (size_t)ldC * 4, (size_t)mi * 4, (size_t)nj,
+                                    cudaMemcpyDeviceToHost, sd));
+      }
+    }
+    pending.clear();
     return GFFM_OK;
   };
 
-  const int steps = std::max(nbA, nbB);
-  for (int t = 0; t < steps && st == GFFM_OK; ++t) {
-    if (t == 0) {
-      st = upload_a(0);
-      if (st == GFFM_OK) st = upload_b(0);
-    } else {
-      if (t < nbB && st == GFFM_OK) st = upload_b(t);
-      if (t < nbA && st == GFFM_OK) st = upload_a(t);
-    }
-    // every tile whose last missing operand block arrived in this step
-    for (int i = 0; i < std::min(t, nbA) && st == GFFM_OK; ++i)
-      if (t < nbB) st = tile(i, t);
-    for (int j = 0; j < std::min(t, nbB) && st == GFFM_OK; ++j)
-      if (t < nbA) st = tile(t, j);
-    if (t < nbA && t < nbB && st == GFFM_OK) st = tile(t, t);
+  if (ctx->profile) {
+    for (auto e : ctx->tile_events) cudaEventDestroy(e);
+    ctx->tile_events.clear();
+    ctx->n_ev = 0;
   }
-  cudaStreamSynchronize(sd);
-  cudaStreamSynchronize(sc);
-  cudaStreamSynchronize(sh);
-  for (auto& e : evA) cudaEventDestroy(e);
-  for (auto& e : evB) cudaEventDestroy(e);
-  for (auto& e : evC) cudaEventDestroy(e);
-  cudaEventDestroy(ev0);
-  if (st == GFFM_OK) GFFM_CUDA(cudaGetLastError());
+  int32_t st = prepare(0);
+  for (int t = 0; t < steps && st == GFFM_OK; ++t) {
+    if (t + 1 < steps) st = prepare(t + 1);  // issued first so that it overlaps the GEMMs of step t
+    if (st != GFFM_OK) break;
+    GFFM_CUDA(cudaStreamWaitEvent(sc, ev_split[t], 0));
+    for (int i = 0; i < std::min(t, nbA) && st == GFFM_OK; ++i)
+      if (t < nbB) st = gemm_tile(i, t);
+    for (int j = 0; j < std::min(t, nbB) && st == GFFM_OK; ++j)
+      if (t < nbA) st = gemm_tile(t, j);
+    if (t < nbA && t < nbB && st == GFFM_OK) st = gemm_tile(t, t);
+    if (st == GFFM_OK) st = finish_tiles();
+  }
+  // the compute stream continues only after the helpers are done (C complete, planes reusable)
+  cudaEventRecord(ev_end, sx);
+  cudaStreamWaitEvent(sc, ev_end, 0);
+  if (host) {
+    cudaStreamSynchronize(sd);
+    cudaStreamSynchronize(sh);
+    cudaStreamSynchronize(sc);
+  }
+  if (st == GFFM_OK) {
+    if (fillA) {
+      fillA->valid = true;
+      fillA->version = A.owner->version;
+    }
+    if (fillB) {
+      fillB->valid = true;
+      fillB->version = B.owner->version;
+    }
+    if (host) GFFM_CUDA(cudaGetLastError());
+  }
   return st;
+}
+}  // namespace
+
+// largest inner dimension one launch may accumulate exactly (int32 accumulators) for inputs < R
+int64_t gffm_gemm_kchunk(uint64_t R, bool rns) { return rns ? 65536 : limb_kmax(R); }
+
+// device-resident front end: used by the dispatcher for large single-chunk products
+int32_t gffm_gemm_tiled(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode, bool balanced) {
+  return tiled_gemm(ctx, C, A, B, nullptr, A.rows, B.cols, A.cols, R, P, mode, balanced);
+}
+
+extern "C" int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, const void* A_host, int64_t lda, const void* B_host,
+                                  int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t dtype, uint64_t N) {
+  if (!ctx || !C_host || !A_host || !B_host) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  if (m <= 0 || n <= 0 || k <= 0) GFFM_FAIL(GFFM_ERR_INVALID, "empty product");
+  if (lda < m || ldb < k || ldc < m) GFFM_FAIL(GFFM_ERR_INVALID, "leading dimension too small");
+  if (dtype != GFFM_U32) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "gffm_gemm_host takes uint32 residues (use upload/gemm/download for other host types)");
+  if (N < 2 || N >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "2 <= N < 2^32 required");
+  if (!gffm_tc_available(ctx)) GFFM_FAIL(GFFM_ERR_CUDA, "tensor-map encoder unavailable");
+  cudaSetDevice(ctx->device);
+  const int64_t kmax = N > 65536 ? 65536 : limb_kmax(N);
+  if (k > kmax)
+    GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "inner dimension %lld exceeds one accumulation chunk (%lld) of the pipelined host GEMM", (long long)k, (long long)kmax);
+  HostIO io;
+  io.A = (const uint32_t*)A_host; io.lda = lda;
+  io.B = (const uint32_t*)B_host; io.ldb = ldb;
+  io.C = (uint32_t*)C_host; io.ldc = ldc;
+  MatView none{nullptr, 0, 0, 0};
+  return tiled_gemm(ctx, none, none, none, &io, m, n, k, N, N, GFFM_GEMM_STORE, /*balanced=*/true);
 }

@@ -96,7 +96,9 @@ int32_t gffm_get_stream(gffm_ctx* ctx, void** cuda_stream);
 /* phase profiling: when on, gemm calls record CUDA events around their phases on the context stream */
 int32_t gffm_set_profiling(gffm_ctx* ctx, int32_t on);
 /* CUDA-event timings (ms) of the phases of the last profiled gemm call -- RNS: {plane split, tcgen05 GEMM kernel, CRT
- * kernel}; LIMB: {plane split, tcgen05 GEMM kernel}.  Blocks until the events have completed. */
+ * kernel}; LIMB: {plane split, tcgen05 GEMM kernel}; tiled multi-stream products (large shapes): {0, sum of the GEMM
+ * launch durations, number of GEMM launches}; eliminations: {panel phase, triangular solves, Schur GEMMs}.  Blocks until
+ * the events have completed. */
 int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t capacity, int32_t* n_written);
 /* number of library kernels launched on this context since creation (bench.py's gpu_launches) */
 int32_t gffm_launch_count(gffm_ctx* ctx, int64_t* count);
