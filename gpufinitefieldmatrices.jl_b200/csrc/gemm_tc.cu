@@ -18,6 +18,7 @@
 //   warp 1      MMA issuer        tcgen05.mma.cta_group::1.kind::i8, tcgen05.commit -> empty[stage] / tmem_full[buf]
 //   warps 2..5  epilogue          tcgen05.ld 32x32b.x16 -> registers -> reduction -> coalesced global stores
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -42,6 +43,7 @@ struct GemmParams {
   int m, n;
   int num_kb;
   int num_m_blk, num_n_blk, batches;
+  int l2_hints;  // 1: A strips (re-read by every n-block of a raster group) EVICT_LAST, B panels (streamed) EVICT_FIRST
   int mb0, nb0;  // tile offsets (in blocks) into the operand planes: sub-problems of a larger plane set (pipelined host GEMM)
   // positional epilogue
   uint32_t* C;
@@ -155,11 +157,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* st = smem + stage * C::STAGE_BYTES;
 #pragma unroll
           for (int a = 0; a < S::PA; ++a)
-            tc::tma_load_3d(st + a * C::A_TILE, &tmA, &full_bar[stage], kb * BK_BYTES, (mb + p.mb0) * BM, z * S::PA + a);
+            if (p.l2_hints) tc::tma_load_3d_hint(st + a * C::A_TILE, &tmA, &full_bar[stage], kb * BK_BYTES, (mb + p.mb0) * BM, z * S::PA + a, tc::kEvictLast);
+            else tc::tma_load_3d(st + a * C::A_TILE, &tmA, &full_bar[stage], kb * BK_BYTES, (mb + p.mb0) * BM, z * S::PA + a);
 #pragma unroll
           for (int b = 0; b < S::PB; ++b)
-            tc::tma_load_3d(st + S::PA * C::A_TILE + b * C::B_TILE, &tmB, &full_bar[stage], kb * BK_BYTES, (nb + p.nb0) * S::BN,
-                            z * S::PB + b);
+            if (p.l2_hints) tc::tma_load_3d_hint(st + S::PA * C::A_TILE + b * C::B_TILE, &tmB, &full_bar[stage], kb * BK_BYTES, (nb + p.nb0) * S::BN,
+                                                 z * S::PB + b, tc::kEvictFirst);
+            else tc::tma_load_3d(st + S::PA * C::A_TILE + b * C::B_TILE, &tmB, &full_bar[stage], kb * BK_BYTES, (nb + p.nb0) * S::BN,
+                                 z * S::PB + b);
           if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -585,7 +590,10 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   }
   const int total = p.batches * p.num_m_blk * p.num_n_blk;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  gemm_tc_kernel<S><<<grid, 192, C::SMEM_BYTES, st ? st : ctx->stream>>>(tmA, tmB, p);
+  static const int hints = getenv("GFFM_L2_HINTS") ? atoi(getenv("GFFM_L2_HINTS")) : 0;
+  GemmParams q = p;
+  q.l2_hints = hints;
+  gemm_tc_kernel<S><<<grid, 192, C::SMEM_BYTES, st ? st : ctx->stream>>>(tmA, tmB, q);
   GFFM_LAUNCH_CHECK(ctx);
   return GFFM_OK;
 }

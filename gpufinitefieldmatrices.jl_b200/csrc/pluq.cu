@@ -23,7 +23,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int PANEL_THREADS = 1024;
+constexpr int PANEL_THREADS_MAX = 512;
 constexpr int PANEL_CLUSTER = 8;
 constexpr int PANEL_W_MAX = 32;
 constexpr int PANEL_SMEM_BUDGET = 200 * 1024;
@@ -43,6 +43,7 @@ struct PluqBufs {
   int* g_dst;        // composed gather list of the last panel: W[g_dst[e]] <- old W[g_src[e]]
   int* g_src;
   const uint32_t* inv_table;  // [x] = x^-1 mod N for N <= 2^20 (batched once per modulus), else nullptr
+  long long* prof;            // optional per-phase cycle counters of the panel kernel (GFFM_PANEL_PROF=1), else nullptr
 };
 
 __device__ __forceinline__ bool better(uint32_t v, int i, uint32_t bv, int bi) { return v > bv || (v == bv && i < bi); }
@@ -67,7 +68,19 @@ __device__ __forceinline__ uint32_t panel_mulmod(uint32_t a, uint32_t b, const M
   }
 }
 
+// (a + nl * u) mod P with a, nl, u < P: one multiply-add and one Barrett step per eliminated element
 template <bool SMALL>
+__device__ __forceinline__ uint32_t panel_fmamod(uint32_t a, uint32_t nl, uint32_t u, const ModP& mp, uint32_t mu32) {
+  if constexpr (SMALL) {  // P <= 2^16: nl*u + a < 2^32
+    const uint32_t x = nl * u + a;
+    const uint32_t r = x - __umulhi(x, mu32) * (uint32_t)mp.P;  // in [0, 2P)
+    return min(r, r - (uint32_t)mp.P);                          // unsigned: picks r - P when r >= P
+  } else {
+    return (uint32_t)mod_u64((uint64_t)nl * u + a, mp);
+  }
+}
+
+template <bool SMALL, int PANEL_THREADS>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, uint32_t* __restrict__ Lm, int64_t ldl,
                   PluqBufs b, const __grid_constant__ ModP mp, uint32_t mu32) {
@@ -76,14 +89,20 @@ pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, u
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARPS = PANEL_THREADS / 32;
+  constexpr int MAXC = 16;  // largest cluster
   extern __shared__ uint32_t panel[];  // [w][rows_c]
+  // published per pivot (double-buffered by parity): candidate (value, row, inverse), its row, and -- on its owner -- row r
   __shared__ uint32_t cand_val[2], cand_inv[2];
   __shared__ int cand_idx[2];
-  __shared__ uint32_t red_val[32];
-  __shared__ int red_idx[32];
-  __shared__ uint32_t sel_val, sel_inv;
-  __shared__ int sel_idx;
-  __shared__ uint32_t rowbuf_p[PANEL_W_MAX], rowbuf_r[PANEL_W_MAX], u_s[PANEL_W_MAX], oldr_s[PANEL_W_MAX];
+  __shared__ uint32_t rowbuf_p[2][PANEL_W_MAX], rowbuf_r[2][PANEL_W_MAX];
+  // block-local scratch
+  __shared__ uint32_t red_val[NWARPS], red_inv[NWARPS];
+  __shared__ int red_idx[NWARPS];
+  __shared__ uint32_t g_val[MAXC], g_inv[MAXC];  // gathered candidates of all CTAs
+  __shared__ int g_idx[MAXC];
+  __shared__ uint32_t allrows[MAXC][PANEL_W_MAX];
+  __shared__ uint32_t u_s[PANEL_W_MAX], oldr_s[PANEL_W_MAX];
   __shared__ int colpiv[PANEL_W_MAX];       // panel column -> pivot ordinal within this panel, or -1
   __shared__ uint32_t pivval[PANEL_W_MAX];  // pivot value of ordinal s
 
@@ -94,14 +113,24 @@ pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, u
   int my_n = rows_total - rank * rows_c;
   my_n = my_n < 0 ? 0 : (my_n > rows_c ? rows_c : my_n);
   const uint32_t P = (uint32_t)mp.P;
+  const bool do_prof = b.prof != nullptr && rank == 0 && tid == 0;
+  long long tprev = do_prof ? clock64() : 0;
+#define PANEL_TICK(slot)                         \
+  if (do_prof) {                                 \
+    const long long tn = clock64();              \
+    b.prof[slot] += tn - tprev;                  \
+    tprev = tn;                                  \
+  }
 
   for (int c = 0; c < w; ++c)
     for (int q = tid; q < my_n; q += PANEL_THREADS) panel[c * rows_c + q] = W[(int64_t)(j0 + c) * ldw + my_lo + q];
   if (tid < PANEL_W_MAX) colpiv[tid] = -1;
   cluster.sync();  // everybody has read st->r before anyone can finish and overwrite it
+  PANEL_TICK(0)
 
   int r = rb;
   for (int jj = 0; jj < w && r < m; ++jj) {
+    const int par = jj & 1;
     // ---- phase A: local argmax (max residue, first index) over rows >= r of column jj
     uint32_t bv = 0;
     int bi = 0x7fffffff;
@@ -125,104 +154,126 @@ pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, u
       }
     }
     if (lane == 0) {
+      // inverse of this WARP's candidate: every warp does it at once, so the table-load latency (or the Euclid chain)
+      // is paid once per pivot and overlaps the block barrier below
       red_val[warp] = bv;
       red_idx[warp] = bi;
+      red_inv[warp] = bv ? (b.inv_table ? b.inv_table[bv] : modinv_u32(bv, P)) : 0u;
     }
-    __syncthreads();
+    __syncthreads();  // S1: also orders the previous pivot's phase C before the row copies below
     if (warp == 0) {
-      bv = red_val[lane];
-      bi = red_idx[lane];
+      uint32_t biv = 0;
+      bv = lane < NWARPS ? red_val[lane] : 0u;
+      bi = lane < NWARPS ? red_idx[lane] : 0x7fffffff;
+      biv = lane < NWARPS ? red_inv[lane] : 0u;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const uint32_t ov = __shfl_xor_sync(0xffffffffu, bv, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const uint32_t oiv = __shfl_xor_sync(0xffffffffu, biv, o);
         if (better(ov, oi, bv, bi)) {
           bv = ov;
           bi = oi;
+          biv = oiv;
         }
       }
       if (lane == 0) {
-        cand_val[jj & 1] = bv;
-        cand_idx[jj & 1] = bi;
-        // inverse of this CTA's candidate, off the post-barrier critical path (batched table when N <= 2^20)
-        cand_inv[jj & 1] = bv ? (b.inv_table ? b.inv_table[bv] : modinv_u32(bv, P)) : 0u;
+        cand_val[par] = bv;
+        cand_idx[par] = bi;
+        cand_inv[par] = biv;
+      }
+      // publish this CTA's candidate row (all w columns): ONE cluster barrier per pivot suffices
+      if (bv != 0 && lane < w) rowbuf_p[par][lane] = panel[lane * rows_c + (bi - my_lo)];
+    } else if (warp == 1) {
+      if (r >= my_lo && r < my_lo + my_n && lane < w) rowbuf_r[par][lane] = panel[lane * rows_c + (r - my_lo)];
+    }
+    PANEL_TICK(1)
+    cluster.sync();
+    PANEL_TICK(2)
+    // ---- phase B: ONE round of DSMEM reads, all in flight together: warp c fetches candidate + row of CTA c, one more
+    // warp fetches row r from its owner
+    {
+      const int owner_r = (r - rb) / rows_c;
+      for (int c = warp; c <= cs; c += NWARPS) {
+        if (c < cs) {
+          if (lane == 0) {
+            g_val[c] = *cluster.map_shared_rank(&cand_val[par], c);
+            g_idx[c] = *cluster.map_shared_rank(&cand_idx[par], c);
+            g_inv[c] = *cluster.map_shared_rank(&cand_inv[par], c);
+          }
+          if (lane < w) allrows[c][lane] = *cluster.map_shared_rank(&rowbuf_p[par][lane], c);
+        } else if (lane < w) {
+          oldr_s[lane] = *cluster.map_shared_rank(&rowbuf_r[par][lane], owner_r);
+        }
       }
     }
-    cluster.sync();
-    // ---- phase B: cluster-wide winner through distributed shared memory
-    if (warp == 0) {
-      uint32_t v = 0, iv = 0;
-      int i = 0x7fffffff;
-      if (lane < cs) {
-        v = *cluster.map_shared_rank(&cand_val[jj & 1], lane);
-        i = *cluster.map_shared_rank(&cand_idx[jj & 1], lane);
-        iv = *cluster.map_shared_rank(&cand_inv[jj & 1], lane);
-      }
+    __syncthreads();  // S2
+    // every warp selects the winner redundantly from the gathered candidates (cheap, avoids a broadcast)
+    uint32_t pv = lane < cs ? g_val[lane] : 0u, pinv = lane < cs ? g_inv[lane] : 0u;
+    int p = lane < cs ? g_idx[lane] : 0x7fffffff, src = lane;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-        const uint32_t oiv = __shfl_xor_sync(0xffffffffu, iv, o);
-        if (better(ov, oi, v, i)) {
-          v = ov;
-          i = oi;
-          iv = oiv;
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t ov = __shfl_xor_sync(0xffffffffu, pv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, p, o);
+      const uint32_t oiv = __shfl_xor_sync(0xffffffffu, pinv, o);
+      const int os = __shfl_xor_sync(0xffffffffu, src, o);
+      if (better(ov, oi, pv, p)) {
+        pv = ov;
+        p = oi;
+        pinv = oiv;
+        src = os;
+      }
+    }
+    PANEL_TICK(3)
+    if (pv == 0) continue;  // no pivot in this column (uniform over the cluster): skip it, row stays
+    if (warp == 0) {
+      if (lane < w) {
+        const uint32_t xp = allrows[src][lane];
+        // new row r = old row p: multipliers of earlier pivots (columns < jj) move with the row, pivot -> 1, rest scaled
+        u_s[lane] = lane > jj ? panel_mulmod<SMALL>(xp, pinv, mp, mu32) : (lane == jj ? 1u % P : xp);
       }
       if (lane == 0) {
-        sel_val = v;
-        sel_idx = i;
-        sel_inv = iv;
+        const int s_ord = r - rb;
+        colpiv[jj] = s_ord;
+        pivval[s_ord] = pv;
+        if (rank == 0) {
+          b.pivcol[r] = j0 + jj;
+          b.pinv[r] = pinv;
+          b.swp[r] = p;
+        }
       }
     }
-    __syncthreads();
-    const uint32_t pv = sel_val;
-    const int p = sel_idx;
-    const uint32_t pinv = sel_inv;
-    if (pv == 0) continue;  // no pivot in this column (uniform over the cluster): skip it, row stays
-    const int owner_p = (p - rb) / rows_c, owner_r = (r - rb) / rows_c;
-    if (rank == owner_p && tid < w) rowbuf_p[tid] = panel[tid * rows_c + (p - my_lo)];
-    if (rank == owner_r && tid >= 32 && tid < 32 + w) rowbuf_r[tid - 32] = panel[(tid - 32) * rows_c + (r - my_lo)];
-    cluster.sync();
-    if (tid < w) {
-      const uint32_t xp = *cluster.map_shared_rank(&rowbuf_p[tid], owner_p);
-      const uint32_t xr = *cluster.map_shared_rank(&rowbuf_r[tid], owner_r);
-      // new row r = old row p: multipliers of earlier pivots (columns < jj) move with the row, pivot -> 1, rest scaled
-      u_s[tid] = tid > jj ? panel_mulmod<SMALL>(xp, pinv, mp, mu32) : (tid == jj ? 1u % P : xp);
-      oldr_s[tid] = xr;
-    }
-    if (tid == 0) {
-      const int s_ord = r - rb;
-      colpiv[jj] = s_ord;
-      pivval[s_ord] = pv;
-      if (rank == 0) {
-        b.pivcol[r] = j0 + jj;
-        b.pinv[r] = pinv;
-        b.swp[r] = p;
-      }
-    }
-    __syncthreads();
-    // ---- phase C: swap rows r <-> p, scale, eliminate (every thread owns fixed rows of the panel)
+    __syncthreads();  // S3
+    PANEL_TICK(4)
+    // ---- phase C: swap rows r <-> p, scale, eliminate.  Every thread owns fixed rows; columns go in chunks of 4 whose
+    // loads are issued before their stores (the compiler cannot reorder shared loads across stores of the same array)
     for (int q = tid; q < my_n; q += PANEL_THREADS) {
       const int i = my_lo + q;
       if (i < r) continue;
+      uint32_t* prow = panel + q;
       if (i == r) {
-        for (int c = 0; c < w; ++c) panel[c * rows_c + q] = u_s[c];
-      } else {
-        const bool isp = (i == p);
-        if (isp)
-          for (int c = 0; c < jj; ++c) panel[c * rows_c + q] = oldr_s[c];
-        const uint32_t l = isp ? oldr_s[jj] : panel[jj * rows_c + q];
-        if (isp) panel[jj * rows_c + q] = l;  // the multiplier stays in the pivot column (becomes L[i][t] at store-back)
-        if (l != 0 || isp) {
-          for (int c = jj + 1; c < w; ++c) {
-            const uint32_t a = isp ? oldr_s[c] : panel[c * rows_c + q];
-            panel[c * rows_c + q] = submod_u32(a, panel_mulmod<SMALL>(l, u_s[c], mp, mu32), P);
-          }
+        for (int c = 0; c < w; ++c) prow[c * rows_c] = u_s[c];
+        continue;
+      }
+      if (i == p)  // position p receives the old row r (its multipliers of earlier pivots included), then is eliminated like any row
+        for (int c = 0; c < w; ++c) prow[c * rows_c] = oldr_s[c];
+      const uint32_t l = prow[jj * rows_c];  // stays in place: becomes L[i][t] at store-back
+      if (l != 0) {
+        const uint32_t nl = P - l;
+        for (int c0 = jj + 1; c0 < w; c0 += 4) {
+          uint32_t* pc = prow + c0 * rows_c;
+          uint32_t a[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c0 + k < w) a[k] = pc[k * rows_c];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c0 + k < w) pc[k * rows_c] = panel_fmamod<SMALL>(a[k], nl, u_s[c0 + k], mp, mu32);
         }
       }
     }
     ++r;
+    PANEL_TICK(5)
   }
   __syncthreads();
   // ---- store-back: pivot columns split into U (rows <= pivot row) and L (rows below), everything else is W
@@ -245,6 +296,8 @@ pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, u
     }
   }
 
+  __syncthreads();
+  PANEL_TICK(6)
   // ---- compose this panel's transpositions (rb..r-1) into one gather list (warp 0 of CTA 0)
   if (rank == 0 && warp == 0) {
     const int k = r - rb;  // <= 32
@@ -385,17 +438,33 @@ update_small_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int c_lo, int 
     }
     __syncthreads();
     if (i0 + ti < m) {
-      for (int c = tc; c < 32; c += 2) {
-        if (c0 + c >= c_hi) break;
-        uint32_t* dst = W + (int64_t)(c0 + c) * ldw + i0 + ti;
-        uint64_t acc = 0;
-        if (big_mod) {
-          for (int t = 0; t < k; ++t) acc = mod_u64(acc + mod_u64((uint64_t)sL[t][ti] * sU[t][c], mp), mp);
-        } else {
-          for (int t = 0; t < k; ++t) acc += (uint64_t)sL[t][ti] * sU[t][c];
-          acc = mod_u64(acc, mp);
+      // register tiling: this thread owns row ti and the 16 columns c = tc, tc+2, ...; the L value of a pivot is loaded
+      // once and reused for all 16 columns, old C values are requested up front
+      uint64_t acc[16];
+      uint32_t oldv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        acc[j] = 0;
+        const int c = tc + 2 * j;
+        oldv[j] = (c0 + c < c_hi) ? W[(int64_t)(c0 + c) * ldw + i0 + ti] : 0u;
+      }
+      if (big_mod) {
+        for (int t = 0; t < k; ++t) {
+          const uint64_t l = sL[t][ti];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = mod_u64(acc[j] + mod_u64(l * sU[t][tc + 2 * j], mp), mp);
         }
-        *dst = submod_u32(*dst, (uint32_t)acc, P);
+      } else {
+        for (int t = 0; t < k; ++t) {
+          const uint32_t l = sL[t][ti];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += (uint64_t)l * sU[t][tc + 2 * j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = tc + 2 * j;
+        if (c0 + c < c_hi) W[(int64_t)(c0 + c) * ldw + i0 + ti] = submod_u32(oldv[j], (uint32_t)mod_u64(acc[j], mp), P);
       }
     }
   }
@@ -513,13 +582,18 @@ struct Elim {
   std::vector<int> pivcol, swp;
 };
 
-template <bool SMALL>
+int panel_threads() {
+  static const int t = (getenv("GFFM_PANEL_THREADS") && atoi(getenv("GFFM_PANEL_THREADS")) == 256) ? 256 : 512;
+  return t;
+}
+
+template <bool SMALL, int THREADS>
 int32_t launch_panel_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int rows_c_max, int cluster, const PluqBufs& b,
                        const ModP& mp) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(cluster);
-  cfg.blockDim = dim3(PANEL_THREADS);
+  cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = (size_t)w * rows_c_max * 4;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute at[1];
@@ -530,7 +604,7 @@ int32_t launch_panel_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, i
   cfg.attrs = at;
   cfg.numAttrs = 1;
   const uint32_t mu32 = (uint32_t)((1ull << 32) / mp.P);
-  GFFM_CUDA(cudaLaunchKernelEx(&cfg, pluq_panel_kernel<SMALL>, W->data, W->ld, (int)W->rows, j0, w, L->data, L->ld, b, mp, mu32));
+  GFFM_CUDA(cudaLaunchKernelEx(&cfg, (pluq_panel_kernel<SMALL, THREADS>), W->data, W->ld, (int)W->rows, j0, w, L->data, L->ld, b, mp, mu32));
   ctx->launches++;
   return GFFM_OK;
 }
@@ -540,16 +614,20 @@ int panel_cluster_size(gffm_ctx* ctx) {
   static int chosen = 0;
   if (chosen) return chosen;
   chosen = PANEL_CLUSTER;
-  cudaFuncSetAttribute(pluq_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
-  cudaFuncSetAttribute(pluq_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
+  cudaFuncSetAttribute(pluq_panel_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
+  cudaFuncSetAttribute(pluq_panel_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
+  cudaFuncSetAttribute(pluq_panel_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
+  cudaFuncSetAttribute(pluq_panel_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
   const char* env = getenv("GFFM_PANEL_CLUSTER");
   const int want = env ? atoi(env) : 16;
-  if (want == 16 && cudaFuncSetAttribute(pluq_panel_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-      cudaFuncSetAttribute(pluq_panel_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+  if (want == 16 && cudaFuncSetAttribute(pluq_panel_kernel<true, 512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+      cudaFuncSetAttribute(pluq_panel_kernel<false, 512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+      cudaFuncSetAttribute(pluq_panel_kernel<true, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+      cudaFuncSetAttribute(pluq_panel_kernel<false, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(16);
-    cfg.blockDim = dim3(PANEL_THREADS);
+    cfg.blockDim = dim3(PANEL_THREADS_MAX);
     cfg.dynamicSmemBytes = PANEL_SMEM_BUDGET;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -559,7 +637,7 @@ int panel_cluster_size(gffm_ctx* ctx) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, pluq_panel_kernel<false>, &cfg) == cudaSuccess && nclusters >= 1) chosen = 16;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, pluq_panel_kernel<false, 512>, &cfg) == cudaSuccess && nclusters >= 1) chosen = 16;
   } else if (want >= 1 && want <= 8) {
     chosen = want;
   }
@@ -570,8 +648,12 @@ int panel_cluster_size(gffm_ctx* ctx) {
 
 int32_t launch_panel(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int rows_c_max, int cluster, const PluqBufs& b,
                      const ModP& mp) {
-  if (mp.P <= 65536) return launch_panel_t<true>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
-  return launch_panel_t<false>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
+  if (panel_threads() == 256) {
+    if (mp.P <= 65536) return launch_panel_t<true, 256>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
+    return launch_panel_t<false, 256>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
+  }
+  if (mp.P <= 65536) return launch_panel_t<true, 512>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
+  return launch_panel_t<false, 512>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
 }
 
 int32_t triinv_views(gffm_ctx* ctx, MatView T, MatView X, bool upper, bool unit_diag, uint64_t P, int* singular_dev,
@@ -624,7 +706,10 @@ int32_t base_block(ElimState& E, int c_lo, int c_hi) {
   const int cluster = panel_cluster_size(ctx);
   const int rows_c_max = (int)ceil_div(m - r0, cluster);
   int w = PANEL_SMEM_BUDGET / (4 * std::max(rows_c_max, 1));
-  static const int w_cap = getenv("GFFM_PANEL_W") ? std::max(1, std::min(PANEL_W_MAX, atoi(getenv("GFFM_PANEL_W")))) : 16;
+  // measured on B200 (profiles/r01_notes.md): 32-column panels win for 16-bit moduli (cheap 32-bit arithmetic in the rank-1
+  // update), 16 columns for larger ones
+  static const int w_env = getenv("GFFM_PANEL_W") ? std::max(1, std::min(PANEL_W_MAX, atoi(getenv("GFFM_PANEL_W")))) : 0;
+  const int w_cap = w_env ? w_env : (E.N <= 65536 ? 32 : 16);
   w = std::min(w, w_cap);
   if (w < 1) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "matrix has too many rows (%d) for the panel kernel", m);
   for (int j0 = c_lo; j0 < c_hi; j0 += w) {
@@ -780,6 +865,12 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
   b.g_dst = (int*)(b.pinv + maxr);
   b.g_src = b.g_dst + 64;
   GFFM_CUDA(cudaMemsetAsync(base, 0, need, ctx->stream));
+  b.prof = nullptr;
+  if (getenv("GFFM_PANEL_PROF")) {
+    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_misc, 256));
+    GFFM_CUDA(cudaMemsetAsync(ctx->ws_misc.ptr, 0, 128, ctx->stream));
+    b.prof = (long long*)ctx->ws_misc.ptr;
+  }
   b.inv_table = nullptr;
   if (N <= (1u << 20)) {  // batched modular inverses: one kernel computes every inverse mod N, cached per context
     if (ctx->inv_table_N != N) {
@@ -802,6 +893,17 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
   }
   GFFM_TRY(elim_rec(E, 0, n));
   const int r0 = E.r;
+  if (b.prof) {
+    long long h[16];
+    cudaMemcpyAsync(h, b.prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    static const char* names[7] = {"load+sync", "A scan+inverse+S1+publish", "cluster.sync", "B dsmem gather+S2+select", "u row + S3",
+                                   "C update (warp 0)", "store-back"};
+    long long tot = 0;
+    for (int i = 0; i < 7; ++i) tot += h[i];
+    fprintf(stderr, "[panel prof] total %.3f Mcycles over %d pivots\n", tot / 1e6, r0);
+    for (int i = 0; i < 7; ++i) fprintf(stderr, "  %-24s %10.3f Mcyc  %5.1f%%  %8.1f cyc/pivot\n", names[i], h[i] / 1e6, 100.0 * h[i] / tot, (double)h[i] / std::max(r0, 1));
+  }
   if (ctx->profile) {
     ctx->n_ev = 0;
     ctx->elim_timings = {E.t_panel, E.t_u12, E.t_trail};
