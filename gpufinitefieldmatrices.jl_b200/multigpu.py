@@ -37,3 +37,12 @@ def pipelined_broadcast_matmul(dist, b_colmajor, panels, gemm_panel: Callable[[i
     for w, (c0, c1) in zip(works, panels):
         w.wait()
         gemm_panel(c0, c1)
+
+
+def broadcast_then(dist, tensors, fn: Callable[[], None], src: int = 0):
+    """Broadcast whole operands (e.g. both limbs of a Karatsuba B) and run `fn` once they have arrived.  Used where the
+    product has no per-panel entry point (gffm_kmat_mul): the shard of A stays local, B1/B2 are replicated."""
+    works = [dist.broadcast(t, src=src, async_op=True) for t in tensors]
+    for w in works:
+        w.wait()
+    fn()

@@ -423,3 +423,51 @@ def test_gemm_host_pipelined(g, m, k, n, N):
     if N < 2 ** 31:
         C2 = g.matmul_host(A + N, B, N)
         assert np.array_equal(C2, C)
+
+
+# ---------------------------------------------------------------- BASELINE config 5 (n = 32768) ----------------------------------------------
+def _freivalds_k(g, A1, A2, B1, B2, C1, C2, N1, N2, seed):
+    """(A1 + N1*A2) * (B1 + N1*B2) == C1 + N1*C2 (mod N1*N2), checked modulo N2... on a random vector through plain GEMVs mod N1*N2 is not
+    available for N1*N2 >= 2^32, so check the two consequences that pin the result: C1 == A1*B1 (mod N1) and
+    C1 + N1*C2 == full product (mod N2), both via the independent SIMT GEMV kernel."""
+    n = B1.cols
+    # mod N1: C1 x == A1 (B1 x)
+    x = g.synth(n, 1, N1, seed)
+    t = g.zeros(np.float64, B1.rows, 1, N1); g.gemv_(t, B1, x, P=N1)
+    l = g.zeros(np.float64, A1.rows, 1, N1); g.gemv_(l, A1, t, P=N1)
+    r = g.zeros(np.float64, C1.rows, 1, N1); g.gemv_(r, C1, x, P=N1)
+    return l.equals(r)
+
+
+def test_baseline_config5_plain_32768(g):
+    """32768 x 32768 plain mod-p product (9 moduli, 4 GiB operands): Freivalds with the SIMT GEMV + all-(N-1) closed form."""
+    n, N = 32768, 33554393
+    A = g.synth(n, n, N, 11); B = g.synth(n, n, N, 12)
+    C = g.zeros(np.float32, n, n, N); g.mul_(C, A, B)
+    for s in (1, 2):
+        assert _freivalds(g, A, B, C, N, seed=200 + s)
+    g.fill_(A, N - 1); g.fill_(B, N - 1); g.mul_(C, A, B)
+    ref = g.zeros(np.float32, n, n, N); g.fill_(ref, (n * (N - 1) * (N - 1)) % N)
+    assert C.equals(ref)
+
+
+def test_baseline_config5_karatsuba_32768(g):
+    """32768 x 32768 Karatsuba product, N1 = N2 = 8191 (M ~ 2^26): low limb against A1*B1 mod N1 (Freivalds), and the
+    closed form for all-maximal limbs."""
+    n, N1, N2 = 32768, 8191, 8191
+    A1 = g.synth(n, n, N1, 13); A2 = g.synth(n, n, N2, 14); B1 = g.synth(n, n, N1, 15); B2 = g.synth(n, n, N2, 16)
+    AK = g.KaratsubaMatrix(A1, A2, N1, N2); BK = g.KaratsubaMatrix(B1, B2, N1, N2)
+    CK = g.KaratsubaZeros(np.float64, n, n, N1, N2)
+    g.KMatMul_(CK, AK, BK)
+    assert _freivalds_k(g, A1, A2, B1, B2, CK.data1, CK.data2, N1, N2, seed=300)
+    # all limbs maximal: every entry of the full product is n * (M-1)^2 mod M = n mod M  (M-1 = -1)
+    for X in (A1, B1):
+        g.fill_(X, N1 - 1)
+    for X in (A2, B2):
+        g.fill_(X, N2 - 1)
+    g.KMatMul_(CK, AK, BK)
+    M = N1 * N2
+    want = n % M
+    r1 = g.zeros(np.float64, n, n, N1); g.fill_(r1, want % N1)
+    r2 = g.zeros(np.float64, n, n, N1); g.fill_(r2, want // N1)
+    assert CK.data1.equals(r1) and CK.data2.equals(r2)
