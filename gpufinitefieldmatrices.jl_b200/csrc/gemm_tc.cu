@@ -43,6 +43,8 @@ struct GemmParams {
   int m, n;
   int num_kb;
   int num_m_blk, num_n_blk, batches;
+  int fake_loads;  // DEBUG (GFFM_FAKE_LOADS=1): after the first ring fill the producer only signals the barriers -- measures the
+                   // tensor pipe without L2->smem traffic (results are garbage)
   int l2_hints;  // 1: A strips (re-read by every n-block of a raster group) EVICT_LAST, B panels (streamed) EVICT_FIRST
   int mb0, nb0;  // tile offsets (in blocks) into the operand planes: sub-problems of a larger plane set (pipelined host GEMM)
   // positional epilogue
@@ -153,8 +155,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         decode_tile(tile, p, z, mb, nb);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.fake_loads == 1 && (tile != (int)blockIdx.x || kb >= S::STAGES)) {
+            tc::mbar_arrive(&full_bar[stage]);
+            if (++stage == S::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           tc::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
+          if (p.fake_loads == 2) {  // DEBUG: real TMA traffic but always the same L2-resident tiles (no DRAM traffic)
+#pragma unroll
+            for (int a = 0; a < S::PA; ++a) tc::tma_load_3d(st + a * C::A_TILE, &tmA, &full_bar[stage], 0, (blockIdx.x & 7) * BM, a);
+#pragma unroll
+            for (int b = 0; b < S::PB; ++b) tc::tma_load_3d(st + S::PA * C::A_TILE + b * C::B_TILE, &tmB, &full_bar[stage], 0, (blockIdx.x & 7) * S::BN, b);
+            if (++stage == S::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
 #pragma unroll
           for (int a = 0; a < S::PA; ++a)
             if (p.l2_hints) tc::tma_load_3d_hint(st + a * C::A_TILE, &tmA, &full_bar[stage], kb * BK_BYTES, (mb + p.mb0) * BM, z * S::PA + a, tc::kEvictLast);
@@ -288,6 +309,214 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc::tc_fence_before();
   __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cluster variant (2 CTAs along M share every B tile): each CTA loads its own A tile and HALF of the B tile, the half is
+// TMA-multicast into both CTAs.  L2->SM traffic per MMA drops by a third (48 -> 32 KB per 128x256x128 k-block), which on a
+// power-capped B200 buys SM clock (profiles/r01_notes.md: the same kernel without operand traffic runs 22 % faster).
+// Both CTAs walk the same (tile, k-block) sequence; a stage is reusable only when BOTH CTAs' MMAs have retired it, so the
+// MMA commit is multicast to both empty barriers (count 2).
+// ---------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_tc_kernel_mc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                  const __grid_constant__ GemmParams p) {
+  using C = Cfg<S>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tfull_bar = empty_bar + S::STAGES;
+  uint64_t* tempty_bar = tfull_bar + C::NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + C::NBUF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = tc::cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  constexpr int B_HALF = C::B_TILE / 2;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmBh);
+    for (int s = 0; s < S::STAGES; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], 2);  // both CTAs of the cluster retire the stage
+    }
+    for (int b = 0; b < C::NBUF; ++b) {
+      tc::mbar_init(&tfull_bar[b], 1);
+      tc::mbar_init(&tempty_bar[b], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();  // peer barriers are initialised before any multicast can reach them
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // cluster tiles: pairs of m-blocks (2*mp, 2*mp+1) x one n-block, rasterised GROUP_M/2 pairs wide
+  const int num_mp = (p.num_m_blk + 1) >> 1;
+  const int total = p.batches * num_mp * p.num_n_blk;
+  auto decode = [&](int t, int& z, int& mb, int& nb) {
+    const int per_batch = num_mp * p.num_n_blk;
+    z = t / per_batch;
+    int r = t - z * per_batch;
+    const int gw = GROUP_M / 2;
+    const int per_group = gw * p.num_n_blk;
+    const int g = r / per_group;
+    const int first = g * gw;
+    const int gsize = min(num_mp - first, gw);
+    r -= g * per_group;
+    mb = 2 * (first + (r % gsize)) + (int)crank;
+    nb = r / gsize;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total; tile += num_clusters) {
+        int z, mb, nb;
+        decode(tile, z, mb, nb);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          tc::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+#pragma unroll
+          for (int a = 0; a < S::PA; ++a)
+            tc::tma_load_3d(st + a * C::A_TILE, &tmA, &full_bar[stage], kb * BK_BYTES, (mb + p.mb0) * BM, z * S::PA + a);
+#pragma unroll
+          for (int b = 0; b < S::PB; ++b)
+            tc::tma_load_3d_mcast(st + S::PA * C::A_TILE + b * C::B_TILE + crank * B_HALF, &tmBh, &full_bar[stage], kb * BK_BYTES,
+                                  (nb + p.nb0) * S::BN + (int)crank * (S::BN / 2), z * S::PB + b, (uint16_t)0x3);
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tc::make_idesc_i8(BM, S::BN, S::SIGNED, S::SIGNED);
+    int stage = 0;
+    uint32_t phase = 0;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int tile = cluster_id; tile < total; tile += num_clusters) {
+      tc::mbar_wait(&tempty_bar[buf], bphase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t acc_base = tmem_base + buf * C::ACC_COLS;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = tc::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + S::PA * C::A_TILE;
+#pragma unroll
+          for (int kk = 0; kk < BK_BYTES / UMMA_K; ++kk) {
+#pragma unroll
+            for (int pr = 0; pr < S::NPROD; ++pr) {
+              const uint64_t da = tc::make_smem_desc_sw128(sa + S::pa(pr) * C::A_TILE + kk * UMMA_K);
+              const uint64_t db = tc::make_smem_desc_sw128(sb + S::pb(pr) * C::B_TILE + kk * UMMA_K);
+              bool first_in_slot = true;
+#pragma unroll
+              for (int q = 0; q < pr; ++q)
+                if (S::slot(q) == S::slot(pr)) first_in_slot = false;
+              const uint32_t accumulate = (kb > 0 || kk > 0 || !first_in_slot) ? 1u : 0u;
+              tc::mma_i8_ss(acc_base + S::slot(pr) * S::BN, da, db, idesc, accumulate);
+            }
+          }
+          tc::mma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);  // stage retired here -> tell both producers
+          if (kb == p.num_kb - 1) tc::mma_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == S::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++buf == C::NBUF) {
+        buf = 0;
+        bphase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int tile = cluster_id; tile < total; tile += num_clusters) {
+      int z, mb, nb;
+      decode(tile, z, mb, nb);
+      tc::mbar_wait(&tfull_bar[buf], bphase);
+      tc::tc_fence_after();
+      const int row = mb * BM + q * 32 + lane;
+      const bool row_ok = row < p.m;
+      const uint32_t acc_base = tmem_base + buf * C::ACC_COLS + lane_addr;
+      const int col0 = nb * S::BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < S::BN; c0 += 16) {
+        if (col0 + c0 >= p.n) break;
+        uint32_t v[S::NSLOT][16];
+#pragma unroll
+        for (int s = 0; s < S::NSLOT; ++s) tc::tmem_ld16(acc_base + s * S::BN + c0, v[s]);
+        tc::tmem_ld_wait();
+        if constexpr (S::EPI == EPI_POS) {
+          uint32_t old[16];
+          uint32_t* dst0 = p.C + (int64_t)(col0 + c0) * p.ldc + row;
+          if (p.mode != GFFM_GEMM_STORE) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) old[c] = (row_ok && col0 + c0 + c < p.n) ? dst0[(int64_t)c * p.ldc] : 0u;
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            uint64_t acc = (uint64_t)v[0][c];
+            if constexpr (S::NSLOT == 3) acc += ((uint64_t)v[1][c] << 8) + ((uint64_t)v[2][c] << 16);
+            uint32_t r = (uint32_t)mod_u64(acc, p.modP);
+            if (p.mode == GFFM_GEMM_ADD) r = addmod_u32(old[c], r, (uint32_t)p.modP.P);
+            else if (p.mode == GFFM_GEMM_SUB) r = submod_u32(old[c], r, (uint32_t)p.modP.P);
+            old[c] = r;
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (row_ok && col0 + c0 + c < p.n) dst0[(int64_t)c * p.ldc] = old[c];
+        } else {
+          const RnsModDev md = p.mods[z];
+          uint8_t* eplane = p.E + (int64_t)z * p.e_plane_stride;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = col0 + c0 + c;
+            const uint32_t u = v[0][c] + md.off;
+            uint32_t e = u - __umulhi(u, md.mu) * md.m;
+            if (e >= md.m) e -= md.m;
+            e *= md.u;
+            e -= __umulhi(e, md.mu) * md.m;
+            if (e >= md.m) e -= md.m;
+            if (row_ok && col < p.n) eplane[(int64_t)col * p.lde + row] = (uint8_t)e;
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[buf]);
+      if (++buf == C::NBUF) {
+        buf = 0;
+        bphase ^= 1;
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();  // no CTA may leave while its peer can still multicast into it
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
@@ -580,9 +809,36 @@ int32_t make_plane_tmap(CUtensorMap* tm, void* planes, int64_t Kp, int64_t rowsP
   return GFFM_OK;
 }
 
+int32_t make_plane_tmap(CUtensorMap* tm, void* planes, int64_t Kp, int64_t rowsP, int64_t nplanes, int box_rows);
+
+// GFFM_MCAST: 1 = cluster-of-2 kernel with TMA-multicast B halves (default when it applies), 0 = single-CTA kernel
+inline int mcast_mode() {
+  static const int m = getenv("GFFM_MCAST") ? atoi(getenv("GFFM_MCAST")) : 0;
+  return m;
+}
+
 template <class S>
-int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st = nullptr) {
+int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st = nullptr,
+                    const CUtensorMap* tmB_half = nullptr) {
   using C = Cfg<S>;
+  if (tmB_half && mcast_mode() && p.num_m_blk >= 2) {
+    static bool attr_mc = false;
+    if (!attr_mc) {
+      GFFM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel_mc<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      attr_mc = true;
+    }
+    const int num_mp = (p.num_m_blk + 1) / 2;
+    const int total_c = p.batches * num_mp * p.num_n_blk;
+    int clusters = ctx->num_sms / 2;
+    if (total_c < clusters) clusters = total_c;
+    static const int hints2 = getenv("GFFM_L2_HINTS") ? atoi(getenv("GFFM_L2_HINTS")) : 0;
+    GemmParams q = p;
+    q.l2_hints = hints2;
+    q.fake_loads = 0;
+    gemm_tc_kernel_mc<S><<<clusters * 2, 192, C::SMEM_BYTES, st ? st : ctx->stream>>>(tmA, *tmB_half, q);
+    GFFM_LAUNCH_CHECK(ctx);
+    return GFFM_OK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     GFFM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -591,8 +847,10 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   const int total = p.batches * p.num_m_blk * p.num_n_blk;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
   static const int hints = getenv("GFFM_L2_HINTS") ? atoi(getenv("GFFM_L2_HINTS")) : 0;
+  static const int fake = getenv("GFFM_FAKE_LOADS") ? atoi(getenv("GFFM_FAKE_LOADS")) : 0;
   GemmParams q = p;
   q.l2_hints = hints;
+  q.fake_loads = fake;
   gemm_tc_kernel<S><<<grid, 192, C::SMEM_BYTES, st ? st : ctx->stream>>>(tmA, tmB, q);
   GFFM_LAUNCH_CHECK(ctx);
   return GFFM_OK;
@@ -797,8 +1055,10 @@ int32_t gffm_gemm_tc_limb_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView
     GFFM_TRY(acquire_planes(ctx, 1, B, B2, k0, kc, Kp, rowsPB, sp, 0, R, &ctx->ws_planes_b, &pb));
     prof_mark(ctx, 1);
     CUtensorMap tmA, tmB;
+    CUtensorMap tmBh;
     GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, L, BM));
     GFFM_TRY(make_plane_tmap(&tmB, pb, Kp, rowsPB, L, BN));
+    GFFM_TRY(make_plane_tmap(&tmBh, pb, Kp, rowsPB, L, BN / 2));
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.m = (int)m;
@@ -811,8 +1071,8 @@ int32_t gffm_gemm_tc_limb_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView
     p.ldc = Cv.ld;
     p.mode = (k0 == 0) ? mode : (mode == GFFM_GEMM_SUB ? GFFM_GEMM_SUB : GFFM_GEMM_ADD);
     p.modP = make_modp(P);
-    if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p));
-    else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p));
+    if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p, nullptr, &tmBh));
+    else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p, nullptr, &tmBh));
     prof_mark(ctx, 2);
   }
   return GFFM_OK;
@@ -859,9 +1119,10 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     GFFM_TRY(acquire_planes(ctx, 0, A, A2, k0, kc, Kp, rowsPA, spa, balanced ? 1 : 0, R, &ctx->ws_planes_a, &pa));
     GFFM_TRY(acquire_planes(ctx, 1, B, B2, k0, kc, Kp, rowsPB, spb, balanced ? 1 : 0, R, &ctx->ws_planes_b, &pb));
     prof_mark(ctx, 1);
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmBh;
     GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, s, BM));
     GFFM_TRY(make_plane_tmap(&tmB, pb, Kp, rowsPB, s, BN));
+    GFFM_TRY(make_plane_tmap(&tmBh, pb, Kp, rowsPB, s, BN / 2));
     p.m = (int)m;
     p.n = (int)n;
     p.num_kb = (int)(Kp / 128);
@@ -871,7 +1132,7 @@ int32_t gffm_gemm_tc_rns_ex(gffm_ctx* ctx, MatView Cv, MatView A, const MatView*
     p.E = (uint8_t*)ctx->ws_eplanes.ptr;
     p.lde = lde;
     p.e_plane_stride = e_plane;
-    GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p));
+    GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p, nullptr, &tmBh));
     prof_mark(ctx, 2);
     GFFM_TRY(launch_crt(ctx, ctx->stream, cp, (const uint8_t*)ctx->ws_eplanes.ptr, lde, e_plane, m, n, Cv.p, Cv.ld, kara_hi, ldhi));
     prof_mark(ctx, 3);
@@ -977,15 +1238,38 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     sp.nplanes = nplanes = L;
     sp.mode = 0;
   }
-  // block sizes: host mode up to 8x8 tiles (short tail after the last upload), device mode up to 4x4 (fewer launches)
-  const int64_t max_blocks = host ? 8 : 4, min_block = host ? 1024 : 2048;
-  auto pick = [&](int64_t extent, int64_t align) {
-    if (extent < 2 * min_block) return round_up(extent, align);
-    const int64_t nb = std::min<int64_t>(max_blocks, extent / min_block);
-    return round_up(ceil_div(extent, nb), align);
+  // block boundaries.  Host mode: up to 8 blocks per operand with DECREASING sizes (weights 6,6,5,5,4,3,2,1): the tiles that
+  // can only start after the last upload are the last block row/column, so small final blocks shorten the exposed tail.
+  // Device mode: up to 4 equal blocks (fewer launches).
+  auto boundaries = [&](int64_t extent, int64_t align) {
+    std::vector<int64_t> off{0};
+    const int64_t min_block = host ? 1024 : 2048;
+    if (extent < 2 * min_block) {
+      off.push_back(extent);
+      return off;
+    }
+    if (!host) {
+      const int64_t nb = std::min<int64_t>(4, extent / min_block);
+      const int64_t b = round_up(ceil_div(extent, nb), align);
+      for (int64_t o = b; o < extent; o += b) off.push_back(o);
+      off.push_back(extent);
+      return off;
+    }
+    static const int wts[8] = {6, 6, 5, 5, 4, 3, 2, 1};
+    const int64_t nb = std::min<int64_t>(8, extent / min_block);
+    int64_t wsum = 0;
+    for (int i = 0; i < nb; ++i) wsum += wts[8 - nb + i];
+    int64_t acc = 0;
+    for (int i = 0; i < nb - 1; ++i) {
+      acc += wts[8 - nb + i];
+      int64_t o = round_up(extent * acc / wsum, align);
+      if (o > off.back() && o < extent) off.push_back(o);
+    }
+    off.push_back(extent);
+    return off;
   };
-  const int64_t bm = pick(m, BM), bn = pick(n, BN);
-  const int nbA = (int)ceil_div(m, bm), nbB = (int)ceil_div(n, bn);
+  const std::vector<int64_t> offA = boundaries(m, BM), offB = boundaries(n, BN);
+  const int nbA = (int)offA.size() - 1, nbB = (int)offB.size() - 1;
   const int64_t Kp = round_up(k, 128), rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
   const int64_t lde = round_up(m, 128), e_plane = lde * n;
   // buffers
@@ -1040,9 +1324,10 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     GFFM_CUDA(cudaStreamWaitEvent(sh, ev0, 0));
     GFFM_CUDA(cudaStreamWaitEvent(sd, ev0, 0));
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBh;
   GFFM_TRY(make_plane_tmap(&tmA, pA, Kp, rowsPA, nplanes, BM));
   GFFM_TRY(make_plane_tmap(&tmB, pB, Kp, rowsPB, nplanes, BN));
+  GFFM_TRY(make_plane_tmap(&tmBh, pB, Kp, rowsPB, nplanes, BN / 2));
   const ModP mpR = make_modp(R), mpP = make_modp(P);
   const int nblk_mod = ctx->num_sms * 8;
   std::vector<cudaEvent_t> ev_split(steps);
@@ -1050,7 +1335,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
   // step t: make block t of A and of B available as planes (aux stream), one step ahead of the GEMM
   auto prepare = [&](int t) -> int32_t {
     if (t < nbA && !hitA) {
-      const int64_t i0 = t * bm, mi = std::min(bm, m - i0);
+      const int64_t i0 = offA[t], mi = offA[t + 1] - i0;
       if (host) {
         GFFM_CUDA(cudaMemcpy2DAsync(dA + i0, (size_t)ldA * 4, io->A + i0, (size_t)io->lda * 4, (size_t)mi * 4, (size_t)k, cudaMemcpyHostToDevice, sh));
         cudaEvent_t e = next_ev();
@@ -1063,7 +1348,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
       GFFM_TRY(run_split(ctx, true, v, nullptr, 0, k, pA + i0 * Kp, Kp, rowsPA, sp, sx));
     }
     if (t < nbB && !hitB) {
-      const int64_t j0 = t * bn, nj = std::min(bn, n - j0);
+      const int64_t j0 = offB[t], nj = offB[t + 1] - j0;
       if (host) {
         GFFM_CUDA(cudaMemcpy2DAsync(dB + j0 * ldB, (size_t)ldB * 4, io->B + j0 * io->ldb, (size_t)io->ldb * 4, (size_t)k * 4, (size_t)nj,
                                     cudaMemcpyHostToDevice, sh));
@@ -1086,7 +1371,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
   };
   std::vector<Pending> pending;
   auto gemm_tile = [&](int i, int j) -> int32_t {
-    const int64_t i0 = i * bm, mi = std::min(bm, m - i0), j0 = j * bn, nj = std::min(bn, n - j0);
+    const int64_t i0 = offA[i], mi = offA[i + 1] - i0, j0 = offB[j], nj = offB[j + 1] - j0;
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.m = (int)mi;
@@ -1108,15 +1393,15 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
       p.E = E + j0 * lde + i0;
       p.lde = lde;
       p.e_plane_stride = e_plane;
-      GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p, sc));
+      GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, p, sc, &tmBh));
     } else {
       p.batches = 1;
       p.C = dC + j0 * ldC + i0;
       p.ldc = ldC;
       p.mode = mode;
       p.modP = mpP;
-      if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p, sc));
-      else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p, sc));
+      if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p, sc, &tmBh));
+      else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p, sc, &tmBh));
     }
     if (ctx->profile) {
       GFFM_CUDA(cudaEventRecord(t1, sc));
@@ -1131,7 +1416,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
   // after the GEMM of a tile: CRT (aux stream) and, in host mode, the D2H copy of the finished C tile
   auto finish_tiles = [&]() -> int32_t {
     for (const Pending& t : pending) {
-      const int64_t i0 = t.i * bm, mi = std::min(bm, m - i0), j0 = t.j * bn, nj = std::min(bn, n - j0);
+      const int64_t i0 = offA[t.i], mi = offA[t.i + 1] - i0, j0 = offB[t.j], nj = offB[t.j + 1] - j0;
       cudaEvent_t ready = t.done;
       if (rns) {
         GFFM_CUDA(cudaStreamWaitEvent(sx, t.done, 0));
@@ -1154,6 +1439,12 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     ctx->tile_events.clear();
     ctx->n_ev = 0;
   }
+  const bool hprof = host && getenv("GFFM_HOST_PROF") != nullptr;
+  cudaEvent_t hp[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (hprof) {
+    for (auto& e : hp) cudaEventCreate(&e);
+    cudaEventRecord(hp[0], sh);
+  }
   int32_t st = prepare(0);
   for (int t = 0; t < steps && st == GFFM_OK; ++t) {
     if (t + 1 < steps) st = prepare(t + 1);  // issued first so that it overlaps the GEMMs of step t
@@ -1166,6 +1457,11 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     if (t < nbA && t < nbB && st == GFFM_OK) st = gemm_tile(t, t);
     if (st == GFFM_OK) st = finish_tiles();
   }
+  if (hprof) {
+    cudaEventRecord(hp[1], sh);
+    cudaEventRecord(hp[2], sc);
+    cudaEventRecord(hp[3], sd);
+  }
   // the compute stream continues only after the helpers are done (C complete, planes reusable)
   cudaEventRecord(ev_end, sx);
   cudaStreamWaitEvent(sc, ev_end, 0);
@@ -1173,6 +1469,14 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     cudaStreamSynchronize(sd);
     cudaStreamSynchronize(sh);
     cudaStreamSynchronize(sc);
+    if (hprof) {
+      float a = 0, b2 = 0, c2 = 0;
+      cudaEventElapsedTime(&a, hp[0], hp[1]);
+      cudaEventElapsedTime(&b2, hp[0], hp[2]);
+      cudaEventElapsedTime(&c2, hp[0], hp[3]);
+      fprintf(stderr, "[gemm_host] blocks %dx%d: H2D done %.2f ms, last GEMM done %.2f ms, last D2H done %.2f ms\n", nbA, nbB, a, b2, c2);
+      for (auto& e : hp) cudaEventDestroy(e);
+    }
   }
   if (st == GFFM_OK) {
     if (fillA) {
