@@ -273,12 +273,14 @@ def main():
         gemm_avg = statistics.mean(gemm_ms[1:] if len(gemm_ms) > 1 and world > 1 else gemm_ms) if gemm_ms else None
         achieved = int8_ops / (gemm_avg * 1e-3) / 1e12 if gemm_avg else None
         int8_peak = 2.0 * peaks["bf16"]
+        sustained_random = None
         peak_src = f"2 x bf16 dense {peaks['bf16']} TFLOP/s, {peaks['src']} (proxy: no int8 entry in MEASURED_PEAKS.json)"
         ip = os.path.join(ROOT, "profiles", "int8_peak.json")
         if os.path.exists(ip):  # measured by tools/int8_peak.cu on this pool's B200: back-to-back tcgen05 kind::i8 MMAs from resident smem
             try:
                 d8 = json.load(open(ip))
                 int8_peak = float(d8["int8_tops_sustained"])
+                sustained_random = d8.get("int8_tops_sustained_random_data")
                 peak_src = (f"measured int8 tensor-pipe peak {int8_peak} TOP/s (tools/int8_peak.cu: back-to-back tcgen05.mma kind::i8 128x256x32, operands "
                             f"resident in smem, all {d8.get('sms')} SMs, no HBM traffic so no power throttling); MEASURED_PEAKS.json has no int8 entry "
                             f"(its bf16 {peaks['bf16']} TFLOP/s x2 = {2*peaks['bf16']:.0f})")
@@ -295,6 +297,10 @@ def main():
                     "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": (achieved / int8_peak) if achieved else None,
                     "traffic": traffic, "launch_ms": gemm_avg, "int8_mma_units_per_k_step": units,
                     "peak_source": peak_src,
+                    # same microbenchmark with uniformly random operand bytes, run back to back for seconds: what the tensor pipe
+                    # sustains under the board power cap when NOTHING but MMAs runs (informational; frac uses the higher peak)
+                    "peak_sustained_random_operands": sustained_random,
+                    "frac_of_sustained_random": (achieved / sustained_random) if (achieved and sustained_random) else None,
                     "phases_ms_last_step": phase_ms}
 
         # ---- e2e through the public API with host buffers (rank-local shard; H2D A,B + GEMM + D2H C per step) --------

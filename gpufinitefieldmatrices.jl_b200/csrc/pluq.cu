@@ -42,7 +42,7 @@ struct PluqBufs {
   int* swp;          // [t] row swapped with row t when pivot t was chosen
   int* g_dst;        // composed gather list of the last panel: W[g_dst[e]] <- old W[g_src[e]]
   int* g_src;
-  const uint32_t* inv_table;  // [x] = x^-1 mod N for N <= 2^20 (batched once per modulus), else nullptr
+  const uint32_t* inv_table;  // [x] = x^-1 mod N for N <= 2^26 (batched once per modulus), else nullptr
   long long* prof;            // optional per-phase cycle counters of the panel kernel (GFFM_PANEL_PROF=1), else nullptr
 };
 
@@ -79,6 +79,60 @@ __device__ __forceinline__ uint32_t panel_fmamod(uint32_t a, uint32_t nl, uint32
     return (uint32_t)mod_u64((uint64_t)nl * u + a, mp);
   }
 }
+
+// compose the transpositions rb..r-1 of one panel into a single gather list (executed by one warp of CTA 0)
+__device__ __forceinline__ void compose_gather_list(const PluqBufs& b, int rb, int r, int m, int lane) {
+
+    const int k = r - rb;  // <= 32
+    int near = rb + lane;  // content (original row) now sitting at position rb+lane
+    int far_pos = -1, far_src = -1, nf = 0;
+    for (int s = 0; s < k; ++s) {
+      const int p = b.swp[rb + s];  // written by tid 0 of this CTA above
+      if (p == rb + s) continue;
+      const int mine = __shfl_sync(0xffffffffu, near, s);
+      if (p < rb + 32) {
+        const int other = __shfl_sync(0xffffffffu, near, p - rb);
+        if (lane == s) near = other;
+        if (lane == p - rb) near = mine;
+      } else {
+        unsigned hit = __ballot_sync(0xffffffffu, lane < nf && far_pos == p);
+        int e;
+        if (hit) e = __ffs(hit) - 1;
+        else {
+          e = nf++;
+          if (lane == e) {
+            far_pos = p;
+            far_src = p;
+          }
+        }
+        const int other = __shfl_sync(0xffffffffu, far_src, e);
+        if (lane == s) near = other;
+        if (lane == e) far_src = mine;
+      }
+    }
+    int cnt = 0;
+    // near entries that moved
+    const bool nm = lane < 32 && near != rb + lane && (rb + lane) < m;
+    unsigned nmask = __ballot_sync(0xffffffffu, nm);
+    if (nm) {
+      const int e = __popc(nmask & ((1u << lane) - 1));
+      b.g_dst[e] = rb + lane;
+      b.g_src[e] = near;
+    }
+    cnt = __popc(nmask);
+    const bool fm = lane < nf && far_src != far_pos;
+    unsigned fmask = __ballot_sync(0xffffffffu, fm);
+    if (fm) {
+      const int e = cnt + __popc(fmask & ((1u << lane) - 1));
+      b.g_dst[e] = far_pos;
+      b.g_src[e] = far_src;
+    }
+    cnt += __popc(fmask);
+    if (lane == 0) {
+      b.st->rb = rb;
+      b.st->n_gather = cnt;
+    }
+  }
 
 template <bool SMALL, int PANEL_THREADS>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
@@ -299,57 +353,399 @@ pluq_panel_kernel(uint32_t* __restrict__ W, int64_t ldw, int m, int j0, int w, u
   __syncthreads();
   PANEL_TICK(6)
   // ---- compose this panel's transpositions (rb..r-1) into one gather list (warp 0 of CTA 0)
-  if (rank == 0 && warp == 0) {
-    const int k = r - rb;  // <= 32
-    int near = rb + lane;  // content (original row) now sitting at position rb+lane
-    int far_pos = -1, far_src = -1, nf = 0;
-    for (int s = 0; s < k; ++s) {
-      const int p = b.swp[rb + s];  // written by tid 0 of this CTA above
-      if (p == rb + s) continue;
-      const int mine = __shfl_sync(0xffffffffu, near, s);
-      if (p < rb + 32) {
-        const int other = __shfl_sync(0xffffffffu, near, p - rb);
-        if (lane == s) near = other;
-        if (lane == p - rb) near = mine;
-      } else {
-        unsigned hit = __ballot_sync(0xffffffffu, lane < nf && far_pos == p);
-        int e;
-        if (hit) e = __ffs(hit) - 1;
-        else {
-          e = nf++;
-          if (lane == e) {
-            far_pos = p;
-            far_src = p;
-          }
-        }
-        const int other = __shfl_sync(0xffffffffu, far_src, e);
-        if (lane == s) near = other;
-        if (lane == e) far_src = mine;
+  if (rank == 0 && warp == 0) compose_gather_list(b, rb, r, m, lane);
+  cluster.sync();  // all CTAs read st->r long ago; order the final write after every CTA's last use
+  if (rank == 0 && tid == 0) b.st->r = r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// register-resident panel kernel (default when a CTA's row slice fits 2 rows per thread).  Same cluster layout and
+// same results as pluq_panel_kernel, different data flow:
+//   * every thread keeps its (up to) two panel rows in registers -- the pivot loop is fully unrolled so all column
+//     indices are static; the rank-1 update is pure register arithmetic (u is read from shared memory as a broadcast);
+//   * the argmax needs no scan: the thread-local candidates of column jj+1 are produced while column jj is being
+//     eliminated (column jj+1 is updated first), and the candidate's inverse is a table load issued at that point and
+//     consumed only after the warp reduction of the next pivot step;
+//   * candidates are PUSHED: every CTA scales its own candidate row by its own inverse and stores row + (value, index,
+//     inverse) into the shared memory of all CTAs before the cluster barrier, so after the barrier the winner, its
+//     normalised row u and the displaced row r are local -- one cluster barrier and two block barriers per pivot.
+// ---------------------------------------------------------------------------------------------------
+// ---- cluster push primitives: asynchronous remote shared-memory stores that credit their bytes to an mbarrier of the
+// DESTINATION CTA (st.async ... mbarrier::complete_tx::bytes).  The consumer waits on its own mbarrier for the expected
+// byte count: no fence, no cluster-wide barrier, and a CTA proceeds as soon as ITS data has landed.
+__device__ __forceinline__ uint32_t psm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t psm_remote(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(psm_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void pmbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(psm_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pmbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(psm_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pmbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(psm_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+struct PanelAr {
+  uint32_t P, mu, sh;  // ARITH 0: mu = floor(2^32 / P); ARITH 1: mu = floor(2^(32+sh) / P), sh = bits(P) - 1
+  ModP mp;
+};
+
+// ARITH 0: P <= 2^16 (32-bit Barrett);  1: 2^16 < P < 2^30 (quotient estimate from the top 32 bits);  2: generic 64-bit
+// Barrett;  3: P < 2^16 LAZY -- eliminated values stay in [0, 2P) (x = nl*u + a <= (P-1)^2 + 2P - 1 < 2^32), only the next
+// pivot column, published rows and the final store are brought back to [0, P);  4: 2^16 < P < 2^30 LAZY -- values stay in
+// [0, 2.6 P): with x < P^2 + 2.6 P the quotient estimate is still at most 2.6 short.
+template <int ARITH>
+__device__ __forceinline__ uint32_t pa_reduce(uint64_t x, const PanelAr& ar) {  // x < P^2 (ARITH 3: <= P^2), result < P
+  if constexpr (ARITH == 0 || ARITH == 3) {
+    const uint32_t x32 = (uint32_t)x;
+    const uint32_t r = x32 - __umulhi(x32, ar.mu) * ar.P;  // in [0, 2P)
+    return min(r, r - ar.P);
+  } else if constexpr (ARITH == 1 || ARITH == 4) {
+    const uint32_t xh = (uint32_t)(x >> ar.sh);
+    uint32_t r = (uint32_t)x - __umulhi(xh, ar.mu) * ar.P;  // in [0, 2.5 P)
+    r = min(r, r - ar.P);
+    return min(r, r - ar.P);
+  } else {
+    return (uint32_t)mod_u64(x, ar.mp);
+  }
+}
+template <int ARITH>
+__device__ __forceinline__ uint32_t pa_canon(uint32_t x, const PanelAr& ar) {
+  if constexpr (ARITH == 3) return min(x, x - ar.P);
+  if constexpr (ARITH == 4) {
+    x = min(x, x - ar.P);
+    return min(x, x - ar.P);
+  }
+  return x;
+}
+// (a + nl * u) mod P, nl, u < P; ARITH 3: a < 2P and the result is only < 2P
+template <int ARITH>
+__device__ __forceinline__ uint32_t pa_fmamod(uint32_t a, uint32_t nl, uint32_t u, const PanelAr& ar) {
+  if constexpr (ARITH == 3) {
+    const uint32_t x32 = nl * u + a;
+    return x32 - __umulhi(x32, ar.mu) * ar.P;
+  } else if constexpr (ARITH == 4) {
+    const uint64_t x = (uint64_t)nl * u + a;
+    return (uint32_t)x - __umulhi((uint32_t)(x >> ar.sh), ar.mu) * ar.P;
+  } else if constexpr (ARITH == 0) {
+    return pa_reduce<0>((uint64_t)(nl * u + a), ar);
+  } else {
+    return pa_reduce<ARITH>((uint64_t)nl * u + a, ar);
+  }
+}
+template <int ARITH>
+__device__ __forceinline__ uint32_t pa_mulmod(uint32_t a, uint32_t c, const PanelAr& ar) {  // a, c < P -> result < P
+  if constexpr (ARITH == 0 || ARITH == 3) return pa_reduce<ARITH>((uint64_t)(a * c), ar);
+  return pa_reduce<ARITH>((uint64_t)a * c, ar);
+}
+
+constexpr int PREG_ROWS = 1024;  // rows per CTA: PREG_RPT rows per thread, PREG_ROWS / PREG_RPT threads
+constexpr int PREG_MAXC = 16;    // largest cluster
+
+template <int ARITH, int PW, int PREG_RPT>
+__global__ void __launch_bounds__(PREG_ROWS / PREG_RPT, 1)
+pluq_panel_reg_kernel(uint32_t* __restrict__ Wm, int64_t ldw, int m, int j0, int w, uint32_t* __restrict__ Lm, int64_t ldl, PluqBufs b,
+                      const __grid_constant__ PanelAr ar) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int PREG_T = PREG_ROWS / PREG_RPT;
+  constexpr int NW = PREG_T / 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ uint32_t red_val[NW], red_inv[NW];
+  __shared__ int red_idx[NW];
+  __shared__ __align__(16) uint32_t rowbuf_w[NW][PW], rowbuf_r[PW];  // every warp publishes its own candidate row: no second block barrier
+  // filled by the asynchronous remote stores of every CTA (double-buffered by pivot parity); xbar[par] counts their bytes
+  __shared__ __align__(16) uint4 g_cand[2][PREG_MAXC];  // (value, row, inverse, -)
+  __shared__ __align__(16) uint32_t allrows[2][PREG_MAXC][PW];
+  __shared__ __align__(16) uint32_t oldr[2][PW];
+  __shared__ __align__(8) uint64_t xbar[2];
+  __shared__ int colpiv[PW];       // panel column -> pivot ordinal within this panel, or -1
+  __shared__ uint32_t pivval[PW];  // pivot value of ordinal s
+  __shared__ uint32_t pinv_s[PW];  // per ordinal: inverse, swap partner, column -- written to global memory once, at the end
+  __shared__ int swp_s[PW], pcol_s[PW];
+
+  const int rb = b.st->r;
+  const int rows_total = m - rb;
+  const int rows_c = (rows_total + cs - 1) / cs;
+  const int my_lo = rb + rank * rows_c;
+  int my_n = rows_total - rank * rows_c;
+  my_n = my_n < 0 ? 0 : (my_n > rows_c ? rows_c : my_n);
+  const uint32_t P = ar.P;
+  // optional cycle counters (GFFM_PANEL_PROF=1): accumulated in shared memory by thread 0 of CTA 0, flushed once at the end
+  __shared__ long long prof_s[8];
+  const bool do_prof = b.prof != nullptr && rank == 0 && tid == 0;
+  if (do_prof)
+    for (int i = 0; i < 8; ++i) prof_s[i] = 0;
+  long long tprev = do_prof ? clock64() : 0;
+#define PREG_TICK(slot)                          \
+  if (do_prof) {                                 \
+    const long long tn = clock64();              \
+    prof_s[slot] += tn - tprev;                  \
+    tprev = clock64();                           \
+  }
+
+  uint32_t a[PREG_RPT][PW];
+  int gi[PREG_RPT];  // global row of slot k, or -1
+#pragma unroll
+  for (int k = 0; k < PREG_RPT; ++k) {
+    const int q = tid + PREG_T * k;
+    gi[k] = q < my_n ? my_lo + q : -1;
+#pragma unroll
+    for (int c = 0; c < PW; ++c) a[k][c] = (gi[k] >= 0 && c < w) ? Wm[(int64_t)(j0 + c) * ldw + gi[k]] : 0u;
+  }
+  if (tid < PW) colpiv[tid] = -1;
+  if (tid == 0) {
+    pmbar_init(&xbar[0], 1);
+    pmbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t xbytes = (uint32_t)cs * (PW * 4 + 16) + PW * 4;  // per pivot: every CTA's row + candidate, and row r once
+  cluster.sync();  // everybody has read st->r before anyone can finish and overwrite it; shared arrays + mbarriers exist cluster-wide
+  PREG_TICK(0)
+
+  int r = rb;
+  // The panel is kept ROTATED: at pivot step jj register position pos holds logical column (jj + pos) mod PW, so the
+  // pivot column is always position 0 and every register index below is static although jj is a run-time loop counter.
+  // The rotation by one position is folded into the elimination (results are written one position to the left).
+  // thread-local candidate of the current column: (value, row) and -- table path -- its inverse (load in flight)
+  uint32_t lv = 0, linv = 0;
+  int li = 0x7fffffff;
+  auto local_cand = [&](int rmin) {
+    lv = 0;
+    li = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < PREG_RPT; ++k) {
+      if (gi[k] >= rmin && better(a[k][0], gi[k], lv, li)) {
+        lv = a[k][0];
+        li = gi[k];
       }
     }
-    int cnt = 0;
-    // near entries that moved
-    const bool nm = lane < 32 && near != rb + lane && (rb + lane) < m;
-    unsigned nmask = __ballot_sync(0xffffffffu, nm);
-    if (nm) {
-      const int e = __popc(nmask & ((1u << lane) - 1));
-      b.g_dst[e] = rb + lane;
-      b.g_src[e] = near;
+    linv = (lv && b.inv_table) ? b.inv_table[lv] : 0u;
+  };
+  // copy the row held in slot `hi` to shared memory: one branch per slot keeps the register indices static; 128-bit stores
+  auto store_row = [&](uint32_t* dst, bool hi) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    if (PREG_RPT == 2 && hi) {
+#pragma unroll
+      for (int c = 0; c < PW; c += 4) d4[c >> 2] = make_uint4(a[PREG_RPT - 1][c], a[PREG_RPT - 1][c + 1], a[PREG_RPT - 1][c + 2], a[PREG_RPT - 1][c + 3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < PW; c += 4) d4[c >> 2] = make_uint4(a[0][c], a[0][c + 1], a[0][c + 2], a[0][c + 3]);
     }
-    cnt = __popc(nmask);
-    const bool fm = lane < nf && far_src != far_pos;
-    unsigned fmask = __ballot_sync(0xffffffffu, fm);
-    if (fm) {
-      const int e = cnt + __popc(fmask & ((1u << lane) - 1));
-      b.g_dst[e] = far_pos;
-      b.g_src[e] = far_src;
+  };
+  local_cand(r);
+
+  int jj = 0;
+  for (; jj < w && r < m; ++jj) {
+    const int par = jj & 1;
+    if (tid == 0) pmbar_expect_tx(&xbar[par], xbytes);
+    // the owner of row r publishes it (raw) before anything modifies it
+    const int qr = r - my_lo;
+    const bool owns_r = qr >= 0 && qr < my_n;
+    if (owns_r && ((qr & (PREG_T - 1)) >> 5) == warp) {  // warp-uniform: 15 of 16 warps skip the copy code entirely
+      if ((qr & 31) == lane) store_row(rowbuf_r, qr >= PREG_T);
     }
-    cnt += __popc(fmask);
-    if (lane == 0) {
-      b.st->rb = rb;
-      b.st->n_gather = cnt;
+    // ---- warp argmax (max residue, first index) on the REDUX unit; the winning lane publishes value, row index, inverse and
+    // its whole row, so the block-level decision below needs no further barrier
+    {
+      const uint32_t wv = __reduce_max_sync(FULL, lv);
+      const int wi = __reduce_min_sync(FULL, lv == wv ? li : 0x7fffffff);
+      if (wv == 0) {
+        if (lane == 0) red_val[warp] = 0u;
+      } else if (lv == wv && li == wi) {
+        red_val[warp] = wv;
+        red_idx[warp] = wi;
+        red_inv[warp] = b.inv_table ? linv : modinv_u32(wv, P);
+        store_row(rowbuf_w[warp], wi == gi[PREG_RPT - 1]);
+      }
+    }
+    __syncthreads();  // S1
+    PREG_TICK(1)
+    // ---- block argmax, redundantly in every warp
+    uint32_t bv, biv = 0;
+    int bi, ww;
+    {
+      const uint32_t v = lane < NW ? red_val[lane] : 0u;
+      const int i = (lane < NW && v) ? red_idx[lane] : 0x7fffffff;
+      bv = __reduce_max_sync(FULL, v);
+      bi = __reduce_min_sync(FULL, v == bv ? i : 0x7fffffff);
+      const unsigned hit = __ballot_sync(FULL, v == bv && i == bi);
+      ww = hit ? __ffs(hit) - 1 : 0;
+      if (bv) biv = red_inv[ww];
+    }
+    PREG_TICK(2)
+    // ---- push: warp d sends this CTA's candidate (normalised row, value, index, inverse) and, if owned, row r to CTA d.
+    // Lanes 0..PW/4-1 carry four columns each (one 16-byte st.async), the next lane the candidate record.
+    if (warp < cs) {
+      const uint32_t rbar = psm_remote(&xbar[par], warp);
+      if (lane < PW / 4) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (bv != 0) {
+          const uint4 x4 = *reinterpret_cast<const uint4*>(&rowbuf_w[ww][4 * lane]);
+          const uint32_t x[4] = {x4.x, x4.y, x4.z, x4.w};
+          uint32_t y[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int pos = 4 * lane + e;
+            const uint32_t xc = pa_canon<ARITH>(x[e], ar);
+            // pivot -> 1, columns right of it (and the zero padding) scaled by the inverse; the wrapped-around positions
+            // >= PW - jj hold the multipliers of earlier pivots, which move with the row unchanged
+            y[e] = pos == 0 ? 1u % P : (pos < PW - jj ? pa_mulmod<ARITH>(xc, biv, ar) : xc);
+          }
+          v = make_uint4(y[0], y[1], y[2], y[3]);
+        }
+        st_async_v4(psm_remote(&allrows[par][rank][4 * lane], warp), v, rbar);
+        if (owns_r) {
+          const uint4 o4 = *reinterpret_cast<const uint4*>(&rowbuf_r[4 * lane]);
+          st_async_v4(psm_remote(&oldr[par][4 * lane], warp),
+                      make_uint4(pa_canon<ARITH>(o4.x, ar), pa_canon<ARITH>(o4.y, ar), pa_canon<ARITH>(o4.z, ar), pa_canon<ARITH>(o4.w, ar)), rbar);
+        }
+      } else if (lane == PW / 4) {
+        st_async_v4(psm_remote(&g_cand[par][rank], warp), make_uint4(bv, (uint32_t)bi, biv, 0u), rbar);
+      }
+    }
+    PREG_TICK(3)
+    pmbar_wait_cluster(&xbar[par], (uint32_t)(jj >> 1) & 1u);
+    PREG_TICK(4)
+    // ---- global winner, selected redundantly by every warp from local shared memory
+    uint32_t pv;
+    int p, src;
+    {
+      const uint32_t v = lane < cs ? g_cand[par][lane].x : 0u;
+      const int i = (lane < cs && v) ? (int)g_cand[par][lane].y : 0x7fffffff;
+      pv = __reduce_max_sync(FULL, v);
+      p = __reduce_min_sync(FULL, v == pv ? i : 0x7fffffff);
+      const unsigned hit = __ballot_sync(FULL, v == pv && i == p);
+      src = hit ? __ffs(hit) - 1 : 0;
+    }
+    const bool have = pv != 0;  // false: no pivot in this column (uniform over the cluster): skip it, row r stays
+    if (have && tid == 0) {
+      const int s_ord = r - rb;
+      colpiv[jj] = s_ord;
+      pivval[s_ord] = pv;
+      pinv_s[s_ord] = g_cand[par][src].z;
+      swp_s[s_ord] = p;
+      pcol_s[s_ord] = j0 + jj;
+    }
+    PREG_TICK(5)
+    // ---- swap rows r <-> p, eliminate and rotate (registers only)
+    const uint32_t* u = allrows[par][src];
+    uint32_t nl[PREG_RPT], keep[PREG_RPT];
+#pragma unroll
+    for (int k = 0; k < PREG_RPT; ++k) {
+      // rows r and p are replaced; the test is made warp-uniform first so that the 2 x 32 copies are real branches that
+      // (almost) every warp skips instead of predicated code executed by all
+      if (have && __any_sync(FULL, gi[k] == r || gi[k] == p)) {
+        if (gi[k] == r) {
+#pragma unroll
+          for (int c = 0; c < PW; ++c) a[k][c] = u[c];
+        } else if (gi[k] == p) {  // position p receives the old row r (its multipliers of earlier pivots included)
+#pragma unroll
+          for (int c = 0; c < PW; ++c) a[k][c] = oldr[par][c];
+        }
+      }
+      const uint32_t l = a[k][0];  // below the pivot: becomes L[i][t] at store-back
+      nl[k] = (have && gi[k] > r && l) ? P - l : 0u;
+      keep[k] = l;
+    }
+    const int nact = have ? PW - 1 - jj : 0;  // positions 1..nact are the columns right of the pivot
+    const int rnext = have ? r + 1 : r;
+    // position 1 first: it is the next pivot column, its candidates (and the inverse-table load) start right away
+    {
+      const uint32_t u1 = u[1];
+#pragma unroll
+      for (int k = 0; k < PREG_RPT; ++k) a[k][0] = pa_canon<ARITH>(nact >= 1 ? pa_fmamod<ARITH>(a[k][1], nl[k], u1, ar) : a[k][1], ar);
+      local_cand(rnext);
+    }
+#pragma unroll
+    for (int g = 2; g < PW; g += 4) {
+      if (g <= nact) {  // uniform: groups of four positions that (mostly) need the update
+#pragma unroll
+        for (int pos = g; pos < g + 4 && pos < PW; ++pos) {
+          const uint32_t uc = u[pos];
+#pragma unroll
+          for (int k = 0; k < PREG_RPT; ++k) a[k][pos - 1] = pos <= nact ? pa_fmamod<ARITH>(a[k][pos], nl[k], uc, ar) : a[k][pos];
+        }
+      } else {
+#pragma unroll
+        for (int pos = g; pos < g + 4 && pos < PW; ++pos)
+#pragma unroll
+          for (int k = 0; k < PREG_RPT; ++k) a[k][pos - 1] = a[k][pos];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PREG_RPT; ++k) a[k][PW - 1] = keep[k];
+    r = rnext;
+    PREG_TICK(6)
+  }
+  // undo the remaining rotation so that position == logical column again
+  for (; jj < PW; ++jj) {
+#pragma unroll
+    for (int k = 0; k < PREG_RPT; ++k) {
+      const uint32_t t0 = a[k][0];
+#pragma unroll
+      for (int pos = 1; pos < PW; ++pos) a[k][pos - 1] = a[k][pos];
+      a[k][PW - 1] = t0;
     }
   }
+  __syncthreads();
+  // ---- store-back: pivot columns split into U (rows <= pivot row) and L (rows below), everything else is W
+#pragma unroll
+  for (int c = 0; c < PW; ++c) {
+    if (c < w) {
+      const int s_ord = colpiv[c];
+      const int t = rb + s_ord;
+#pragma unroll
+      for (int k = 0; k < PREG_RPT; ++k) {
+        const int i = gi[k];
+        if (i < 0) continue;
+        const uint32_t v = pa_canon<ARITH>(a[k][c], ar);
+        uint32_t* wdst = Wm + (int64_t)(j0 + c) * ldw + i;
+        if (s_ord < 0 || i < t) {
+          *wdst = v;
+        } else if (i == t) {
+          *wdst = v;  // == 1
+          Lm[(int64_t)t * ldl + i] = pivval[s_ord];
+        } else {
+          *wdst = 0;
+          Lm[(int64_t)t * ldl + i] = v;
+        }
+      }
+    }
+  }
+  if (rank == 0 && tid < r - rb) {
+    b.pivcol[rb + tid] = pcol_s[tid];
+    b.pinv[rb + tid] = pinv_s[tid];
+    b.swp[rb + tid] = swp_s[tid];
+  }
+  __syncthreads();
+  PREG_TICK(7)
+  if (do_prof)
+    for (int i = 0; i < 8; ++i) b.prof[i] += prof_s[i];
+  if (rank == 0 && warp == 0) compose_gather_list(b, rb, r, m, lane);
   cluster.sync();  // all CTAs read st->r long ago; order the final write after every CTA's last use
   if (rank == 0 && tid == 0) b.st->r = r;
 }
@@ -646,8 +1042,77 @@ int panel_cluster_size(gffm_ctx* ctx) {
   return chosen;
 }
 
+PanelAr make_panel_ar(const ModP& mp) {
+  PanelAr ar;
+  memset(&ar, 0, sizeof(ar));
+  ar.P = (uint32_t)mp.P;
+  ar.mp = mp;
+  if (mp.P <= 65536) {
+    ar.mu = (uint32_t)((1ull << 32) / mp.P);
+  } else if (mp.P < (1ull << 30)) {
+    int bits = 0;
+    while ((mp.P >> bits) != 0) ++bits;
+    ar.sh = (uint32_t)(bits - 1);
+    const unsigned __int128 q = ((unsigned __int128)1 << (32 + ar.sh)) / mp.P;
+    ar.mu = q > 0xffffffffull ? 0xffffffffu : (uint32_t)q;
+  }
+  return ar;
+}
+int panel_arith(const ModP& mp) { return mp.P < 65536 ? 3 : (mp.P == 65536 ? 0 : (mp.P < (1ull << 30) ? 4 : 2)); }
+
+template <int ARITH, int PW, int RPT>
+int32_t launch_panel_reg_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int cluster, const PluqBufs& b, const ModP& mp) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pluq_panel_reg_kernel<ARITH, PW, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaGetLastError();
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster);
+  cfg.blockDim = dim3(PREG_ROWS / RPT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const PanelAr ar = make_panel_ar(mp);
+  GFFM_CUDA(cudaLaunchKernelEx(&cfg, (pluq_panel_reg_kernel<ARITH, PW, RPT>), W->data, W->ld, (int)W->rows, j0, w, L->data, L->ld, b, ar));
+  ctx->launches++;
+  return GFFM_OK;
+}
+
+// register-resident panel: needs rows_c <= PREG_ROWS and a panel of at most 32 columns
+bool panel_reg_enabled() {
+  static const bool on = !(getenv("GFFM_PANEL_REG") && atoi(getenv("GFFM_PANEL_REG")) == 0);
+  return on;
+}
+int32_t launch_panel_reg(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int cluster, const PluqBufs& b, const ModP& mp) {
+  const int ar = panel_arith(mp);
+  static const int rpt = (getenv("GFFM_PANEL_RPT") && atoi(getenv("GFFM_PANEL_RPT")) == 1) ? 1 : 2;
+#define GFFM_PREG(A)                                                                                                   \
+  {                                                                                                                    \
+    if (rpt == 2)                                                                                                      \
+      return w <= 16 ? launch_panel_reg_t<A, 16, 2>(ctx, W, L, j0, w, cluster, b, mp)                                  \
+                     : launch_panel_reg_t<A, 32, 2>(ctx, W, L, j0, w, cluster, b, mp);                                 \
+    return w <= 16 ? launch_panel_reg_t<A, 16, 1>(ctx, W, L, j0, w, cluster, b, mp)                                    \
+                   : launch_panel_reg_t<A, 32, 1>(ctx, W, L, j0, w, cluster, b, mp);                                   \
+  }
+  if (ar == 3) GFFM_PREG(3)
+  if (ar == 0) GFFM_PREG(0)
+  if (ar == 4) GFFM_PREG(4)
+  GFFM_PREG(2)
+#undef GFFM_PREG
+}
+
 int32_t launch_panel(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int rows_c_max, int cluster, const PluqBufs& b,
                      const ModP& mp) {
+  if (panel_reg_enabled() && rows_c_max <= PREG_ROWS && w <= 32) return launch_panel_reg(ctx, W, L, j0, w, cluster, b, mp);
   if (panel_threads() == 256) {
     if (mp.P <= 65536) return launch_panel_t<true, 256>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
     return launch_panel_t<false, 256>(ctx, W, L, j0, w, rows_c_max, cluster, b, mp);
@@ -709,7 +1174,8 @@ int32_t base_block(ElimState& E, int c_lo, int c_hi) {
   // measured on B200 (profiles/r01_notes.md): 32-column panels win for 16-bit moduli (cheap 32-bit arithmetic in the rank-1
   // update), 16 columns for larger ones
   static const int w_env = getenv("GFFM_PANEL_W") ? std::max(1, std::min(PANEL_W_MAX, atoi(getenv("GFFM_PANEL_W")))) : 0;
-  const int w_cap = w_env ? w_env : (E.N <= 65536 ? 32 : 16);
+  const bool reg_path = panel_reg_enabled() && rows_c_max <= PREG_ROWS;
+  const int w_cap = w_env ? w_env : ((E.N <= 65536 || reg_path) ? 32 : 16);
   w = std::min(w, w_cap);
   if (w < 1) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "matrix has too many rows (%d) for the panel kernel", m);
   for (int j0 = c_lo; j0 < c_hi; j0 += w) {
@@ -872,7 +1338,7 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
     b.prof = (long long*)ctx->ws_misc.ptr;
   }
   b.inv_table = nullptr;
-  if (N <= (1u << 20)) {  // batched modular inverses: one kernel computes every inverse mod N, cached per context
+  if (N <= (1u << 26)) {  // batched modular inverses: one kernel computes every inverse mod N (<= 256 MiB), cached per context
     if (ctx->inv_table_N != N) {
       GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_invtab, (size_t)N * 4));
       inv_table_kernel<<<(unsigned)ceil_div((int64_t)N, 256), 256, 0, ctx->stream>>>((uint32_t*)ctx->ws_invtab.ptr, (uint32_t)N);
@@ -897,12 +1363,15 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
     long long h[16];
     cudaMemcpyAsync(h, b.prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    static const char* names[7] = {"load+sync", "A scan+inverse+S1+publish", "cluster.sync", "B dsmem gather+S2+select", "u row + S3",
-                                   "C update (warp 0)", "store-back"};
+    static const char* names_smem[8] = {"load+sync", "A scan+inverse+S1+publish", "cluster.sync", "B dsmem gather+S2+select", "u row + S3",
+                                        "C update (warp 0)", "store-back", "-"};
+    static const char* names_reg[8] = {"load+sync", "warp argmax + S1", "block argmax + S1b", "push (remote stores)", "cluster.sync",
+                                       "select winner", "eliminate+rotate (thread 0)", "store-back"};
+    const char** names = panel_reg_enabled() ? names_reg : names_smem;
     long long tot = 0;
-    for (int i = 0; i < 7; ++i) tot += h[i];
+    for (int i = 0; i < 8; ++i) tot += h[i];
     fprintf(stderr, "[panel prof] total %.3f Mcycles over %d pivots\n", tot / 1e6, r0);
-    for (int i = 0; i < 7; ++i) fprintf(stderr, "  %-24s %10.3f Mcyc  %5.1f%%  %8.1f cyc/pivot\n", names[i], h[i] / 1e6, 100.0 * h[i] / tot, (double)h[i] / std::max(r0, 1));
+    for (int i = 0; i < 8; ++i) fprintf(stderr, "  %-24s %10.3f Mcyc  %5.1f%%  %8.1f cyc/pivot\n", names[i], h[i] / 1e6, 100.0 * h[i] / tot, (double)h[i] / std::max(r0, 1));
   }
   if (ctx->profile) {
     ctx->n_ev = 0;
