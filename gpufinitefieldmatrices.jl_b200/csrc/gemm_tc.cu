@@ -1124,7 +1124,9 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
     attr_set = true;
   }
   const int total = p.batches * p.num_m_blk * p.num_n_blk;
-  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+  static const int max_ctas = getenv("GFFM_GEMM_CTAS") ? atoi(getenv("GFFM_GEMM_CTAS")) : 0;  // experiment: leave SMs to concurrent kernels
+  const int sms = (max_ctas > 0 && max_ctas < ctx->num_sms) ? max_ctas : ctx->num_sms;
+  const int grid = total < sms ? total : sms;
   static const int hints = getenv("GFFM_L2_HINTS") ? atoi(getenv("GFFM_L2_HINTS")) : 0;
   static const int fake = getenv("GFFM_FAKE_LOADS") ? atoi(getenv("GFFM_FAKE_LOADS")) : 0;
   GemmParams q = p;

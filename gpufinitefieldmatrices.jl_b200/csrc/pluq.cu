@@ -407,8 +407,22 @@ __device__ __forceinline__ void pmbar_wait_cluster(uint64_t* bar, uint32_t parit
 
 struct PanelAr {
   uint32_t P, mu, sh;  // ARITH 0: mu = floor(2^32 / P); ARITH 1: mu = floor(2^(32+sh) / P), sh = bits(P) - 1
+  uint32_t mu2, sh2;   // left-looking kernel, any P < 2^29: sh2 = bits(P) - 1, mu2 = min(floor(2^(32+sh2) / P), 2^32 - 1)
   ModP mp;
 };
+
+// x < 32 * P^2 -> x mod P.  For P < 2^26 the top 32 bits of x give a quotient estimate that is at most 4 short, so the
+// remainder fits 32 bits and three conditional subtractions finish the job; larger P take the generic 64-bit Barrett.
+__device__ __forceinline__ uint32_t ll_reduce(uint64_t x, const PanelAr& ar) {
+  if (ar.sh2 <= 25) {
+    const uint32_t xh = (uint32_t)(x >> ar.sh2);
+    uint32_t r = (uint32_t)x - __umulhi(xh, ar.mu2) * ar.P;
+    r = min(r, r - ar.P);
+    r = min(r, r - ar.P);
+    return min(r, r - ar.P);
+  }
+  return (uint32_t)mod_u64(x, ar.mp);
+}
 
 // ARITH 0: P <= 2^16 (32-bit Barrett);  1: 2^16 < P < 2^30 (quotient estimate from the top 32 bits);  2: generic 64-bit
 // Barrett;  3: P < 2^16 LAZY -- eliminated values stay in [0, 2P) (x = nl*u + a <= (P-1)^2 + 2P - 1 < 2^32), only the next
@@ -751,6 +765,340 @@ pluq_panel_reg_kernel(uint32_t* __restrict__ Wm, int64_t ldw, int m, int j0, int
 }
 
 // ---------------------------------------------------------------------------------------------------
+// LEFT-LOOKING register panel kernel (default for P < 2^29).  Same layout and exchange protocol as
+// pluq_panel_reg_kernel, but a pivot no longer updates all remaining panel columns (3 multiplies per element and
+// pivot on the half-rate integer pipe).  Instead a column is brought up to date only when it becomes the pivot column:
+//   a[i][jj] -= sum_{t < jj} l[i][t] * U[t][jj]      one 32x32+64 multiply-add per term, ONE reduction per row and pivot
+// with the multipliers l[i][t] read from the row's own registers and U (the normalised pivot rows of this panel) from a
+// PW x PW table in shared memory.  The candidate row of every CTA gets the same treatment for ALL its remaining
+// columns by the pushing warps (lane = column), so the pushed row is the final normalised pivot row.
+// Registers are rotated by four positions after every fourth pivot; inside a group of four the pivot position is static.
+// ---------------------------------------------------------------------------------------------------
+template <int PW, bool PROF>
+__global__ void __launch_bounds__(512, 1)
+pluq_panel_ll_kernel(uint32_t* __restrict__ Wm, int64_t ldw, int m, int j0, int w, uint32_t* __restrict__ Lm, int64_t ldl, PluqBufs b,
+                     const __grid_constant__ PanelAr ar) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int T = 512, NW = T / 32, RPT = 2;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ uint32_t red_val[NW], red_inv[NW];
+  __shared__ int red_idx[NW];
+  __shared__ __align__(16) uint32_t rowbuf_w[NW][PW], rowbuf_r[PW];
+  __shared__ __align__(16) uint4 g_cand[2][PREG_MAXC];  // (value, row, inverse, -)
+  __shared__ __align__(16) uint32_t allrows[2][PREG_MAXC][PW];
+  __shared__ __align__(16) uint32_t oldr[2][PW];
+  __shared__ __align__(8) uint64_t xbar[2];
+  __shared__ uint32_t Utab[PW][PW];  // [pivot column t][logical column c]: normalised pivot rows (zero row for a skipped column)
+  __shared__ int colpiv[PW];
+  __shared__ uint32_t pivval[PW], pinv_s[PW];
+  __shared__ int swp_s[PW], pcol_s[PW];
+
+  const int rb = b.st->r;
+  const int rows_total = m - rb;
+  const int rows_c = (rows_total + cs - 1) / cs;
+  const int my_lo = rb + rank * rows_c;
+  int my_n = rows_total - rank * rows_c;
+  my_n = my_n < 0 ? 0 : (my_n > rows_c ? rows_c : my_n);
+  const uint32_t P = ar.P;
+  __shared__ long long prof_s[8];
+  const bool do_prof = PROF && b.prof != nullptr && rank == 0 && tid == 0;
+  if (do_prof)
+    for (int i = 0; i < 8; ++i) prof_s[i] = 0;
+  long long tprev = do_prof ? clock64() : 0;
+#define PLL_TICK(slot)                           \
+  if (PROF && do_prof) {                         \
+    const long long tn = clock64();              \
+    prof_s[slot] += tn - tprev;                  \
+    tprev = clock64();                           \
+  }
+
+  uint32_t a[RPT][PW];
+  int gi[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int q = tid + T * k;
+    gi[k] = q < my_n ? my_lo + q : -1;
+#pragma unroll
+    for (int c = 0; c < PW; ++c) a[k][c] = (gi[k] >= 0 && c < w) ? Wm[(int64_t)(j0 + c) * ldw + gi[k]] : 0u;
+  }
+  if (tid < PW) colpiv[tid] = -1;
+  if (tid == 0) {
+    pmbar_init(&xbar[0], 1);
+    pmbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t xbytes = (uint32_t)cs * (PW * 4 + 16) + PW * 4;
+  cluster.sync();
+  PLL_TICK(0)
+
+  int r = rb;
+  uint32_t lv = 0, linv = 0;
+  int li = 0x7fffffff;
+  auto store_row = [&](uint32_t* dst, bool hi) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    if (hi) {
+#pragma unroll
+      for (int c = 0; c < PW; c += 4) d4[c >> 2] = make_uint4(a[1][c], a[1][c + 1], a[1][c + 2], a[1][c + 3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < PW; c += 4) d4[c >> 2] = make_uint4(a[0][c], a[0][c + 1], a[0][c + 2], a[0][c + 3]);
+    }
+  };
+  // candidates of the column at register position 0..3 (static S)
+#define PLL_LOCAL_CAND(S, RMIN)                                             \
+  {                                                                         \
+    lv = 0;                                                                 \
+    li = 0x7fffffff;                                                        \
+    if (gi[0] >= (RMIN) && better(a[0][S], gi[0], lv, li)) {                \
+      lv = a[0][S];                                                         \
+      li = gi[0];                                                           \
+    }                                                                       \
+    if (gi[1] >= (RMIN) && better(a[1][S], gi[1], lv, li)) {                \
+      lv = a[1][S];                                                         \
+      li = gi[1];                                                           \
+    }                                                                       \
+    linv = (lv && b.inv_table) ? b.inv_table[lv] : 0u;                      \
+  }
+  PLL_LOCAL_CAND(0, r)
+
+  int J4 = 0;  // 4 * (group index): register position pos holds logical column (J4 + pos) mod PW
+  bool done = false;
+  for (; J4 < PW && !done; J4 += 4) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int jj = J4 + s;
+      if (jj >= w || r >= m) {
+        done = true;
+        break;
+      }
+      const int par = jj & 1;
+      if (tid == 0) pmbar_expect_tx(&xbar[par], xbytes);
+      const int qr = r - my_lo;
+      const bool owns_r = qr >= 0 && qr < my_n;
+      if (owns_r && ((qr & (T - 1)) >> 5) == warp) {
+        if ((qr & 31) == lane) store_row(rowbuf_r, qr >= T);
+      }
+      // ---- warp argmax; the winning lane publishes value, row index, inverse and its whole row
+      {
+        const uint32_t wv = __reduce_max_sync(FULL, lv);
+        const int wi = __reduce_min_sync(FULL, lv == wv ? li : 0x7fffffff);
+        if (wv == 0) {
+          if (lane == 0) red_val[warp] = 0u;
+        } else if (lv == wv && li == wi) {
+          red_val[warp] = wv;
+          red_idx[warp] = wi;
+          red_inv[warp] = b.inv_table ? linv : modinv_u32(wv, P);
+          store_row(rowbuf_w[warp], wi == gi[1]);
+        }
+      }
+      __syncthreads();  // S1
+      PLL_TICK(1)
+      uint32_t bv, biv = 0;
+      int bi, ww;
+      {
+        const uint32_t v = lane < NW ? red_val[lane] : 0u;
+        const int i = (lane < NW && v) ? red_idx[lane] : 0x7fffffff;
+        bv = __reduce_max_sync(FULL, v);
+        bi = __reduce_min_sync(FULL, v == bv ? i : 0x7fffffff);
+        const unsigned hit = __ballot_sync(FULL, v == bv && i == bi);
+        ww = hit ? __ffs(hit) - 1 : 0;
+        if (bv) biv = red_inv[ww];
+      }
+      PLL_TICK(2)
+      // ---- push: lane = register position.  Columns right of the pivot are first brought up to date with the jj earlier
+      // pivots of this panel (dot product of the row's multipliers with a column of Utab), then scaled by the inverse.
+      if (warp < cs) {
+        const uint32_t rbar = psm_remote(&xbar[par], warp);
+        if (lane < PW) {
+          uint32_t v = 0;
+          if (bv != 0) {
+            const uint32_t* rw = rowbuf_w[ww];
+            const uint32_t x = rw[lane];
+            if (lane == s) {
+              v = 1u % P;
+            } else if (lane > s && lane < PW - J4) {  // a column right of the pivot (or zero padding)
+              const int col = J4 + lane;
+              uint64_t acc0 = 0, acc1 = 0;  // two chains, loads of four terms in flight together
+              for (int e = 0; e < J4; e += 4) {  // older groups (wrapped positions)
+                const uint32_t l0 = rw[PW - 1 - e], l1 = rw[PW - 2 - e], l2 = rw[PW - 3 - e], l3 = rw[PW - 4 - e];
+                const uint32_t u0 = Utab[J4 - 1 - e][col], u1 = Utab[J4 - 2 - e][col], u2 = Utab[J4 - 3 - e][col], u3 = Utab[J4 - 4 - e][col];
+                acc0 += (uint64_t)l0 * u0;
+                acc1 += (uint64_t)l1 * u1;
+                acc0 += (uint64_t)l2 * u2;
+                acc1 += (uint64_t)l3 * u3;
+              }
+#pragma unroll
+              for (int sp = 0; sp < s; ++sp) acc0 += (uint64_t)rw[sp] * Utab[J4 + sp][col];  // this group
+              const uint32_t am = ll_reduce(acc0 + acc1, ar);
+              const uint32_t xu = x >= am ? x - am : x + P - am;
+              v = ll_reduce((uint64_t)xu * biv, ar);
+            } else {
+              v = x;  // multipliers of earlier pivots move with the row unchanged
+            }
+          }
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
+                           psm_remote(&allrows[par][rank][lane], warp)),
+                       "r"(v), "r"(rbar)
+                       : "memory");
+          if (owns_r)
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
+                             psm_remote(&oldr[par][lane], warp)),
+                         "r"(rowbuf_r[lane]), "r"(rbar)
+                         : "memory");
+        }
+        if (lane == 0) st_async_v4(psm_remote(&g_cand[par][rank], warp), make_uint4(bv, (uint32_t)bi, biv, 0u), rbar);
+      }
+      PLL_TICK(3)
+      pmbar_wait_cluster(&xbar[par], (uint32_t)(jj >> 1) & 1u);
+      PLL_TICK(4)
+      uint32_t pv;
+      int p, src;
+      {
+        const uint32_t v = lane < cs ? g_cand[par][lane].x : 0u;
+        const int i = (lane < cs && v) ? (int)g_cand[par][lane].y : 0x7fffffff;
+        pv = __reduce_max_sync(FULL, v);
+        p = __reduce_min_sync(FULL, v == pv ? i : 0x7fffffff);
+        const unsigned hit = __ballot_sync(FULL, v == pv && i == p);
+        src = hit ? __ffs(hit) - 1 : 0;
+      }
+      const bool have = pv != 0;
+      const uint32_t* u = allrows[par][src];
+      // every warp records the new pivot row in the U table (identical values; the warp reads back only its own writes
+      // before the next block barrier)
+      if (lane < PW) Utab[jj][(J4 + lane) & (PW - 1)] = have ? u[lane] : 0u;
+      __syncwarp();
+      if (have && tid == 0) {
+        const int s_ord = r - rb;
+        colpiv[jj] = s_ord;
+        pivval[s_ord] = pv;
+        pinv_s[s_ord] = g_cand[par][src].z;
+        swp_s[s_ord] = p;
+        pcol_s[s_ord] = j0 + jj;
+      }
+      PLL_TICK(5)
+      // ---- swap rows r <-> p (register copies, skipped by every warp that owns neither)
+      if (have && __any_sync(FULL, gi[0] == r || gi[0] == p || gi[1] == r || gi[1] == p)) {
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          if (gi[k] == r) {
+#pragma unroll
+            for (int c = 0; c < PW; ++c) a[k][c] = u[c];
+          } else if (gi[k] == p) {
+#pragma unroll
+            for (int c = 0; c < PW; ++c) a[k][c] = oldr[par][c];
+          }
+        }
+      }
+      const int rnext = have ? r + 1 : r;
+      // ---- bring the NEXT pivot column (register position s + 1) up to date for the rows below the pivot, then its candidates
+      if (jj + 1 < PW) {
+        const int col = jj + 1;
+        uint64_t acc[RPT][2] = {{0, 0}, {0, 0}};  // two chains per row
+#pragma unroll
+        for (int e0 = 0; e0 < PW - 4; e0 += 4) {
+          if (e0 < J4) {  // uniform: one older group of four pivots
+            uint32_t uv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) uv[e] = Utab[J4 - 1 - e0 - e][col];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+              for (int k = 0; k < RPT; ++k) acc[k][e & 1] += (uint64_t)a[k][PW - 1 - e0 - e] * uv[e];
+          }
+        }
+#pragma unroll
+        for (int sp = 0; sp <= s; ++sp) {
+          const uint32_t uv = Utab[J4 + sp][col];
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) acc[k][sp & 1] += (uint64_t)a[k][sp] * uv;
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          if (gi[k] >= rnext) {
+            const uint32_t am = ll_reduce(acc[k][0] + acc[k][1], ar);
+            const uint32_t x = a[k][s + 1];
+            a[k][s + 1] = x >= am ? x - am : x + P - am;
+          }
+        }
+        if (s < 3) {
+          PLL_LOCAL_CAND(s + 1, rnext)
+        }
+      }
+      r = rnext;
+      PLL_TICK(6)
+    }
+    if (done) break;
+    // rotate by four: position 4 (the next pivot column, already up to date) becomes position 0
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t t0 = a[k][0], t1 = a[k][1], t2 = a[k][2], t3 = a[k][3];
+#pragma unroll
+      for (int pos = 4; pos < PW; ++pos) a[k][pos - 4] = a[k][pos];
+      a[k][PW - 4] = t0;
+      a[k][PW - 3] = t1;
+      a[k][PW - 2] = t2;
+      a[k][PW - 1] = t3;
+    }
+    PLL_LOCAL_CAND(0, r)
+  }
+#undef PLL_LOCAL_CAND
+  // undo the remaining rotation so that position == logical column again
+  for (int q4 = J4 & (PW - 1); q4 != 0 && q4 < PW; q4 += 4) {
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t t0 = a[k][0], t1 = a[k][1], t2 = a[k][2], t3 = a[k][3];
+#pragma unroll
+      for (int pos = 4; pos < PW; ++pos) a[k][pos - 4] = a[k][pos];
+      a[k][PW - 4] = t0;
+      a[k][PW - 3] = t1;
+      a[k][PW - 2] = t2;
+      a[k][PW - 1] = t3;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < PW; ++c) {
+    if (c < w) {
+      const int s_ord = colpiv[c];
+      const int t = rb + s_ord;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int i = gi[k];
+        if (i < 0) continue;
+        const uint32_t v = a[k][c];
+        uint32_t* wdst = Wm + (int64_t)(j0 + c) * ldw + i;
+        if (s_ord < 0 || i < t) {
+          *wdst = v;
+        } else if (i == t) {
+          *wdst = v;  // == 1
+          Lm[(int64_t)t * ldl + i] = pivval[s_ord];
+        } else {
+          *wdst = 0;
+          Lm[(int64_t)t * ldl + i] = v;
+        }
+      }
+    }
+  }
+  if (rank == 0 && tid < r - rb) {
+    b.pivcol[rb + tid] = pcol_s[tid];
+    b.pinv[rb + tid] = pinv_s[tid];
+    b.swp[rb + tid] = swp_s[tid];
+  }
+  __syncthreads();
+  PLL_TICK(7)
+  if (do_prof)
+    for (int i = 0; i < 8; ++i) b.prof[i] += prof_s[i];
+  if (rank == 0 && warp == 0) compose_gather_list(b, rb, r, m, lane);
+  cluster.sync();
+  if (rank == 0 && tid == 0) b.st->r = r;
+#undef PLL_TICK
+}
+
+// ---------------------------------------------------------------------------------------------------
 // apply the composed gather list of the last panel to columns [c_lo, c_hi) of a matrix (one warp per column)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -1047,6 +1395,13 @@ PanelAr make_panel_ar(const ModP& mp) {
   memset(&ar, 0, sizeof(ar));
   ar.P = (uint32_t)mp.P;
   ar.mp = mp;
+  {
+    int bits = 0;
+    while ((mp.P >> bits) != 0) ++bits;
+    ar.sh2 = (uint32_t)(bits - 1);
+    const unsigned __int128 q = ((unsigned __int128)1 << (32 + ar.sh2)) / mp.P;
+    ar.mu2 = q > 0xffffffffull ? 0xffffffffu : (uint32_t)q;
+  }
   if (mp.P <= 65536) {
     ar.mu = (uint32_t)((1ull << 32) / mp.P);
   } else if (mp.P < (1ull << 30)) {
@@ -1087,12 +1442,48 @@ int32_t launch_panel_reg_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int 
   return GFFM_OK;
 }
 
+template <int PW, bool PROF>
+int32_t launch_panel_ll_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int cluster, const PluqBufs& b, const ModP& mp) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pluq_panel_ll_kernel<PW, PROF>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaGetLastError();
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const PanelAr ar = make_panel_ar(mp);
+  GFFM_CUDA(cudaLaunchKernelEx(&cfg, (pluq_panel_ll_kernel<PW, PROF>), W->data, W->ld, (int)W->rows, j0, w, L->data, L->ld, b, ar));
+  ctx->launches++;
+  return GFFM_OK;
+}
+// left-looking variant: 31 products of two residues must fit a 64-bit accumulator
+bool panel_ll_enabled(const ModP& mp) {
+  static const bool on = !(getenv("GFFM_PANEL_LL") && atoi(getenv("GFFM_PANEL_LL")) == 0);
+  return on && mp.P < (1ull << 29);
+}
+
 // register-resident panel: needs rows_c <= PREG_ROWS and a panel of at most 32 columns
 bool panel_reg_enabled() {
   static const bool on = !(getenv("GFFM_PANEL_REG") && atoi(getenv("GFFM_PANEL_REG")) == 0);
   return on;
 }
 int32_t launch_panel_reg(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int cluster, const PluqBufs& b, const ModP& mp) {
+  if (panel_ll_enabled(mp)) {
+    if (b.prof) return w <= 16 ? launch_panel_ll_t<16, true>(ctx, W, L, j0, w, cluster, b, mp) : launch_panel_ll_t<32, true>(ctx, W, L, j0, w, cluster, b, mp);
+    return w <= 16 ? launch_panel_ll_t<16, false>(ctx, W, L, j0, w, cluster, b, mp) : launch_panel_ll_t<32, false>(ctx, W, L, j0, w, cluster, b, mp);
+  }
   const int ar = panel_arith(mp);
   static const int rpt = (getenv("GFFM_PANEL_RPT") && atoi(getenv("GFFM_PANEL_RPT")) == 1) ? 1 : 2;
 #define GFFM_PREG(A)                                                                                                   \
