@@ -527,8 +527,12 @@ pluq_panel_reg_kernel(uint32_t* __restrict__ Wm, int64_t ldw, int m, int j0, int
   for (int k = 0; k < PREG_RPT; ++k) {
     const int q = tid + PREG_T * k;
     gi[k] = q < my_n ? my_lo + q : -1;
+    const uint32_t* src = Wm + (int64_t)j0 * ldw + (gi[k] >= 0 ? gi[k] : 0);
 #pragma unroll
-    for (int c = 0; c < PW; ++c) a[k][c] = (gi[k] >= 0 && c < w) ? Wm[(int64_t)(j0 + c) * ldw + gi[k]] : 0u;
+    for (int c = 0; c < PW; ++c) {
+      a[k][c] = (gi[k] >= 0 && c < w) ? *src : 0u;
+      src += ldw;
+    }
   }
   if (tid < PW) colpiv[tid] = -1;
   if (tid == 0) {
@@ -727,27 +731,32 @@ pluq_panel_reg_kernel(uint32_t* __restrict__ Wm, int64_t ldw, int m, int j0, int
   }
   __syncthreads();
   // ---- store-back: pivot columns split into U (rows <= pivot row) and L (rows below), everything else is W
+  {
+    uint32_t* wcol = Wm + (int64_t)j0 * ldw;
 #pragma unroll
-  for (int c = 0; c < PW; ++c) {
-    if (c < w) {
-      const int s_ord = colpiv[c];
-      const int t = rb + s_ord;
+    for (int c = 0; c < PW; ++c) {
+      if (c < w) {
+        const int s_ord = colpiv[c];  // uniform
+        if (s_ord < 0) {
 #pragma unroll
-      for (int k = 0; k < PREG_RPT; ++k) {
-        const int i = gi[k];
-        if (i < 0) continue;
-        const uint32_t v = pa_canon<ARITH>(a[k][c], ar);
-        uint32_t* wdst = Wm + (int64_t)(j0 + c) * ldw + i;
-        if (s_ord < 0 || i < t) {
-          *wdst = v;
-        } else if (i == t) {
-          *wdst = v;  // == 1
-          Lm[(int64_t)t * ldl + i] = pivval[s_ord];
+          for (int k = 0; k < PREG_RPT; ++k)
+            if (gi[k] >= 0) wcol[gi[k]] = pa_canon<ARITH>(a[k][c], ar);
         } else {
-          *wdst = 0;
-          Lm[(int64_t)t * ldl + i] = v;
+          const int t = rb + s_ord;
+          uint32_t* lcol = Lm + (int64_t)t * ldl;
+          const uint32_t pvv = pivval[s_ord];
+#pragma unroll
+          for (int k = 0; k < PREG_RPT; ++k) {
+            const int i = gi[k];
+            if (i >= 0) {
+              const uint32_t v = pa_canon<ARITH>(a[k][c], ar);
+              wcol[i] = i <= t ? v : 0u;  // the pivot itself is stored as 1
+              if (i >= t) lcol[i] = i == t ? pvv : v;
+            }
+          }
         }
       }
+      wcol += ldw;
     }
   }
   if (rank == 0 && tid < r - rb) {
@@ -822,8 +831,12 @@ pluq_panel_ll_kernel(uint32_t* __restrict__ Wm, int64_t ldw, int m, int j0, int 
   for (int k = 0; k < RPT; ++k) {
     const int q = tid + T * k;
     gi[k] = q < my_n ? my_lo + q : -1;
+    const uint32_t* src = Wm + (int64_t)j0 * ldw + (gi[k] >= 0 ? gi[k] : 0);
 #pragma unroll
-    for (int c = 0; c < PW; ++c) a[k][c] = (gi[k] >= 0 && c < w) ? Wm[(int64_t)(j0 + c) * ldw + gi[k]] : 0u;
+    for (int c = 0; c < PW; ++c) {
+      a[k][c] = (gi[k] >= 0 && c < w) ? *src : 0u;
+      src += ldw;
+    }
   }
   if (tid < PW) colpiv[tid] = -1;
   if (tid == 0) {
@@ -1060,27 +1073,32 @@ pluq_panel_ll_kernel(uint32_t* __restrict__ Wm, int64_t ldw, int m, int j0, int 
     }
   }
   __syncthreads();
+  {
+    uint32_t* wcol = Wm + (int64_t)j0 * ldw;
 #pragma unroll
-  for (int c = 0; c < PW; ++c) {
-    if (c < w) {
-      const int s_ord = colpiv[c];
-      const int t = rb + s_ord;
+    for (int c = 0; c < PW; ++c) {
+      if (c < w) {
+        const int s_ord = colpiv[c];  // uniform
+        if (s_ord < 0) {
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const int i = gi[k];
-        if (i < 0) continue;
-        const uint32_t v = a[k][c];
-        uint32_t* wdst = Wm + (int64_t)(j0 + c) * ldw + i;
-        if (s_ord < 0 || i < t) {
-          *wdst = v;
-        } else if (i == t) {
-          *wdst = v;  // == 1
-          Lm[(int64_t)t * ldl + i] = pivval[s_ord];
+          for (int k = 0; k < RPT; ++k)
+            if (gi[k] >= 0) wcol[gi[k]] = a[k][c];
         } else {
-          *wdst = 0;
-          Lm[(int64_t)t * ldl + i] = v;
+          const int t = rb + s_ord;
+          uint32_t* lcol = Lm + (int64_t)t * ldl;
+          const uint32_t pvv = pivval[s_ord];
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) {
+            const int i = gi[k];
+            if (i >= 0) {
+              const uint32_t v = a[k][c];
+              wcol[i] = i <= t ? v : 0u;  // the pivot itself is stored as 1
+              if (i >= t) lcol[i] = i == t ? pvv : v;
+            }
+          }
         }
       }
+      wcol += ldw;
     }
   }
   if (rank == 0 && tid < r - rb) {

@@ -247,7 +247,12 @@ def _check_pluq_invariant(g, Ag, U, L, pr, pc):
 
 
 @pytest.mark.parametrize("m,n,N,seed", [(1, 1, 7, 1), (10, 10, 7, 1), (33, 33, 2, 2), (100, 100, 65521, 3), (257, 257, 33554393, 4), (300, 200, 65521, 5),
-                                        (200, 300, 11, 6), (1000, 1000, 13, 7), (700, 700, 4294967291, 8)])
+                                        (200, 300, 11, 6), (1000, 1000, 13, 7), (700, 700, 4294967291, 8),
+                                        # one case per arithmetic path of the panel kernels: left-looking with the 32-bit quotient
+                                        # estimate (17 / 26 bits), left-looking with the 64-bit Barrett (29 bits), right-looking lazy
+                                        # (30 bits); tall input whose row slices exceed the register kernels (shared-memory panel)
+                                        (200, 200, 131071, 12), (260, 260, 67108859, 11), (300, 300, 536870909, 9),
+                                        (300, 300, 805306457, 10), (20000, 40, 65521, 13)])
 def test_pluq_lu_rref_inverse_vs_oracle(g, m, n, N, seed):
     A = O.synth_matrix(seed, m, n, N)
     if min(m, n) > 20 and seed in (5, 6, 7):
