@@ -52,9 +52,44 @@ extern "C" int32_t gffm_create(int32_t device, gffm_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = true;
+  {  // keep freed matrix / plane-cache blocks in the default pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   for (int i = 0; i < 8; ++i) GFFM_CUDA(cudaEventCreate(&ctx->ev[i]));
   *out = ctx;
   return GFFM_OK;
+}
+
+cudaError_t gffm_dev_alloc(gffm_ctx* ctx, void** ptr, size_t bytes) {
+  cudaError_t e = cudaMallocAsync(ptr, bytes ? bytes : 4, ctx->stream);
+  if (e != cudaSuccess) {  // pool fragmented or exhausted: hand cached blocks back to the driver and retry once
+    cudaGetLastError();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
+    e = cudaMallocAsync(ptr, bytes ? bytes : 4, ctx->stream);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      *ptr = nullptr;
+    }
+  }
+  return e;
+}
+void gffm_dev_free(gffm_ctx* ctx, void* ptr) {
+  if (!ptr) return;
+  if (cudaFreeAsync(ptr, ctx->stream) != cudaSuccess) {
+    cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ptr);
+  }
 }
 
 static void ws_free(gffm_workspace* ws) {
@@ -209,11 +244,10 @@ extern "C" int32_t gffm_mat_create(gffm_ctx* ctx, int64_t rows, int64_t cols, ui
   m->owned = true;
   cudaSetDevice(ctx->device);
   size_t bytes = (size_t)m->ld * m->pcols * sizeof(uint32_t);
-  cudaError_t e = cudaMalloc(&m->data, bytes);
+  cudaError_t e = gffm_dev_alloc(ctx, (void**)&m->data, bytes);
   if (e != cudaSuccess) {
-    cudaGetLastError();
     delete m;
-    GFFM_FAIL(GFFM_ERR_OOM, "cudaMalloc of %zu bytes failed", bytes);
+    GFFM_FAIL(GFFM_ERR_OOM, "device allocation of %zu bytes failed", bytes);
   }
   GFFM_CUDA(cudaMemsetAsync(m->data, 0, bytes, ctx->stream));
   *out = m;
@@ -240,7 +274,7 @@ extern "C" int32_t gffm_mat_wrap(gffm_ctx* ctx, void* dptr, int64_t rows, int64_
 
 static void free_plane_caches(gffm_mat* m) {
   for (int r = 0; r < 2; ++r) {
-    if (m->cache[r].ptr) cudaFree(m->cache[r].ptr);
+    if (m->cache[r].ptr) gffm_dev_free(m->ctx, m->cache[r].ptr);
     m->cache[r] = gffm_plane_cache();
   }
 }
@@ -254,24 +288,17 @@ extern "C" int32_t gffm_mat_touch(gffm_mat* m) {
 extern "C" int32_t gffm_mat_drop_cache(gffm_mat* m) {
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   cudaSetDevice(m->ctx->device);
-  cudaStreamSynchronize(m->ctx->stream);
   free_plane_caches(m);
   return GFFM_OK;
 }
 
 extern "C" int32_t gffm_mat_destroy(gffm_mat* m) {
   if (!m) return GFFM_OK;
-  if (m->cache[0].ptr || m->cache[1].ptr) {
-    cudaSetDevice(m->ctx->device);
-    cudaStreamSynchronize(m->ctx->stream);
-    free_plane_caches(m);
-  }
-  if (m->owned && m->data) {
-    // stream-ordered: wait for queued work that may still use the buffer (safe from a finalizer thread)
-    cudaSetDevice(m->ctx->device);
-    cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->data);
-  }
+  // stream-ordered release: the blocks return to the pool after the work already queued on the context's stream (every
+  // helper stream of the library is joined to it before an API call returns); safe from a finalizer thread
+  cudaSetDevice(m->ctx->device);
+  if (m->cache[0].ptr || m->cache[1].ptr) free_plane_caches(m);
+  if (m->owned && m->data) gffm_dev_free(m->ctx, m->data);
   delete m;
   return GFFM_OK;
 }

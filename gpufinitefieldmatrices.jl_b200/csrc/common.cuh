@@ -88,6 +88,11 @@ struct gffm_mat {
 static inline void gffm_touch(gffm_mat* m) { m->version++; }
 
 int32_t gffm_ws_reserve(gffm_ctx* ctx, gffm_workspace* ws, size_t bytes);
+// Stream-ordered device memory for matrices and plane caches (cudaMallocAsync on the device's default pool, which is told to
+// keep freed blocks): temporaries such as the W / L factors of an elimination cost microseconds instead of a device-wide
+// cudaMalloc / cudaFree.  gffm_dev_free orders the release after the work queued on the context's stream.
+cudaError_t gffm_dev_alloc(gffm_ctx* ctx, void** ptr, size_t bytes);
+void gffm_dev_free(gffm_ctx* ctx, void* ptr);
 int32_t gffm_pinned_reserve(gffm_ctx* ctx, size_t bytes);
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

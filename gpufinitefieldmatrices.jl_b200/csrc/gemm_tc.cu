@@ -1181,13 +1181,11 @@ int32_t acquire_planes(gffm_ctx* ctx, int role, const MatView& X, const MatView*
     }
     if (c.bytes < bytes) {
       if (c.ptr) {
-        GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(c.ptr);
+        gffm_dev_free(ctx, c.ptr);
         c.ptr = nullptr;
         c.bytes = 0;
       }
-      if (cudaMalloc(&c.ptr, bytes) != cudaSuccess) {  // no memory for a cache: fall back to the shared workspace
-        cudaGetLastError();
+      if (gffm_dev_alloc(ctx, &c.ptr, bytes) != cudaSuccess) {  // no memory for a cache: fall back to the shared workspace
         c.ptr = nullptr;
         own = nullptr;
       } else {
@@ -1591,16 +1589,12 @@ int32_t plane_buffer(gffm_ctx* ctx, int role, const MatView& X, int64_t k, int64
     }
     if (c.bytes < bytes) {
       if (c.ptr) {
-        GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(c.ptr);
+        gffm_dev_free(ctx, c.ptr);
         c.ptr = nullptr;
         c.bytes = 0;
       }
-      if (cudaMalloc(&c.ptr, bytes) == cudaSuccess) c.bytes = bytes;
-      else {
-        cudaGetLastError();
-        c.ptr = nullptr;
-      }
+      if (gffm_dev_alloc(ctx, &c.ptr, bytes) == cudaSuccess) c.bytes = bytes;
+      else c.ptr = nullptr;
     }
     if (c.ptr) {
       c.valid = false;

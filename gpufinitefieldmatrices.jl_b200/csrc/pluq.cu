@@ -16,6 +16,7 @@
 // reference's swap-with-fixed-last-column quirk is not reproduced by the blocked path).
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <chrono>
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -1710,6 +1711,12 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
   const uint64_t N = A->N;
   if (N >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "elimination needs N < 2^32");
   gffm_mat *W = nullptr, *L = nullptr;
+  static const bool host_prof = getenv("GFFM_HOST_PROF") != nullptr;
+  auto now_ms = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  const double hp0 = host_prof ? now_ms() : 0;
   GFFM_TRY(gffm_mat_create(ctx, m, n, N, A->pad, &W));
   out->W = W;
   GFFM_TRY(gffm_mat_create(ctx, m, m, N, A->pad, &L));
@@ -1766,7 +1773,12 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
     E.scap = tmp_bytes;
     E.linv_pool = reinterpret_cast<uint32_t*>(E.sbase + tmp_bytes);
   }
+  const double hp1 = host_prof ? now_ms() : 0;
   GFFM_TRY(elim_rec(E, 0, n));
+  if (host_prof) {
+    const double hp2 = now_ms();
+    fprintf(stderr, "[elim host prof] setup (alloc W,L + copy + tables) %.2f ms, elimination %.2f ms\n", hp1 - hp0, hp2 - hp1);
+  }
   const int r0 = E.r;
   if (b.prof) {
     long long h[16];
