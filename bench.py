@@ -381,9 +381,10 @@ def main():
                     U_, L_, pr_, pc_, rk_ = g.pluq_gpu_kernel(A_, return_rank=True)
                     torch.cuda.synchronize(); tp_ = time.perf_counter() - t0
                     del U_, L_
-                torch.cuda.synchronize(); t0 = time.perf_counter()
-                R_ = g.rref(A_)
-                torch.cuda.synchronize(); tr_ = time.perf_counter() - t0
+                for rep in range(2):
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    R_ = g.rref(A_)
+                    torch.cuda.synchronize(); tr_ = time.perf_counter() - t0
                 extras[f"pluq_n{np_}_mod{Np}"] = {"seconds": tp_, "rank": rk_, "rref_seconds": tr_}
                 del A_, R_
 
