@@ -1658,7 +1658,18 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     off.push_back(extent);
     return off;
   };
-  const std::vector<int64_t> offA = boundaries(m, BM), offB = boundaries(n, BN);
+  std::vector<int64_t> offA = boundaries(m, BM), offB = boundaries(n, BN);
+  // GFFM_HOST_SCHED=1d: upload B first (one block, copied and split in 8 column sub-panels), then 16 equal row blocks of A, each
+  // multiplied with all of B as soon as it has arrived -- the GPU idles while B is in flight but then runs flat out, and every
+  // finished row block of C leaves immediately (see profiles/r01_notes.md for the comparison with the 2-D interleaving)
+  static const bool sched_1d = getenv("GFFM_HOST_SCHED") && !strcmp(getenv("GFFM_HOST_SCHED"), "1d");
+  if (host && sched_1d && m >= 16 * 256) {
+    offB = {0, n};
+    offA.clear();
+    const int64_t b = round_up(ceil_div(m, 16), BM);
+    for (int64_t o = 0; o < m; o += b) offA.push_back(o);
+    offA.push_back(m);
+  }
   const int nbA = (int)offA.size() - 1, nbB = (int)offB.size() - 1;
   const int64_t Kp = round_up(k, 128), rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
   const int64_t lde = round_up(m, 128), e_plane = lde * n;
@@ -1699,7 +1710,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
   cudaStream_t sc = ctx->stream, sx = ctx->s_aux, sh = ctx->s_h2d, sd = ctx->s_d2h;
   const int steps = std::max(nbA, nbB);
   // events: pool owned by the context (grow-only)
-  const size_t need_ev = 2 + 3 * (size_t)steps + 2 * (size_t)nbA * nbB;
+  const size_t need_ev = 2 + 3 * (size_t)steps + 2 * (size_t)nbA * nbB + 16;
   while (ctx->ev_pool.size() < need_ev) {
     cudaEvent_t e;
     GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1738,18 +1749,24 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
       GFFM_TRY(run_split(ctx, true, v, nullptr, 0, k, pA + i0 * Kp, Kp, rowsPA, sp, sx));
     }
     if (t < nbB && !hitB) {
-      const int64_t j0 = offB[t], nj = offB[t + 1] - j0;
-      if (host) {
-        GFFM_CUDA(cudaMemcpy2DAsync(dB + j0 * ldB, (size_t)ldB * 4, io->B + j0 * io->ldb, (size_t)io->ldb * 4, (size_t)k * 4, (size_t)nj,
-                                    cudaMemcpyHostToDevice, sh));
-        cudaEvent_t e = next_ev();
-        GFFM_CUDA(cudaEventRecord(e, sh));
-        GFFM_CUDA(cudaStreamWaitEvent(sx, e, 0));
-        mod_inplace_kernel<<<nblk_mod, 256, 0, sx>>>(dB + j0 * ldB, ldB, k, nj, mpR);
-        GFFM_LAUNCH_CHECK(ctx);
+      const int64_t jb = offB[t], njb = offB[t + 1] - jb;
+      // a single B block (1-D schedule) is copied and split in 8 sub-panels so that the split overlaps the upload
+      const int nsub = (host && nbB == 1 && njb >= 8 * BN) ? 8 : 1;
+      const int64_t sub = round_up(ceil_div(njb, nsub), BN);
+      for (int64_t j0 = jb; j0 < jb + njb; j0 += sub) {
+        const int64_t nj = std::min(sub, jb + njb - j0);
+        if (host) {
+          GFFM_CUDA(cudaMemcpy2DAsync(dB + j0 * ldB, (size_t)ldB * 4, io->B + j0 * io->ldb, (size_t)io->ldb * 4, (size_t)k * 4, (size_t)nj,
+                                      cudaMemcpyHostToDevice, sh));
+          cudaEvent_t e = next_ev();
+          GFFM_CUDA(cudaEventRecord(e, sh));
+          GFFM_CUDA(cudaStreamWaitEvent(sx, e, 0));
+          mod_inplace_kernel<<<nblk_mod, 256, 0, sx>>>(dB + j0 * ldB, ldB, k, nj, mpR);
+          GFFM_LAUNCH_CHECK(ctx);
+        }
+        MatView v{dB + j0 * ldB, ldB, k, nj};
+        GFFM_TRY(run_split(ctx, false, v, nullptr, 0, k, pB + j0 * Kp, Kp, rowsPB, sp, sx));
       }
-      MatView v{dB + j0 * ldB, ldB, k, nj};
-      GFFM_TRY(run_split(ctx, false, v, nullptr, 0, k, pB + j0 * Kp, Kp, rowsPB, sp, sx));
     }
     ev_split[t] = next_ev();
     GFFM_CUDA(cudaEventRecord(ev_split[t], sx));
