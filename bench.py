@@ -200,19 +200,19 @@ def main():
             ctx.sync()
             del Bs
         C = g.zeros(np.float32, mloc, n, N, ctx=ctx)
-        panels = g.multigpu.col_panels(n, args.panels if world > 1 else 1)
+        panels = g.multigpu.col_panels(n, args.panels if world > 1 else 1, align=g.multigpu.PANEL_ALIGN)
         npan = len(panels)
         pan = panels[0][1] - panels[0][0]
-
-        def gemm_panel(c0, c1):
-            g.capi.check(C.lib.gffm_gemm_block(C.h, 0, c0, A.h, 0, 0, B.h, 0, c0, mloc, c1 - c0, n, 0, 0, g.capi.GEMM_STORE, g.capi.ALGO_AUTO))
+        # N > 1: NCCL broadcast of B in column panels on a communication stream; ONE gffm_gemm_panels call per step consumes them
+        # (split of panel p+1 / CRT of panel p under the GEMM of panel p; the next step's broadcast runs under this step's GEMMs)
+        bm = g.multigpu.BroadcastMatmul(torch, dist, C, A, B, Bt, panels, src=0) if world > 1 else None
 
         def step():
             A.touch()  # every step is a FRESH product: the cached 8-bit planes of A are rebuilt (B is external memory, never cached)
             if world == 1:
                 g.mul_(C, A, B)
-            else:  # NCCL broadcast of B in column panels, GEMM of panel p overlaps the broadcast of panel p+1
-                g.multigpu.pipelined_broadcast_matmul(dist, Bt, panels, gemm_panel, src=0)
+            else:
+                bm.step()
 
         for _ in range(W):
             step()
@@ -227,6 +227,8 @@ def main():
         e0.record(stream)
         for _ in range(K):
             step()
+        if bm is not None:
+            bm.finish()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1) / K
@@ -400,7 +402,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{n}x{n} * {n}x{n} matmul mod {N} ({bits}-bit modulus), A,B resident as uint32 residues", "n": n, "modulus": N,
                        "encoding": "RNS int8 tcgen05" if N > 65536 else "positional int8 limbs tcgen05",
-                       "sharding": "single GPU" if world == 1 else f"row blocks of A over {world} GPUs, B broadcast from rank 0 by NCCL in {npan} column panels overlapped with the GEMM",
+                       "sharding": "single GPU" if world == 1 else f"row blocks of A over {world} GPUs, B broadcast from rank 0 by NCCL every step in {npan} column panels on a communication stream, consumed by gffm_gemm_panels (split/CRT under the GEMM, next step's broadcast under this step's GEMMs)",
                        "l2_policy": f"inputs larger than L2: A and B are {4 * n * n / 2**20:.0f} MiB each vs 126 MB L2", "checksum_rank0": f"{checksum:016x}",
                        "extras": extras},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

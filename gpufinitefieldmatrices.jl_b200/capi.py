@@ -105,6 +105,7 @@ SIGNATURES = {
     "gffm_gemm": [_vp, _vp, _vp, _u64, _u64, _i32, _i32],
     "gffm_gemm_block": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _u64, _u64, _i32, _i32],
     "gffm_gemm_host": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _u64],
+    "gffm_gemm_panels": [_vp, _vp, _vp, _i32, _pi64, _pvp, _pvp, _u64, _u64],
     "gffm_gemv": [_vp, _vp, _vp, _u64, _u64],
     "gffm_ewise": [_i32, _vp, _vp, _vp, _i64, _u64],
     "gffm_pluq": [_vp, _pvp, _pvp, _pi64, _pi64, _pi64, _pi64, _pi64, _i32],

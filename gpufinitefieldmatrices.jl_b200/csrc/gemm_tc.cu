@@ -1571,6 +1571,16 @@ struct HostIO {  // host mode only
   int64_t ldc = 0;
 };
 
+// device mode, B arriving in column panels (multi-GPU layer: NCCL broadcast of B on another stream): panel p =
+// columns [off[p], off[p+1]); ready[p] is recorded by the caller once panel p is in place, consumed[p] is recorded
+// here once panel p has been turned into operand planes (its residues may be overwritten from then on)
+struct PanelFeed {
+  int npanels = 0;
+  const int64_t* off = nullptr;
+  cudaEvent_t const* ready = nullptr;
+  cudaEvent_t const* consumed = nullptr;
+};
+
 // returns true when the planes of X are already cached (no split needed); otherwise *out points to the buffer to fill
 // (the owner's cache buffer, (re)allocated here, or the shared workspace) and *fill_cache says whether to validate it
 int32_t plane_buffer(gffm_ctx* ctx, int role, const MatView& X, int64_t k, int64_t Kp, int64_t rowsP, const SplitParams& sp,
@@ -1611,7 +1621,7 @@ int32_t plane_buffer(gffm_ctx* ctx, int role, const MatView& X, int64_t k, int64
 }
 
 int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO* io, int64_t m, int64_t n, int64_t k, uint64_t R, uint64_t P,
-                   int mode, bool balanced) {
+                   int mode, bool balanced, const PanelFeed* feed = nullptr) {
   const bool host = io != nullptr;
   const bool rns = R > 65536;
   const int L = R <= 256 ? 1 : 2;
@@ -1669,6 +1679,10 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     const int64_t b = round_up(ceil_div(m, 16), BM);
     for (int64_t o = 0; o < m; o += b) offA.push_back(o);
     offA.push_back(m);
+  }
+  if (feed) {  // the caller's panels of B; A (this rank's row block) is one block, split once while panel 0 is in flight
+    offA = {0, m};
+    offB.assign(feed->off, feed->off + feed->npanels + 1);
   }
   const int nbA = (int)offA.size() - 1, nbB = (int)offB.size() - 1;
   const int64_t Kp = round_up(k, 128), rowsPA = round_up(m, BM), rowsPB = round_up(n, BN);
@@ -1748,6 +1762,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
       MatView v{dA + i0, ldA, mi, k};
       GFFM_TRY(run_split(ctx, true, v, nullptr, 0, k, pA + i0 * Kp, Kp, rowsPA, sp, sx));
     }
+    if (t < nbB && feed && feed->ready && feed->ready[t]) GFFM_CUDA(cudaStreamWaitEvent(sx, feed->ready[t], 0));
     if (t < nbB && !hitB) {
       const int64_t jb = offB[t], njb = offB[t + 1] - jb;
       // a single B block (1-D schedule) is copied and split in 8 sub-panels so that the split overlaps the upload
@@ -1770,6 +1785,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     }
     ev_split[t] = next_ev();
     GFFM_CUDA(cudaEventRecord(ev_split[t], sx));
+    if (t < nbB && feed && feed->consumed && feed->consumed[t]) GFFM_CUDA(cudaEventRecord(feed->consumed[t], sx));
     return GFFM_OK;
   };
   struct Pending {
@@ -1926,4 +1942,51 @@ extern "C" int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, cons
   io.C = (uint32_t*)C_host; io.ldc = ldc;
   MatView none{nullptr, 0, 0, 0};
   return tiled_gemm(ctx, none, none, none, &io, m, n, k, N, N, GFFM_GEMM_STORE, /*balanced=*/true);
+}
+
+// Sharded product step of the multi-GPU layer (new; the reference is single-GPU).  This rank's row block A is multiplied with
+// a B that ARRIVES in column panels (NCCL broadcast issued by the caller on its own stream).  The 8-bit plane split of panel
+// p+1 and the CRT of panel p run on the auxiliary stream while the tensor-core GEMM of panel p occupies the compute stream;
+// consumed[p] lets the caller start the NEXT step's broadcast of panel p while this step is still multiplying.
+extern "C" int32_t gffm_gemm_panels(gffm_mat* C, gffm_mat* A, gffm_mat* B, int32_t npanels, const int64_t* col_off, void* const* ready,
+                                    void* const* consumed, uint64_t R, uint64_t P) {
+  if (!C || !A || !B || !col_off) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  if (C == A || C == B) GFFM_FAIL(GFFM_ERR_INVALID, "gemm_panels: C must not alias an operand");
+  if (!P && (A->N != B->N || A->N != C->N)) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "gemm operands have different moduli");
+  if (A->cols != B->rows || C->rows != A->rows || C->cols != B->cols)
+    GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "gemm_panels: C %lldx%lld = A %lldx%lld * B %lldx%lld", (long long)C->rows, (long long)C->cols,
+              (long long)A->rows, (long long)A->cols, (long long)B->rows, (long long)B->cols);
+  if (npanels < 1 || col_off[0] != 0 || col_off[npanels] != B->cols) GFFM_FAIL(GFFM_ERR_INVALID, "gemm_panels: panels must cover [0, cols(B))");
+  for (int p = 0; p < npanels; ++p)
+    if (col_off[p + 1] < col_off[p]) GFFM_FAIL(GFFM_ERR_INVALID, "gemm_panels: panel offsets must be non-decreasing");
+  if (!P) P = C->N;
+  if (!R) R = A->N > B->N ? A->N : B->N;
+  if (P >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "gemm needs 0 < P < 2^32");
+  gffm_ctx* ctx = C->ctx;
+  cudaSetDevice(ctx->device);
+  gffm_touch(C);
+  const int64_t m = A->rows, k = A->cols, n = B->cols;
+  bool aligned = true;
+  for (int p = 1; p < npanels; ++p) aligned = aligned && (col_off[p] % 256 == 0);  // tile offsets into the operand planes
+  for (int p = 0; p < npanels; ++p) aligned = aligned && (col_off[p + 1] > col_off[p]);
+  const bool rns = R > 65536;
+  const bool pipelined = aligned && R < (1ull << 32) && gffm_tc_available(ctx) && k >= 128 && k <= gffm_gemm_kchunk(R, rns) && m >= 128 && n >= 256;
+  if (!pipelined) {  // small or unaligned shapes: panel by panel on the compute stream through the ordinary dispatcher
+    for (int p = 0; p < npanels; ++p) {
+      if (ready && ready[p]) GFFM_CUDA(cudaStreamWaitEvent(ctx->stream, (cudaEvent_t)ready[p], 0));
+      const int64_t c0 = col_off[p], nc = col_off[p + 1] - c0;
+      if (nc > 0 && m > 0)
+        GFFM_TRY(gffm_gemm_views(ctx, sub_view(view_of(C), 0, c0, m, nc), cached_view_of(A), sub_view(view_of(B), 0, c0, k, nc), R, P, GFFM_GEMM_STORE,
+                                 GFFM_ALGO_AUTO));
+      if (consumed && consumed[p]) GFFM_CUDA(cudaEventRecord((cudaEvent_t)consumed[p], ctx->stream));
+    }
+    return GFFM_OK;
+  }
+  PanelFeed feed;
+  feed.npanels = npanels;
+  feed.off = col_off;
+  feed.ready = (cudaEvent_t const*)ready;
+  feed.consumed = (cudaEvent_t const*)consumed;
+  // B is never taken from / put into the plane cache here: its residues change behind the library's back every step
+  return tiled_gemm(ctx, view_of(C), cached_view_of(A), view_of(B), nullptr, m, n, k, R, P, GFFM_GEMM_STORE, rns && (R % P) == 0, &feed);
 }

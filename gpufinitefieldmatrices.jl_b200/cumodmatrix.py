@@ -605,3 +605,27 @@ def lower_triangular_inverse_no_copy(A, debug=False):
 
 backward_sub_gpu_type_32 = upper_triangular_inverse_no_copy  # substitution_inplace.jl:51-56
 forward_sub_gpu_type_32 = lower_triangular_inverse_no_copy   # substitution_inplace.jl:37-43
+
+
+# ---- Hensel lifting of an inverse: src/CuModMatrix/triangular/hensel.jl:13-21 ------------------------------------
+def hensel_pseudoinverse(N, precision, A: CuModMatrix, T: CuModMatrix) -> CuModMatrix:
+    """`hensel_pseudoinverse(N, precision, A, T)`: lifts T with A*T = I (mod N) to A*T = I (mod N^precision) by the Newton
+    step `T = 2*T - T*(A*T)` (hensel.jl:15-18), all products on the tensor cores.  A and T carry the modulus N^precision
+    (< 2^32 here; use karatsuba.hensel_pseudoinverse for two-limb moduli).  Returns the lifted T as a CuModMatrix (the
+    reference converts to a Nemo residue-ring matrix, hensel.jl:19-20; `.to_int()` gives the host integers)."""
+    M = int(N) ** int(precision)
+    if A.N != M or T.N != M:
+        raise capi.CuModArrayModulusMismatchException(capi.ERR_MODULUS_MISMATCH, f"A and T must carry the modulus N^precision = {M}")
+    if A.rows != A.cols or (T.rows, T.cols) != (A.rows, A.cols):
+        raise capi.CuModMatrixNotSquareException(capi.ERR_NOT_SQUARE, "hensel_pseudoinverse needs square A and T of the same size")
+    T = copy(T)
+    W = CuModMatrix._new(A.rows, A.cols, M, like=A)
+    V = CuModMatrix._new(A.rows, A.cols, M, like=A)
+    i = 1
+    while i < precision:
+        mul_(W, A, T)                                  # A*T
+        mul_(V, T, W)                                  # T*(A*T)
+        _ew(capi.EW_SMUL, W, T, scalar=2)              # 2*T
+        _ew(capi.EW_SUB, T, W, V)                      # T = 2*T - T*(A*T)
+        i *= 2
+    return T

@@ -205,6 +205,14 @@ function mul_host!(C::Matrix{UInt32}, A::Matrix{UInt32}, B::Matrix{UInt32}, N::I
     check(ccall((:gffm_gemm_host, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int32, UInt64),
                 ctx.h, C, size(C, 1), A, m, B, k, m, n, k, 3, N)); C
 end
+# multi-GPU layer: one sharded product step, B arriving in column panels (1-based inclusive column ranges start at col_off[p]+1);
+# ready / consumed are vectors of raw CUevent handles (C_NULL entries allowed), e.g. CUDA.CuEvent(...).handle
+function mul_panels!(C::CuModArray{T,2}, A::CuModArray{T,2}, B::CuModArray{T,2}, col_off::Vector{Int64};
+                     ready::Vector{Ptr{Cvoid}}=Ptr{Cvoid}[], consumed::Vector{Ptr{Cvoid}}=Ptr{Cvoid}[], R::Integer=0, P::Integer=0) where {T}
+    np = length(col_off) - 1
+    check(ccall((:gffm_gemm_panels, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, UInt64, UInt64),
+                C.h, A.h, B.h, np, col_off, isempty(ready) ? C_NULL : ready, isempty(consumed) ? C_NULL : consumed, R, P)); C
+end
 gemm_block!(C, cr, cc, A, ar, ac, B, br, bc, m, n, k; R=0, P=0, mode=0, algo=0) =
     check(ccall((:gffm_gemm_block, libgffm), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, UInt64, UInt64, Int32, Int32),
                 C.h, cr - 1, cc - 1, A.h, ar - 1, ac - 1, B.h, br - 1, bc - 1, m, n, k, R, P, mode, algo))
@@ -318,11 +326,33 @@ sub!(C::KaratsubaArray, A::KaratsubaArray, B::KaratsubaArray) = _kew(2, C, A, B,
 scalar_multiply!(C::KaratsubaArray, A::KaratsubaArray, s::Integer) = _kew(7, C, A, nothing, s)   # :631-666
 negate!(C::KaratsubaArray, A::KaratsubaArray) = _kew(6, C, A, nothing, 0)                 # :691-731
 
+# ---- Hensel lifting of an inverse (reference src/CuModMatrix/triangular/hensel.jl:13-21; not loaded there, needs Nemo) -----
+# A, T carry the modulus N^precision; returns the lifted T (device matrix; the reference wraps Array(T) in a Nemo residue ring)
+function hensel_pseudoinverse(N::Integer, precision::Integer, A::CuModArray{E,2}, T::CuModArray{E,2}) where {E}
+    (A.N == N^precision == T.N) || throw(CuModArrayModulusMismatchException("A and T must carry the modulus N^precision"))
+    T = copy(T); W = _like(A); V = _like(A)
+    i = 1
+    while i < precision
+        mul!(W, A, T); mul!(V, T, W)          # T*(A*T)
+        mul!(W, T, 2); sub!(T, W, V)          # T = 2T - T*(A*T)
+        i *= 2
+    end
+    T
+end
+function hensel_pseudoinverse!(steps::Integer, A::KaratsubaArray{E,2}, T::KaratsubaArray{E,2}) where {E}   # two-limb moduli up to 2^52
+    W = KaratsubaZeros(E, rows(A.data1), cols(A.data1), A.N1, A.N2); V = KaratsubaZeros(E, rows(A.data1), cols(A.data1), A.N1, A.N2)
+    for _ in 1:steps
+        KMatMul!(W, A, T); KMatMul!(V, T, W); scalar_multiply!(W, T, 2); sub!(T, W, V)
+    end
+    T
+end
+
 export CuModArray, CuModMatrix, CuModVector, rows, cols, unsafe_Array, eye, zeros, rand, zero!, add!, sub!, elementwise_multiply!,
        negate!, scalar_add!, scalar_sub!, mod_elements!, change_modulus, change_modulus_no_alloc!, mulN!, stripe_mul!,
        mat_mul_gpu_type, mat_mul_type_inplace!, pluq_gpu_kernel, pluq, lu, rref, rank, inverse, is_invertible, is_invertible_with_inverse,
        upper_triangular_inverse_no_copy, lower_triangular_inverse_no_copy, forward_sub_gpu_type_32, backward_sub_gpu_type_32,
        apply_col_perm!, apply_col_inv_perm!, apply_row_perm!, apply_row_inv_perm!, perm_array_to_matrix, mod_inv,
+       hensel_pseudoinverse, hensel_pseudoinverse!, mul_panels!, mul_host!,
        KaratsubaArray, KaratsubaMatrix, KaratsubaVector, KaratsubaZeros, MatToKMat, KMatMul!, KMatMul_gemv!, initialize_plan!, scalar_multiply!,
        CuModArraySizeMismatchException, CuModArrayModulusMismatchException, CuModMatrixTooLargeException, CuModMatrixNotSquareException,
        CuModMatrixModulusNotPrimeException, InverseOverflowError, InverseNotDefinedException, MatrixNotInvertibleException

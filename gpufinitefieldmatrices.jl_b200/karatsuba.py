@@ -101,3 +101,21 @@ def negate_(C, A):
     """KaratsubaMatrix.jl:691-731."""
     _same(C, A)
     return _kew(capi.EW_RSSUB, C, A)
+
+
+def hensel_pseudoinverse(precision_steps: int, A: KaratsubaMatrix, T: KaratsubaMatrix) -> KaratsubaMatrix:
+    """Newton/Hensel lift `T = 2*T - T*(A*T)` (src/CuModMatrix/triangular/hensel.jl:15-18) on two-limb matrices modulo
+    M = N1*N2 (up to 2^52): each of the `precision_steps` iterations doubles the p-adic precision of A*T = I.  T is
+    updated in place and returned."""
+    _same(T, A)
+    from .cumodmatrix import zeros
+    r, c = A.data1.rows, A.data1.cols
+    ctx = A.data1.ctx
+    W = KaratsubaZeros(A.data1.elem_type, r, c, A.N1, A.N2, ctx=ctx)
+    V = KaratsubaZeros(A.data1.elem_type, r, c, A.N1, A.N2, ctx=ctx)
+    for _ in range(int(precision_steps)):
+        KMatMul_(W, A, T)
+        KMatMul_(V, T, W)
+        scalar_multiply_(W, T, 2)
+        sub_(T, W, V)
+    return T

@@ -1,13 +1,26 @@
 """Multi-GPU layer (new; the reference is single-GPU): one process per GPU, `torch.distributed` for the plumbing.
 
 Matmul and Karatsuba products shard by ROW BLOCKS of A (and C): rank g owns rows [g*ceil(m/G), ...).  B lives on the
-source rank and is broadcast in COLUMN PANELS; the modular GEMM of panel p (through the C ABI, `gffm_gemm_block`) is
-enqueued as soon as panel p has arrived, so it overlaps the NCCL broadcast of panel p+1 over NVLink.  No reduction is
-needed.  The pipeline below is backend-agnostic (NCCL on GPUs, gloo in the CPU tests) -- the compute is injected.
+source rank and is broadcast in COLUMN PANELS over NVLink.  Two drivers:
+
+* `BroadcastMatmul` (GPUs): the broadcasts run on a dedicated communication stream and mark one CUDA event per panel; ONE
+  ABI call (`gffm_gemm_panels`) consumes the panels -- plane split of panel p+1 and CRT of panel p on the library's
+  auxiliary stream while the tensor-core GEMM of panel p owns the compute stream.  The library hands back a `consumed`
+  event per panel, so the broadcast of the NEXT step's panel p only waits until this step has turned panel p into operand
+  planes: in a sequence of products the collective runs entirely under the previous product's GEMMs.
+* `pipelined_broadcast_matmul` (backend-agnostic, gloo in the CPU tests): same data flow with the per-panel compute
+  injected, one broadcast in flight ahead of the compute.
+
+No reduction is needed in either.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Tuple
+import ctypes as C
+from typing import Callable, List, Sequence, Tuple
+
+from . import capi
+
+PANEL_ALIGN = 256  # widest GEMM tile (columns): interior panel boundaries are multiples of it (gffm_gemm_panels)
 
 
 def row_block(m: int, world: int, rank: int) -> Tuple[int, int]:
@@ -17,15 +30,19 @@ def row_block(m: int, world: int, rank: int) -> Tuple[int, int]:
     return r0, min(m, r0 + per)
 
 
-def col_panels(n: int, npanels: int) -> List[Tuple[int, int]]:
-    """Column panels [c0, c1) of B used to pipeline the broadcast against the GEMM."""
-    npanels = max(1, min(npanels, n if n > 0 else 1))
+def col_panels(n: int, npanels: int, align: int = 1) -> List[Tuple[int, int]]:
+    """Column panels [c0, c1) of B used to pipeline the broadcast against the GEMM.  With `align` > 1 every interior
+    boundary is a multiple of it (fewer panels than asked for when n is small)."""
+    if n <= 0:
+        return []
+    npanels = max(1, min(npanels, n))
     per = (n + npanels - 1) // npanels
-    return [(c0, min(n, c0 + per)) for c0 in range(0, n, per)] if n > 0 else []
+    per = ((per + align - 1) // align) * align
+    return [(c0, min(n, c0 + per)) for c0 in range(0, n, per)]
 
 
 def pipelined_broadcast_matmul(dist, b_colmajor, panels, gemm_panel: Callable[[int, int], None], src: int = 0):
-    """One sharded product step.
+    """One sharded product step, compute injected.
 
     b_colmajor : tensor of shape (n_cols, ld) whose row j is column j of B (column-major storage); on `src` it holds
                  B, on the other ranks it is the receive buffer.
@@ -46,3 +63,55 @@ def broadcast_then(dist, tensors, fn: Callable[[], None], src: int = 0):
     for w in works:
         w.wait()
     fn()
+
+
+class BroadcastMatmul:
+    """Repeated sharded products C_shard = A_shard * B mod N with B broadcast from `src` every step (GPU only).
+
+    C, A     : CuModMatrix row blocks of this rank (same context).
+    B        : CuModMatrix wrapping `b_colmajor` (external memory: never plane-cached).
+    b_colmajor: torch tensor (n_cols, ld) int32, row j = column j of B; holds B on `src`, receive buffer elsewhere.
+    deliver  : deliver(c0, c1) enqueues the arrival of columns [c0, c1) in `b_colmajor` on the CURRENT torch stream
+               (default: dist.broadcast of b_colmajor[c0:c1] from `src`; the 1-GPU tests inject a device copy instead).
+    """
+
+    def __init__(self, torch, dist, C, A, B, b_colmajor, panels: Sequence[Tuple[int, int]], src: int = 0, deliver=None):
+        self.torch, self.dist = torch, dist
+        self.C, self.A, self.B, self.bt = C, A, B, b_colmajor
+        self.panels = list(panels)
+        self.src = src
+        self.deliver = deliver if deliver is not None else (lambda c0, c1: dist.broadcast(b_colmajor[c0:c1], src=src))
+        dev = b_colmajor.device
+        self.comm = torch.cuda.Stream(device=dev)
+        np_ = len(self.panels)
+        self.ready = [torch.cuda.Event() for _ in range(np_)]
+        self.consumed = [torch.cuda.Event() for _ in range(np_)]
+        self.off = (C.c_int64 * (np_ + 1))(*([p[0] for p in self.panels] + [self.panels[-1][1]]))
+        self._ready_h = (C.c_void_p * np_)()
+        self._cons_h = (C.c_void_p * np_)()
+        self._first = True
+
+    def step(self):
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        if self._first:
+            # whatever filled / last read the buffers on the caller's stream precedes the first delivery
+            self.comm.wait_stream(cur)
+            with torch.cuda.stream(cur):
+                for e in self.consumed:  # torch creates the CUDA event lazily, at the first record
+                    e.record(cur)
+        with torch.cuda.stream(self.comm):
+            for p, (c0, c1) in enumerate(self.panels):
+                self.comm.wait_event(self.consumed[p])  # previous step no longer reads panel p
+                self.deliver(c0, c1)
+                self.ready[p].record(self.comm)
+        for p in range(len(self.panels)):
+            self._ready_h[p] = self.ready[p].cuda_event
+            self._cons_h[p] = self.consumed[p].cuda_event
+        self._first = False
+        capi.check(self.C.lib.gffm_gemm_panels(self.C.h, self.A.h, self.B.h, len(self.panels), self.off,
+                                               self._ready_h, self._cons_h, 0, 0))
+
+    def finish(self):
+        """Make the current stream wait for the communication stream (before the buffers are reused or freed)."""
+        self.torch.cuda.current_stream().wait_stream(self.comm)

@@ -164,6 +164,16 @@ int32_t gffm_gemm_block(gffm_mat* C, int64_t cr0, int64_t cc0, gffm_mat* A, int6
  * three streams.  Blocks until C_host is complete. */
 int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, const void* A_host, int64_t lda, const void* B_host, int64_t ldb,
                        int64_t m, int64_t n, int64_t k, int32_t dtype, uint64_t N);
+/* Multi-GPU layer (new -- the reference is single-GPU; north_star (4): products shard by row blocks of A, B is broadcast).
+ * One sharded product step on this rank: C = A * B mod P where A, C are this rank's row blocks and B ARRIVES in `npanels`
+ * column panels [col_off[p], col_off[p+1]) (0-based, col_off has npanels+1 entries covering [0, cols(B)); interior offsets
+ * that are multiples of 256 take the pipelined path).  ready[p] (cudaEvent_t or NULL; the array may be NULL) has been
+ * recorded by the caller on the stream that delivers panel p (e.g. after ncclBroadcast); the plane split of panel p+1 and the
+ * CRT of panel p run on an internal stream while the tensor-core GEMM of panel p runs on the context stream.  consumed[p]
+ * (optional) is recorded once panel p has been read for the last time, so the caller may already overwrite it with the next
+ * step's data.  Semantics of the result are those of mul!(C,A,B) (CuModMatrix.jl:767-787). */
+int32_t gffm_gemm_panels(gffm_mat* C, gffm_mat* A, gffm_mat* B, int32_t npanels, const int64_t* col_off, void* const* ready,
+                         void* const* consumed, uint64_t in_bound_R, uint64_t mod_P);
 /* mul!(z,A,x;R,P) (CuModMatrix.jl:816-836, stripe_mul.jl:82-168): z = A*x mod P, x and z are n x 1 matrices */
 int32_t gffm_gemv(gffm_mat* z, gffm_mat* A, gffm_mat* x, uint64_t in_bound_R, uint64_t mod_P);
 

@@ -504,3 +504,19 @@ def karatsuba_matmul_direct(A1, A2, B1, B2, N1, N2):
         Bf = Bf[:, None]
     C = (Af @ Bf) % (N1 * N2)
     return np.array(C % N1, dtype=np.int64), np.array(C // N1, dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Hensel lifting of an inverse -- src/CuModMatrix/triangular/hensel.jl:13-21 (not loaded by the reference package:
+# it needs Nemo for the final residue-ring matrix; the arithmetic is the three-line Newton loop below)
+# ----------------------------------------------------------------------------------------------------------
+def hensel_pseudoinverse(N: int, precision: int, A, T):
+    """T with A*T == I (mod N)  ->  T with A*T == I (mod N^precision); exact python integers (object arrays)."""
+    M = N ** precision
+    A = np.array(A, dtype=object) % M
+    T = np.array(T, dtype=object) % M
+    i = 1
+    while i < precision:  # hensel.jl:15-18
+        T = (2 * T - T.dot(A.dot(T) % M)) % M
+        i *= 2
+    return T

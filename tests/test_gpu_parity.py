@@ -476,3 +476,116 @@ def test_baseline_config5_karatsuba_32768(g):
     r1 = g.zeros(np.float64, n, n, N1); g.fill_(r1, want % N1)
     r2 = g.zeros(np.float64, n, n, N1); g.fill_(r2, want // N1)
     assert CK.data1.equals(r1) and CK.data2.equals(r2)
+
+
+# ---------------------------------------------------------------- multi-GPU layer on one GPU ----------------------------------------------
+@pytest.mark.parametrize("m,k,n,N,offs", [
+    (70, 50, 90, 33554393, [0, 17, 17, 60, 90]),            # small + unaligned + empty panel -> panel-by-panel dispatcher path
+    (640, 1024, 1536, 33554393, [0, 256, 768, 1536]),       # pipelined, RNS
+    (300, 1000, 1300, 65521, [0, 512, 1024, 1300]),         # pipelined, two positional limbs, ragged edges
+    (1000, 640, 2048, 11, [0, 1024, 2048]),                 # pipelined, one limb
+    (256, 4096, 512, 2 ** 26, [0, 512]),                    # a single panel
+])
+def test_gemm_panels_vs_oracle(g, m, k, n, N, offs):
+    """gffm_gemm_panels without events == mul! == oracle (the panel pipeline of the multi-GPU layer, fed from resident B)."""
+    import ctypes as C
+    A = O.synth_matrix(51, m, k, N); B = O.synth_matrix(52, k, n, N)
+    dA = g.CuModMatrix(A, N); dB = g.CuModMatrix(B, N); dC = g.zeros(np.float32, m, n, N)
+    off = (C.c_int64 * len(offs))(*offs)
+    g.capi.check(dC.lib.gffm_gemm_panels(dC.h, dA.h, dB.h, len(offs) - 1, off, None, None, 0, 0))
+    assert np.array_equal(dC.to_int(), O.matmul_mod(A, B, N))
+    with pytest.raises(g.GffmError):
+        bad = (C.c_int64 * 3)(0, 5, n - 1)
+        g.capi.check(dC.lib.gffm_gemm_panels(dC.h, dA.h, dB.h, 2, bad, None, None, 0, 0))
+    with pytest.raises(g.CuModArraySizeMismatchException):
+        g.capi.check(dC.lib.gffm_gemm_panels(dC.h, dB.h, dA.h, len(offs) - 1, off, None, None, 0, 0))
+
+
+@pytest.mark.parametrize("N", [33554393, 65521])
+def test_broadcast_matmul_streamed_panels(g, N):
+    """BroadcastMatmul on one GPU: the 'broadcast' is a device copy on the communication stream, B changes every step.
+    Checks the ready/consumed event protocol (panel p of step s+1 may overwrite the receive buffer as soon as step s has
+    turned it into planes) -- every step must see exactly its own B."""
+    import torch
+    m, k, n = 1024, 2048, 4096
+    ctx = g.Context(0)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        A = g.synth(m, k, N, 61, ctx=ctx)
+        ld = ((k + 31) // 32) * 32
+        srcs = []
+        for s in range(3):
+            Bs = g.synth(k, n, N, 70 + s, ctx=ctx)
+            t = torch.zeros((n, ld), dtype=torch.int32, device="cuda")
+            W = g.CuModMatrix.wrap_device(t.data_ptr(), k, n, ld, N, ctx=ctx)
+            g.copy_(W, Bs)
+            srcs.append((t, W))
+        Bt = torch.zeros((n, ld), dtype=torch.int32, device="cuda")
+        B = g.CuModMatrix.wrap_device(Bt.data_ptr(), k, n, ld, N, ctx=ctx)
+        Cs = [g.zeros(np.float32, m, n, N, ctx=ctx) for _ in range(3)]
+        ctx.sync()
+        cur = {"s": 0}
+        panels = g.multigpu.col_panels(n, 4, align=g.multigpu.PANEL_ALIGN)
+        assert panels == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
+
+        def deliver(c0, c1):
+            Bt[c0:c1].copy_(srcs[cur["s"]][0][c0:c1], non_blocking=True)
+
+        for s in range(3):
+            cur["s"] = s
+            bm = g.multigpu.BroadcastMatmul(torch, None, Cs[s], A, B, Bt, panels, deliver=deliver) if s == 0 else bm
+            bm.C = Cs[s]
+            A.touch()
+            bm.step()
+        bm.finish()
+        ctx.sync()
+        torch.cuda.synchronize()
+        for s in range(3):
+            ref = g.zeros(np.float32, m, n, N, ctx=ctx)
+            g.mul_(ref, A, srcs[s][1])
+            assert Cs[s].equals(ref), f"step {s}"
+        ctx.sync()
+
+
+# ---------------------------------------------------------------- Hensel lifting (SURVEY 8f rank 4) ----------------------------------------------
+@pytest.mark.parametrize("p,prec,n", [(7, 4, 40), (13, 7, 150), (2, 30, 64), (181, 4, 300)])
+def test_hensel_pseudoinverse(g, p, prec, n):
+    """hensel_pseudoinverse (triangular/hensel.jl:13-21) on CuModMatrix: mod-p inverse from the GPU elimination, lifted to
+    p^prec (< 2^32) by tensor-core products; bit-exact vs the python-int oracle and A*T == I (mod p^prec)."""
+    M = p ** prec
+    seed = 90
+    while True:
+        A = O.synth_matrix(seed, n, n, M)
+        ok, T0 = g.is_invertible_with_inverse(g.CuModMatrix(A % p, p))
+        if ok:
+            break
+        seed += 1
+    T0h = T0.to_int()
+    T = g.hensel_pseudoinverse(p, prec, g.CuModMatrix(A, M), g.CuModMatrix(T0h, M))
+    want = O.hensel_pseudoinverse(p, prec, A, T0h)
+    assert np.array_equal(T.to_int().astype(object), want)
+    I = (g.CuModMatrix(A, M) * T).to_int()
+    assert np.array_equal(I, np.eye(n, dtype=np.int64))
+    with pytest.raises(g.CuModArrayModulusMismatchException):
+        g.hensel_pseudoinverse(p, prec, g.CuModMatrix(A % p, p), T0)
+
+
+def test_hensel_pseudoinverse_karatsuba(g):
+    """The same Newton lift on two-limb matrices: modulus 13^7 = 13^4 * 13^3 (the reference's Karatsuba test moduli,
+    test/KaratsubaMatrix/basic_operations_test.jl:77-78), three doublings from a mod-13 inverse."""
+    p, N1, N2, n = 13, 13 ** 4, 13 ** 3, 96
+    M = N1 * N2
+    seed = 95
+    while True:
+        A = O.synth_matrix(seed, n, n, M)
+        ok, T0 = g.is_invertible_with_inverse(g.CuModMatrix(A % p, p))
+        if ok:
+            break
+        seed += 1
+    T0h = T0.to_int()
+    AK = g.MatToKMat(A, N1, N2); TK = g.MatToKMat(T0h, N1, N2)
+    g.karatsuba.hensel_pseudoinverse(3, AK, TK)            # precision 1 -> 2 -> 4 -> 8 >= 7
+    want = O.hensel_pseudoinverse(p, 8, A, T0h) % M
+    assert np.array_equal(TK.Array(), want)
+    assert np.array_equal(np.array(A, dtype=object).dot(TK.Array()) % M, np.eye(n, dtype=object))

@@ -64,3 +64,10 @@ def test_partition_helpers():
         for p in (1, 3, 8, 100):
             pans = mg.col_panels(n, p)
             assert pans[0][0] == 0 and pans[-1][1] == n and all(a[1] == b[0] for a, b in zip(pans, pans[1:]))
+    # aligned panels (gffm_gemm_panels): interior boundaries are multiples of the GEMM tile width, no empty panel
+    for n in (1, 255, 256, 1000, 16384, 16385, 32768):
+        for p in (1, 3, 8, 16):
+            pans = mg.col_panels(n, p, align=mg.PANEL_ALIGN)
+            assert pans[0][0] == 0 and pans[-1][1] == n and all(a[1] == b[0] for a, b in zip(pans, pans[1:]))
+            assert all(c0 % mg.PANEL_ALIGN == 0 and c1 > c0 for c0, c1 in pans) and len(pans) <= p
+    assert mg.col_panels(16384, 8, align=256) == [(2048 * i, 2048 * (i + 1)) for i in range(8)]

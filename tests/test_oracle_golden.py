@@ -221,3 +221,19 @@ def test_c_oracle_matches_numpy_oracle():
         E, L, pr, piv = OC.echelon(A, N)
         Eo, Lo, pro, pivo = O.echelon(A, N)
         assert np.array_equal(E, Eo) and np.array_equal(L, Lo) and pr == pro and piv == pivo
+
+
+def test_hensel_lift_oracle():
+    """hensel.jl:13-21 restated: the lifted T satisfies A*T == I modulo N^precision and reduces to the start value mod N."""
+    rng = np.random.default_rng(5)
+    for (p, prec, n) in ((7, 4, 6), (13, 7, 5), (2, 20, 4), (65521, 3, 4)):
+        while True:
+            A = rng.integers(0, p ** prec, size=(n, n))
+            ok, T0 = O.is_invertible_with_inverse(A % p, p)
+            if ok:
+                break
+        T = O.hensel_pseudoinverse(p, prec, A, T0)
+        M = p ** prec
+        I = np.eye(n, dtype=object)
+        assert np.array_equal(np.array(A, dtype=object).dot(T) % M, I)
+        assert np.array_equal(np.array(T % p, dtype=np.int64), T0)
