@@ -144,7 +144,12 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--modulus", type=int, default=MOD_DEFAULT)
-    ap.add_argument("--panels", type=int, default=8, help="column panels of B for the pipelined NCCL broadcast (N > 1)")
+    ap.add_argument("--panels", default="8,4", help="column panels of B for the pipelined NCCL broadcast (N > 1); several values: "
+                    "the fastest is picked during the untimed warm-up")
+    ap.add_argument("--gemm-ctas", default="0,140,132", help="cap on the persistent GEMM grid (0 = all SMs) so that the concurrent NCCL "
+                    "kernels find free SMs (N > 1); several values: the fastest is picked during the untimed warm-up")
+    ap.add_argument("--bcast", default="broadcast", choices=["broadcast", "scatter_allgather"],
+                    help="how B is replicated every step (N > 1): ncclBroadcast per panel, or scatter + in-place all-gather per panel")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also time N=11 and N=65521 and PLUQ (reported under config.extras)")
@@ -165,6 +170,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.pop("NCCL_DEBUG", None)  # no "NCCL version" banner on stdout: ONE JSON line
+        if os.environ.get("GFFM_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["GFFM_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, N = args.n, args.modulus
     W = max(3, args.warmup)
@@ -200,12 +208,15 @@ def main():
             ctx.sync()
             del Bs
         C = g.zeros(np.float32, mloc, n, N, ctx=ctx)
-        panels = g.multigpu.col_panels(n, args.panels if world > 1 else 1, align=g.multigpu.PANEL_ALIGN)
-        npan = len(panels)
-        pan = panels[0][1] - panels[0][0]
         # N > 1: NCCL broadcast of B in column panels on a communication stream; ONE gffm_gemm_panels call per step consumes them
         # (split of panel p+1 / CRT of panel p under the GEMM of panel p; the next step's broadcast runs under this step's GEMMs)
-        bm = g.multigpu.BroadcastMatmul(torch, dist, C, A, B, Bt, panels, src=0) if world > 1 else None
+        pan_cands = [int(x) for x in str(args.panels).split(",")] if world > 1 else [1]
+        cta_cands = [int(x) for x in str(args.gemm_ctas).split(",")] if world > 1 else [0]
+        bm = None
+
+        def make_bm(npanels):
+            pans = g.multigpu.col_panels(n, npanels, align=g.multigpu.PANEL_ALIGN)
+            return pans, (g.multigpu.BroadcastMatmul(torch, dist, C, A, B, Bt, pans, src=0, collective=args.bcast) if world > 1 else None)
 
         def step():
             A.touch()  # every step is a FRESH product: the cached 8-bit planes of A are rebuilt (B is external memory, never cached)
@@ -213,6 +224,30 @@ def main():
                 g.mul_(C, A, B)
             else:
                 bm.step()
+
+        tune = {}
+        choice = (pan_cands[0], cta_cands[0])
+        if world > 1 and len(pan_cands) * len(cta_cands) > 1:  # untimed: pick (panels, GEMM grid cap) by a short trial of each
+            for pc in pan_cands:
+                panels, bm = make_bm(pc)
+                for cc in cta_cands:
+                    ctx.set_gemm_ctas(cc)
+                    for _ in range(2):
+                        step()
+                    bm.finish(); barrier()
+                    a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                    a0.record(stream)
+                    for _ in range(6):
+                        step()
+                    bm.finish(); a1.record(stream); barrier()
+                    tt = torch.tensor([a0.elapsed_time(a1) / 6], dtype=torch.float64, device=f"cuda:{local}")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    tune[(pc, cc)] = float(tt.item())
+            choice = min(tune, key=tune.get)  # identical on every rank (all-reduced times)
+        panels, bm = make_bm(choice[0])
+        ctx.set_gemm_ctas(choice[1])
+        npan = len(panels)
+        pan = panels[0][1] - panels[0][0]
 
         for _ in range(W):
             step()
@@ -245,6 +280,17 @@ def main():
             launches = int(lt.item())
         checksum = C.checksum()
         value = 2.0 * n ** 3 / (ms * 1e-3) / 1e9
+        shard_ok = None
+        if world > 1:  # every rank: the pipelined, broadcast-fed shard == the plain product of its row block with the B it received
+            Cref = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+            g.mul_(Cref, A, B)
+            ok = torch.tensor([1 if C.equals(Cref) else 0], dtype=torch.int32, device=f"cuda:{local}")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            bsum = torch.tensor([B.checksum() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=f"cuda:{local}")
+            bmin = bsum.clone(); bmax = bsum.clone()
+            dist.all_reduce(bmin, op=dist.ReduceOp.MIN); dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
+            shard_ok = bool(ok.item() == 1 and bmin.item() == bmax.item())   # and every rank holds the same B
+            del Cref
 
         # ---- roofline of the dominant kernel (tcgen05 GEMM): a few more profiled steps, kernel-only durations --------
         gemm_ms = [phase_ms[1]] if len(phase_ms) >= 2 else []
@@ -402,7 +448,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{n}x{n} * {n}x{n} matmul mod {N} ({bits}-bit modulus), A,B resident as uint32 residues", "n": n, "modulus": N,
                        "encoding": "RNS int8 tcgen05" if N > 65536 else "positional int8 limbs tcgen05",
-                       "sharding": "single GPU" if world == 1 else f"row blocks of A over {world} GPUs, B broadcast from rank 0 by NCCL every step in {npan} column panels on a communication stream, consumed by gffm_gemm_panels (split/CRT under the GEMM, next step's broadcast under this step's GEMMs)",
+                       "sharding": "single GPU" if world == 1 else f"row blocks of A over {world} GPUs, B replicated from rank 0 by NCCL ({args.bcast}) every step in {npan} column panels on a communication stream, consumed by gffm_gemm_panels (split/CRT under the GEMM, next step's broadcast under this step's GEMMs)",
+                       "shards_match_local_product_on_all_ranks": shard_ok,
+                       "gemm_grid_cap": choice[1], "warmup_trials_ms": {f"panels={k[0]},gemm_ctas={k[1]}": round(v, 4) for k, v in tune.items()},
                        "l2_policy": f"inputs larger than L2: A and B are {4 * n * n / 2**20:.0f} MiB each vs 126 MB L2", "checksum_rank0": f"{checksum:016x}",
                        "extras": extras},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

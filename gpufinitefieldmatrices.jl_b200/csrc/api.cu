@@ -179,6 +179,11 @@ extern "C" int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t cap, int
   if (n) *n = k;
   return GFFM_OK;
 }
+extern "C" int32_t gffm_set_gemm_ctas(gffm_ctx* ctx, int32_t ctas) {
+  if (!ctx || ctas < 0) GFFM_FAIL(GFFM_ERR_INVALID, "bad argument");
+  ctx->gemm_ctas = ctas;
+  return GFFM_OK;
+}
 extern "C" int32_t gffm_launch_count(gffm_ctx* ctx, int64_t* count) {
   if (!ctx || !count) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   *count = ctx->launches;

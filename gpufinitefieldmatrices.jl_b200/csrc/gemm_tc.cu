@@ -1124,7 +1124,8 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
     attr_set = true;
   }
   const int total = p.batches * p.num_m_blk * p.num_n_blk;
-  static const int max_ctas = getenv("GFFM_GEMM_CTAS") ? atoi(getenv("GFFM_GEMM_CTAS")) : 0;  // experiment: leave SMs to concurrent kernels
+  static const int env_ctas = getenv("GFFM_GEMM_CTAS") ? atoi(getenv("GFFM_GEMM_CTAS")) : 0;
+  const int max_ctas = ctx->gemm_ctas > 0 ? ctx->gemm_ctas : env_ctas;  // leave SMs to concurrent kernels (NCCL in the multi-GPU layer)
   const int sms = (max_ctas > 0 && max_ctas < ctx->num_sms) ? max_ctas : ctx->num_sms;
   const int grid = total < sms ? total : sms;
   static const int hints = getenv("GFFM_L2_HINTS") ? atoi(getenv("GFFM_L2_HINTS")) : 0;
@@ -1739,6 +1740,31 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
     GFFM_CUDA(cudaStreamWaitEvent(sh, ev0, 0));
     GFFM_CUDA(cudaStreamWaitEvent(sd, ev0, 0));
   }
+  // GFFM_TILED_TRACE=1: timeline of every kernel of the pipeline (timing events around each launch, printed relative to the
+  // start of the call; synchronises at the end of the call -- diagnostics only)
+  static const bool trace_on = getenv("GFFM_TILED_TRACE") != nullptr;
+  struct TraceRec {
+    const char* what;
+    int idx;
+    cudaEvent_t a, b;
+  };
+  std::vector<TraceRec> trace;
+  cudaEvent_t trace0 = nullptr;
+  auto trace_begin = [&](cudaStream_t st) -> cudaEvent_t {
+    if (!trace_on) return nullptr;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    return e;
+  };
+  auto trace_end = [&](const char* what, int idx, cudaEvent_t a, cudaStream_t st) {
+    if (!trace_on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    trace.push_back(TraceRec{what, idx, a, e});
+  };
+  if (trace_on) trace0 = trace_begin(sc);
   CUtensorMap tmA, tmB, tmBh;
   GFFM_TRY(make_plane_tmap(&tmA, pA, Kp, rowsPA, nplanes, BM));
   GFFM_TRY(make_plane_tmap(&tmB, pB, Kp, rowsPB, nplanes, BN));
@@ -1760,7 +1786,9 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
         GFFM_LAUNCH_CHECK(ctx);
       }
       MatView v{dA + i0, ldA, mi, k};
+      cudaEvent_t ta = trace_begin(sx);
       GFFM_TRY(run_split(ctx, true, v, nullptr, 0, k, pA + i0 * Kp, Kp, rowsPA, sp, sx));
+      trace_end("splitA", t, ta, sx);
     }
     if (t < nbB && feed && feed->ready && feed->ready[t]) GFFM_CUDA(cudaStreamWaitEvent(sx, feed->ready[t], 0));
     if (t < nbB && !hitB) {
@@ -1780,7 +1808,9 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
           GFFM_LAUNCH_CHECK(ctx);
         }
         MatView v{dB + j0 * ldB, ldB, k, nj};
+        cudaEvent_t tb = trace_begin(sx);
         GFFM_TRY(run_split(ctx, false, v, nullptr, 0, k, pB + j0 * Kp, Kp, rowsPB, sp, sx));
+        trace_end("splitB", t, tb, sx);
       }
     }
     ev_split[t] = next_ev();
@@ -1810,6 +1840,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
       GFFM_CUDA(cudaEventCreate(&t1));
       GFFM_CUDA(cudaEventRecord(t0, sc));
     }
+    cudaEvent_t tg = trace_begin(sc);
     if (rns) {
       memcpy(p.mods, plan.mods, sizeof(p.mods));
       p.batches = plan.s;
@@ -1826,6 +1857,7 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
       if (L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, p, sc, &tmBh));
       else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, p, sc, &tmBh));
     }
+    trace_end("gemm", i * 100 + j, tg, sc);
     if (ctx->profile) {
       GFFM_CUDA(cudaEventRecord(t1, sc));
       ctx->tile_events.push_back(t0);
@@ -1843,7 +1875,9 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
       cudaEvent_t ready = t.done;
       if (rns) {
         GFFM_CUDA(cudaStreamWaitEvent(sx, t.done, 0));
+        cudaEvent_t tc = trace_begin(sx);
         GFFM_TRY(launch_crt(ctx, sx, plan.cp, E + j0 * lde + i0, lde, e_plane, mi, nj, dC + j0 * ldC + i0, ldC, nullptr, 0));
+        trace_end("crt", t.i * 100 + t.j, tc, sx);
         ready = next_ev();
         GFFM_CUDA(cudaEventRecord(ready, sx));
       }
@@ -1888,6 +1922,23 @@ int32_t tiled_gemm(gffm_ctx* ctx, MatView Cv, MatView A, MatView B, const HostIO
   // the compute stream continues only after the helpers are done (C complete, planes reusable)
   cudaEventRecord(ev_end, sx);
   cudaStreamWaitEvent(sc, ev_end, 0);
+  if (trace_on) {
+    cudaEvent_t tend = trace_begin(sc);
+    cudaStreamSynchronize(sc);
+    float total = 0.f;
+    cudaEventElapsedTime(&total, trace0, tend);
+    fprintf(stderr, "[tiled trace] call: %.3f ms (blocks %dx%d)\n", total, nbA, nbB);
+    for (const TraceRec& r : trace) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, trace0, r.a);
+      cudaEventElapsedTime(&b, trace0, r.b);
+      fprintf(stderr, "[tiled trace]   %-7s %4d  %8.3f -> %8.3f  (%.3f ms)\n", r.what, r.idx, a, b, b - a);
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    cudaEventDestroy(trace0);
+    cudaEventDestroy(tend);
+  }
   if (host) {
     cudaStreamSynchronize(sd);
     cudaStreamSynchronize(sh);

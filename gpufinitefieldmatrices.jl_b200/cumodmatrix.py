@@ -47,6 +47,10 @@ class Context:
         capi.check(self.lib.gffm_last_timings(self.h, buf, 16, C.byref(n)))
         return [buf[i] for i in range(n.value)]
 
+    def set_gemm_ctas(self, ctas: int):
+        """Cap the persistent GEMM grid (0 = one CTA per SM) so that concurrent NCCL kernels find free SMs."""
+        capi.check(self.lib.gffm_set_gemm_ctas(self.h, int(ctas)))
+
     def launch_count(self) -> int:
         n = C.c_int64(0)
         capi.check(self.lib.gffm_launch_count(self.h, C.byref(n)))

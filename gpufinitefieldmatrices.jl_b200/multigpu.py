@@ -15,7 +15,7 @@ No reduction is needed in either.
 """
 from __future__ import annotations
 
-import ctypes as C
+import ctypes
 from typing import Callable, List, Sequence, Tuple
 
 from . import capi
@@ -65,30 +65,63 @@ def broadcast_then(dist, tensors, fn: Callable[[], None], src: int = 0):
     fn()
 
 
+def broadcast_scatter_allgather(dist, panel, src: int = 0):
+    """Broadcast of one column panel as scatter + all-gather: `src` sends a different 1/G slice of the panel to every
+    rank, then the ranks all-gather the slices in place.  Every NVLink port carries 1/G of the panel per peer instead of
+    the whole panel travelling down one ring, and the all-gather is the collective NCCL runs fastest on NVSwitch (NVLS).
+    `panel` is the same region of the replicated buffer on every rank (on `src` it already holds the data); its first
+    dimension must be divisible by the world size, otherwise the plain broadcast is used.  Blocking semantics are those of
+    the enclosed collectives (stream-ordered on CUDA)."""
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    rows = panel.shape[0]
+    if world == 1:
+        return
+    if rows % world != 0 or rows == 0:
+        dist.broadcast(panel, src=src)
+        return
+    per = rows // world
+    mine = panel[rank * per:(rank + 1) * per]
+    if rank == src:
+        dist.scatter(mine, [panel[r * per:(r + 1) * per] for r in range(world)], src=src)
+    else:
+        dist.scatter(mine, None, src=src)
+    dist.all_gather_into_tensor(panel, mine)
+
+
 class BroadcastMatmul:
     """Repeated sharded products C_shard = A_shard * B mod N with B broadcast from `src` every step (GPU only).
 
     C, A     : CuModMatrix row blocks of this rank (same context).
     B        : CuModMatrix wrapping `b_colmajor` (external memory: never plane-cached).
     b_colmajor: torch tensor (n_cols, ld) int32, row j = column j of B; holds B on `src`, receive buffer elsewhere.
+    collective: "broadcast" (ncclBroadcast per panel) or "scatter_allgather" (broadcast_scatter_allgather per panel).
     deliver  : deliver(c0, c1) enqueues the arrival of columns [c0, c1) in `b_colmajor` on the CURRENT torch stream
                (default: dist.broadcast of b_colmajor[c0:c1] from `src`; the 1-GPU tests inject a device copy instead).
     """
 
-    def __init__(self, torch, dist, C, A, B, b_colmajor, panels: Sequence[Tuple[int, int]], src: int = 0, deliver=None):
+    def __init__(self, torch, dist, C, A, B, b_colmajor, panels: Sequence[Tuple[int, int]], src: int = 0, deliver=None,
+                 collective: str = "broadcast"):
         self.torch, self.dist = torch, dist
         self.C, self.A, self.B, self.bt = C, A, B, b_colmajor
         self.panels = list(panels)
         self.src = src
-        self.deliver = deliver if deliver is not None else (lambda c0, c1: dist.broadcast(b_colmajor[c0:c1], src=src))
+        if deliver is None:
+            if collective == "scatter_allgather":
+                deliver = lambda c0, c1: broadcast_scatter_allgather(dist, b_colmajor[c0:c1], src=src)  # noqa: E731
+            elif collective == "broadcast":
+                deliver = lambda c0, c1: dist.broadcast(b_colmajor[c0:c1], src=src)  # noqa: E731
+            else:
+                raise ValueError(f"unknown collective {collective!r}")
+        self.deliver = deliver
         dev = b_colmajor.device
         self.comm = torch.cuda.Stream(device=dev)
         np_ = len(self.panels)
         self.ready = [torch.cuda.Event() for _ in range(np_)]
         self.consumed = [torch.cuda.Event() for _ in range(np_)]
-        self.off = (C.c_int64 * (np_ + 1))(*([p[0] for p in self.panels] + [self.panels[-1][1]]))
-        self._ready_h = (C.c_void_p * np_)()
-        self._cons_h = (C.c_void_p * np_)()
+        self.off = (ctypes.c_int64 * (np_ + 1))(*([p[0] for p in self.panels] + [self.panels[-1][1]]))
+        self._ready_h = (ctypes.c_void_p * np_)()
+        self._cons_h = (ctypes.c_void_p * np_)()
         self._first = True
 
     def step(self):

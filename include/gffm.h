@@ -100,6 +100,9 @@ int32_t gffm_set_profiling(gffm_ctx* ctx, int32_t on);
  * launch durations, number of GEMM launches}; eliminations: {panel phase, triangular solves, Schur GEMMs}.  Blocks until
  * the events have completed. */
 int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t capacity, int32_t* n_written);
+/* Cap on the number of persistent CTAs of the tensor-core GEMM (0 = one per SM, the default).  The GEMM CTA owns its SM's
+ * shared memory, so kernels of OTHER libraries (NCCL's broadcast in the multi-GPU layer) can only run on SMs it leaves free. */
+int32_t gffm_set_gemm_ctas(gffm_ctx* ctx, int32_t ctas);
 /* number of library kernels launched on this context since creation (bench.py's gpu_launches) */
 int32_t gffm_launch_count(gffm_ctx* ctx, int64_t* count);
 

@@ -42,6 +42,32 @@ def _worker(rank, world, port, m, k, n, N, npan, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_sag(rank, world, port, rows, cols, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import gffm_b200 as g
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    buf = torch.zeros((rows, cols), dtype=torch.int32)
+    if rank == 0:
+        buf.copy_(torch.arange(rows * cols, dtype=torch.int32).reshape(rows, cols) * 7 + 3)
+    for (c0, c1) in g.multigpu.col_panels(rows, 3):
+        g.multigpu.broadcast_scatter_allgather(dist, buf[c0:c1], src=0)
+    np.save(os.path.join(out_dir, f"b_{rank}.npy"), buf.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,rows", [(2, 12), (3, 18), (2, 7)])
+def test_broadcast_scatter_allgather(tmp_path, world, rows):
+    """scatter + in-place all-gather == broadcast on every rank (divisible panels; indivisible ones fall back to broadcast)."""
+    port = _free_port()
+    mp.spawn(_worker_sag, args=(world, port, rows, 5, str(tmp_path)), nprocs=world, join=True)
+    want = (np.arange(rows * 5, dtype=np.int32).reshape(rows, 5) * 7 + 3)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"b_{r}.npy"), want), f"rank {r}"
+
+
 @pytest.mark.parametrize("m,k,n,N,npan", [(70, 50, 90, 33554393, 4), (5, 9, 3, 11, 8)])
 def test_sharded_matmul_world2(tmp_path, m, k, n, N, npan):
     world = 2
