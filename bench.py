@@ -61,6 +61,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported (the sampler itself is started before the
+        warm-up so that nvidia-smi is already polling when a short timed region begins)."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -72,7 +77,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        first = getattr(self, "first", 0)
+        lines = self.lines[first:] if len(self.lines) - first >= 2 else self.lines[max(0, first - 3):]  # timed region shorter than the poll period
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -249,12 +256,14 @@ def main():
         npan = len(panels)
         pan = panels[0][1] - panels[0][0]
 
-        for _ in range(W):
-            step()
-        barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for _ in range(W):
+            step()
+        barrier()
+        if rank == 0:
+            sampler.mark()
         ctx.set_profiling(True)
         l0 = ctx.launch_count()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

@@ -8,6 +8,7 @@ from .cumodmatrix import *  # noqa: F401,F403
 from .cumodmatrix import Context, CuModMatrix, CuModVector, default_context
 from . import karatsuba
 from . import multigpu
-from .karatsuba import KaratsubaMatrix, KaratsubaVector, KaratsubaZeros, KMatMul_, KMatMul_gemv_, MatToKMat, initialize_plan_
+from .karatsuba import (KaratsubaArray, KaratsubaMatrix, KaratsubaVector, KaratsubaZeros, Karatsubacopy, KMatMul_, KMatMul_gemv_, KMatToMat,
+                        MatToKMat, initialize_plan_)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -310,8 +310,20 @@ KaratsubaVector(d1::CuModArray{T,1}, d2::CuModArray{T,1}, N1, N2, M=N1 * N2) whe
 function KaratsubaMatrix(::Type{T}, A::AbstractMatrix, N1, N2, M=N1 * N2) where {T}       # KaratsubaMatrix.jl:372-397
     Am = mod.(A, M); KaratsubaMatrix(CuModMatrix(mod.(Am, N1), N1; elem_type=T), CuModMatrix(div.(Am, N1), N1; elem_type=T), N1, N2, M)
 end
-const MatToKMat = KaratsubaMatrix
-KaratsubaZeros(::Type{T}, r, c, N1, N2, M=N1 * N2) where {T} = KaratsubaMatrix(zeros(T, r, c, N1), zeros(T, r, c, N1), N1, N2, M)   # :404-420
+MatToKMat(::Type{T}, A::AbstractArray, M::Integer) where {T} = KaratsubaMatrix(T, A, M, M, M)                  # :367-370
+MatToKMat(A::AbstractArray, M::Integer) = MatToKMat(eltype(A), A, M)                                          # :358-360
+MatToKMat(::Type{T}, A::AbstractArray, N1::Integer, N2::Integer, M::Integer=N1 * N2) where {T} = KaratsubaMatrix(T, A, N1, N2, M)
+KMatToMat(::Type, K::KaratsubaArray) = Array(K)                                                               # :352-356
+Base.size(K::KaratsubaArray) = size(K.data1)                                                                  # :302
+Base.getindex(K::KaratsubaArray, i::Int, j::Int) = Int(K.data1[i, j]) + K.N1 * Int(K.data2[i, j])             # :304
+Base.getindex(K::KaratsubaArray, i::Int) = Int(K.data1[i]) + K.N1 * Int(K.data2[i])                           # :305
+Base.setindex!(K::KaratsubaArray, v, i::Int, j::Int) = (K.data1[i, j] = rem(v, K.N1); K.data2[i, j] = div(v, K.N1))   # :307-310
+Base.setindex!(K::KaratsubaArray, v, i::Int) = (K.data1[i] = rem(v, K.N1); K.data2[i] = div(v, K.N1))         # :312-316
+Base.copy!(B::KaratsubaArray, A::KaratsubaArray) = (copy!(B.data1, A.data1); copy!(B.data2, A.data2); B)      # :338-345
+zero!(K::KaratsubaArray) = (zero!(K.data1); zero!(K.data2); K)                                                # :347-350
+Karatsubacopy(A::KaratsubaArray{T,D}) where {T,D} = KaratsubaArray{T,D}(copy(A.data1), copy(A.data2), nothing, A.N1, A.N2, A.N1 * A.N2)   # :738-744
+_klike(A::KaratsubaArray{T,D}, r=rows(A.data1), c=cols(A.data1)) where {T,D} = KaratsubaZeros(T, r, c, A.N1, A.N2, A.M)
+KaratsubaZeros(::Type{T}, r, c, N1, N2, M=N1 * N2, use_gpu::Bool=true) where {T} = KaratsubaMatrix(zeros(T, r, c, N1), zeros(T, r, c, N1), N1, N2, M)   # :404-420
 initialize_plan!(K::KaratsubaArray) = K        # :422-424 -- the limb add is fused into the GEMM prologue, no plan buffer needed
 Array(K::KaratsubaArray) = Int.(Array(K.data1)) .+ K.N1 .* Int.(Array(K.data2))            # :318-336
 function KMatMul!(C::KaratsubaArray, A::KaratsubaArray, B::KaratsubaArray)                 # :133-204 (and KMatMul_gemv! :238-300)
@@ -326,6 +338,11 @@ add!(C::KaratsubaArray, A::KaratsubaArray, B::KaratsubaArray) = _kew(1, C, A, B,
 sub!(C::KaratsubaArray, A::KaratsubaArray, B::KaratsubaArray) = _kew(2, C, A, B, 0)       # :583-629
 scalar_multiply!(C::KaratsubaArray, A::KaratsubaArray, s::Integer) = _kew(7, C, A, nothing, s)   # :631-666
 negate!(C::KaratsubaArray, A::KaratsubaArray) = _kew(6, C, A, nothing, 0)                 # :691-731
++(A::KaratsubaArray, B::KaratsubaArray) = add!(_klike(A), A, B)                           # :428-438
+-(A::KaratsubaArray, B::KaratsubaArray) = sub!(_klike(A), A, B)                           # :440-449
+*(a::Number, A::KaratsubaArray) = scalar_multiply!(_klike(A), A, a)                       # :451-461
+*(A::KaratsubaArray, a::Number) = a * A                                                   # :463-465
+*(A::KaratsubaArray, B::KaratsubaArray) = KMatMul!(_klike(A, rows(A.data1), cols(B.data1)), A, B)   # :467-503 (unfinished in the reference)
 
 # ---- Hensel lifting of an inverse (reference src/CuModMatrix/triangular/hensel.jl:13-21; not loaded there, needs Nemo) -----
 # A, T carry the modulus N^precision; returns the lifted T (device matrix; the reference wraps Array(T) in a Nemo residue ring)
@@ -354,7 +371,7 @@ export CuModArray, CuModMatrix, CuModVector, rows, cols, unsafe_Array, eye, zero
        upper_triangular_inverse_no_copy, lower_triangular_inverse_no_copy, forward_sub_gpu_type_32, backward_sub_gpu_type_32,
        apply_col_perm!, apply_col_inv_perm!, apply_row_perm!, apply_row_inv_perm!, perm_array_to_matrix, mod_inv,
        hensel_pseudoinverse, hensel_pseudoinverse!, mul_panels!, mul_host!,
-       KaratsubaArray, KaratsubaMatrix, KaratsubaVector, KaratsubaZeros, MatToKMat, KMatMul!, KMatMul_gemv!, initialize_plan!, scalar_multiply!,
+       KaratsubaArray, KaratsubaMatrix, KaratsubaVector, KaratsubaZeros, MatToKMat, KMatToMat, Karatsubacopy, KMatMul!, KMatMul_gemv!, initialize_plan!, scalar_multiply!,
        CuModArraySizeMismatchException, CuModArrayModulusMismatchException, CuModMatrixTooLargeException, CuModMatrixNotSquareException,
        CuModMatrixModulusNotPrimeException, InverseOverflowError, InverseNotDefinedException, MatrixNotInvertibleException
 

@@ -33,17 +33,100 @@ class KaratsubaMatrix:
     def shape(self):
         return self.data1.shape
 
+    def size(self):
+        """`Base.size(A)` (KaratsubaMatrix.jl:302)."""
+        return self.data1.size()
+
+    def __getitem__(self, idx):
+        """`getindex` (KaratsubaMatrix.jl:304-305): data1[i,j] + N1*data2[i,j] (0-based here)."""
+        return int(self.data1[idx]) + self.N1 * int(self.data2[idx])
+
+    def __setitem__(self, idx, v):
+        """`setindex!` (KaratsubaMatrix.jl:307-316): data1 = rem(v, N1), data2 = div(v, N1)."""
+        v = int(v)
+        self.data1[idx] = v % self.N1
+        self.data2[idx] = v // self.N1
+
+    # operators (KaratsubaMatrix.jl:428-503)
+    def _like(self, rows=None, cols=None):
+        from .cumodmatrix import zeros
+        r = self.data1.rows if rows is None else rows
+        c = self.data1.cols if cols is None else cols
+        T, ctx = self.data1.elem_type, self.data1.ctx
+        return KaratsubaMatrix(zeros(T, r, c, self.N1, ctx=ctx), zeros(T, r, c, self.N1, ctx=ctx), self.N1, self.N2, self.M)
+
+    def __add__(self, o):
+        return add_(self._like(), self, o)
+
+    def __sub__(self, o):
+        return sub_(self._like(), self, o)
+
+    def __neg__(self):
+        return negate_(self._like(), self)
+
+    def __mul__(self, o):
+        if isinstance(o, KaratsubaMatrix):  # `*(A,B)`: Karatsuba product (left unfinished in the reference, :467-503)
+            return KMatMul_(self._like(cols=o.data1.cols), self, o)
+        return scalar_multiply_(self._like(), self, o)
+
+    __rmul__ = __mul__
+    __matmul__ = __mul__
+
     def Array(self):
         """`Array(K)` = data1 + N1*data2 (KaratsubaMatrix.jl:318-336) as python ints (exact up to 2^52)."""
         return self.data1.Array(np.int64).astype(object) + self.N1 * self.data2.Array(np.int64).astype(object)
 
 
 KaratsubaVector = KaratsubaMatrix
-MatToKMat = KaratsubaMatrix.from_array
+KaratsubaArray = KaratsubaMatrix
 
 
-def KaratsubaZeros(T, rows, cols, N1, N2, M=None, ctx=None):
-    """KaratsubaMatrix.jl:404-420."""
+def MatToKMat(A, N1=None, N2=None, M=None, elem_type=np.float64, ctx=None):
+    """`MatToKMat` (KaratsubaMatrix.jl:358-401): with one modulus M the limbs are both taken modulo M
+    (`KaratsubaMatrix(T, A, M, M, M)`, :367-370); with N1, N2 it is the split constructor (:372-397)."""
+    if N1 is None:
+        raise TypeError("MatToKMat needs a modulus (the reference's modulus-free form derives one from find_max_ops)")
+    if N2 is None:
+        N2 = N1
+    return KaratsubaMatrix.from_array(A, N1, N2, M, elem_type=elem_type, ctx=ctx)
+
+
+def KMatToMat(K: "KaratsubaMatrix"):
+    """`KMatToMat` (KaratsubaMatrix.jl:352-356): data1 + N1*data2 on the host (exact integers)."""
+    return K.Array()
+
+
+def copy_(B: "KaratsubaMatrix", A: "KaratsubaMatrix"):
+    """`Base.copy!(B, A)` (KaratsubaMatrix.jl:338-345)."""
+    from .cumodmatrix import copy_ as _mcopy
+    _mcopy(B.data1, A.data1)
+    _mcopy(B.data2, A.data2)
+    if A.plan is not None and B.plan is None:
+        initialize_plan_(B)
+    return B
+
+
+def zero_(A: "KaratsubaMatrix"):
+    """`zero!` (KaratsubaMatrix.jl:347-350)."""
+    from .cumodmatrix import zero_ as _mzero
+    _mzero(A.data1)
+    _mzero(A.data2)
+    return A
+
+
+def Karatsubacopy(A: "KaratsubaMatrix"):
+    """`Karatsubacopy` (KaratsubaMatrix.jl:738-744)."""
+    from .cumodmatrix import copy as _mcopy
+    B = KaratsubaMatrix(_mcopy(A.data1), _mcopy(A.data2), A.N1, A.N2, A.N1 * A.N2)
+    if A.plan is not None:
+        initialize_plan_(B)
+    return B
+
+
+def KaratsubaZeros(T, rows, cols, N1, N2, M=None, use_gpu=True, ctx=None):
+    """KaratsubaMatrix.jl:404-420 (`use_gpu` is accepted for signature parity; there is no CPU variant here)."""
+    if not use_gpu:
+        raise ValueError("KaratsubaZeros(use_gpu=false): this build has no CPU path")
     from .cumodmatrix import zeros
     return KaratsubaMatrix(zeros(T, rows, cols, N1, ctx=ctx), zeros(T, rows, cols, N1, ctx=ctx), N1, N2, M)
 

@@ -589,3 +589,33 @@ def test_hensel_pseudoinverse_karatsuba(g):
     want = O.hensel_pseudoinverse(p, 8, A, T0h) % M
     assert np.array_equal(TK.Array(), want)
     assert np.array_equal(np.array(A, dtype=object).dot(TK.Array()) % M, np.eye(n, dtype=object))
+
+
+def test_karatsuba_array_interface(g):
+    """The rest of the KaratsubaArray surface (KaratsubaMatrix.jl:302-316, :338-356, :428-503, :738-744): indexing, copy!, zero!,
+    operators, Karatsubacopy, MatToKMat with a single modulus -- against python integers."""
+    N1, N2 = 13 ** 4, 13 ** 3
+    M = N1 * N2
+    rng = np.random.default_rng(8)
+    A = rng.integers(0, M, size=(40, 30)); B = rng.integers(0, M, size=(40, 30)); Cm = rng.integers(0, M, size=(30, 20))
+    AK = g.MatToKMat(A, N1, N2); BK = g.MatToKMat(B, N1, N2); CK = g.MatToKMat(Cm, N1, N2)
+    Ao, Bo, Co = A.astype(object), B.astype(object), Cm.astype(object)
+    assert AK.size() == (40, 30)
+    assert AK[3, 4] == int(A[3, 4])
+    AK[3, 4] = 123456789; Ao[3, 4] = 123456789
+    assert AK[3, 4] == 123456789 and int(AK.data1[3, 4]) == 123456789 % N1 and int(AK.data2[3, 4]) == 123456789 // N1
+    assert np.array_equal((AK + BK).Array(), (Ao + Bo) % M)
+    assert np.array_equal((AK - BK).Array(), (Ao - Bo) % M)
+    assert np.array_equal((5 * AK).Array(), (5 * Ao) % M)
+    assert np.array_equal((-AK).Array(), (-Ao) % M)
+    assert np.array_equal((AK * CK).Array(), Ao.dot(Co) % M)
+    assert np.array_equal(g.KMatToMat(AK), Ao)
+    D = g.Karatsubacopy(AK)
+    g.karatsuba.zero_(AK)
+    assert not AK.Array().any() and np.array_equal(D.Array(), Ao)
+    g.karatsuba.copy_(AK, D)
+    assert np.array_equal(AK.Array(), Ao)
+    K1 = g.MatToKMat(A % 8191, 8191)                       # single modulus: N1 = N2 = M (KaratsubaMatrix.jl:367-370)
+    assert (K1.N1, K1.N2) == (8191, 8191) and np.array_equal(K1.Array(), (A % 8191).astype(object))
+    with pytest.raises(ValueError):
+        g.KaratsubaZeros(np.float64, 2, 2, N1, N2, use_gpu=False)
