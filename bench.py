@@ -155,6 +155,8 @@ def main():
                     "the fastest is picked during the untimed warm-up")
     ap.add_argument("--gemm-ctas", default="0,140,132", help="cap on the persistent GEMM grid (0 = all SMs) so that the concurrent NCCL "
                     "kernels find free SMs (N > 1); several values: the fastest is picked during the untimed warm-up")
+    ap.add_argument("--grid-cols", type=int, default=1, help="N > 1: column groups of a 2-D process grid (1 = row blocks of A with a full "
+                    "broadcast of B; pc > 1: rank (i, j) multiplies row block i of A with column range j of B and receives only that range)")
     ap.add_argument("--bcast", default="broadcast", choices=["broadcast", "scatter_allgather"],
                     help="how B is replicated every step (N > 1): ncclBroadcast per panel, or scatter + in-place all-gather per panel")
     ap.add_argument("--no-cpu", action="store_true")
@@ -196,8 +198,13 @@ def main():
 
     with torch.cuda.stream(stream):
         # ---- resident inputs: A row block of this rank, B (broadcast from rank 0 each step when world > 1) -----------
-        r0, r1 = g.multigpu.row_block(n, world, rank)
+        mg = g.multigpu
+        pr, pc = mg.process_grid(world, args.grid_cols if world > 1 else 1)
+        gi, gj = mg.grid_coords(rank, pr, pc)
+        r0, r1 = mg.row_block(n, pr, gi)
         mloc = r1 - r0
+        cl0, cl1 = mg.col_range(n, pc, gj, align=mg.PANEL_ALIGN)
+        ncl = cl1 - cl0  # columns of B / C this rank works on (all of them unless --grid-cols > 1)
         if world == 1:
             A = g.synth(n, n, N, SEED_A, ctx=ctx)
         else:
@@ -208,13 +215,15 @@ def main():
             del Afull
         ldb = ((n + 31) // 32) * 32
         Bt = torch.zeros((n, ldb), dtype=torch.int32, device=f"cuda:{local}")  # column-major n x n, leading dim ldb
-        B = g.CuModMatrix.wrap_device(Bt.data_ptr(), n, n, ldb, N, ctx=ctx)
+        Ball = g.CuModMatrix.wrap_device(Bt.data_ptr(), n, n, ldb, N, ctx=ctx)
+        B = Ball if pc == 1 else g.CuModMatrix.wrap_device(Bt.data_ptr() + 4 * cl0 * ldb, n, ncl, ldb, N, ctx=ctx)  # this rank's column range
         if rank == 0:
             Bs = g.synth(n, n, N, SEED_B, ctx=ctx)
-            g.copy_(B, Bs)
+            g.copy_(Ball, Bs)
             ctx.sync()
             del Bs
-        C = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+        C = g.zeros(np.float32, mloc, ncl, N, ctx=ctx)
+        col_groups = mg.make_column_groups(dist, world, pc, src=0) if pc > 1 else None
         # N > 1: NCCL broadcast of B in column panels on a communication stream; ONE gffm_gemm_panels call per step consumes them
         # (split of panel p+1 / CRT of panel p under the GEMM of panel p; the next step's broadcast runs under this step's GEMMs)
         pan_cands = [int(x) for x in str(args.panels).split(",")] if world > 1 else [1]
@@ -222,8 +231,11 @@ def main():
         bm = None
 
         def make_bm(npanels):
-            pans = g.multigpu.col_panels(n, npanels, align=g.multigpu.PANEL_ALIGN)
-            return pans, (g.multigpu.BroadcastMatmul(torch, dist, C, A, B, Bt, pans, src=0, collective=args.bcast) if world > 1 else None)
+            pans = mg.col_panels(ncl, npanels, align=mg.PANEL_ALIGN)  # relative to this rank's column range
+            if world == 1:
+                return pans, None
+            deliver = mg.grid_deliver(dist, Bt, col_groups, rank, pc, n, src=0, align=mg.PANEL_ALIGN) if pc > 1 else None
+            return pans, mg.BroadcastMatmul(torch, dist, C, A, B, Bt, pans, src=0, collective=args.bcast, deliver=deliver)
 
         def step():
             A.touch()  # every step is a FRESH product: the cached 8-bit planes of A are rebuilt (B is external memory, never cached)
@@ -291,14 +303,21 @@ def main():
         value = 2.0 * n ** 3 / (ms * 1e-3) / 1e9
         shard_ok = None
         if world > 1:  # every rank: the pipelined, broadcast-fed shard == the plain product of its row block with the B it received
-            Cref = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+            Cref = g.zeros(np.float32, mloc, ncl, N, ctx=ctx)
             g.mul_(Cref, A, B)
-            ok = torch.tensor([1 if C.equals(Cref) else 0], dtype=torch.int32, device=f"cuda:{local}")
+            same_c = C.equals(Cref)
+            # ... and the B it received is the source's: rank 0 publishes the checksum of every column range
+            src_sums = torch.zeros(pc, dtype=torch.int64, device=f"cuda:{local}")
+            if rank == 0:
+                for j in range(pc):
+                    a, b = mg.col_range(n, pc, j, align=mg.PANEL_ALIGN)
+                    Bj = Ball if pc == 1 else g.CuModMatrix.wrap_device(Bt.data_ptr() + 4 * a * ldb, n, b - a, ldb, N, ctx=ctx)
+                    src_sums[j] = Bj.checksum() & 0x7FFFFFFFFFFFFFFF
+            dist.broadcast(src_sums, src=0)
+            same_b = int(src_sums[gj].item()) == (B.checksum() & 0x7FFFFFFFFFFFFFFF)
+            ok = torch.tensor([1 if (same_c and same_b) else 0], dtype=torch.int32, device=f"cuda:{local}")
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            bsum = torch.tensor([B.checksum() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=f"cuda:{local}")
-            bmin = bsum.clone(); bmax = bsum.clone()
-            dist.all_reduce(bmin, op=dist.ReduceOp.MIN); dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
-            shard_ok = bool(ok.item() == 1 and bmin.item() == bmax.item())   # and every rank holds the same B
+            shard_ok = bool(ok.item() == 1)
             del Cref
 
         # ---- roofline of the dominant kernel (tcgen05 GEMM): a few more profiled steps, kernel-only durations --------
@@ -325,7 +344,7 @@ def main():
             prod, units = 1, 0
             while prod <= need:
                 prod *= mods[units]; units += 1
-        cols_per_launch = n if world == 1 else pan
+        cols_per_launch = ncl if world == 1 else pan
         int8_ops = units * 2.0 * mloc * cols_per_launch * n
         gemm_avg = statistics.mean(gemm_ms[1:] if len(gemm_ms) > 1 and world > 1 else gemm_ms) if gemm_ms else None
         achieved = int8_ops / (gemm_avg * 1e-3) / 1e12 if gemm_avg else None
@@ -364,11 +383,11 @@ def main():
         e2e = None
         if not args.no_e2e:
             hA = torch.empty((n, mloc), dtype=torch.int32).pin_memory()   # column-major mloc x n
-            hB = torch.empty((n, n), dtype=torch.int32).pin_memory()
-            hC = torch.empty((n, mloc), dtype=torch.int32).pin_memory()
+            hB = torch.empty((ncl, n), dtype=torch.int32).pin_memory()   # column-major n x ncl
+            hC = torch.empty((ncl, mloc), dtype=torch.int32).pin_memory()
             g.capi.check(A.lib.gffm_mat_download(A.h, hA.data_ptr(), g.capi.U32, mloc, 0))
             g.capi.check(B.lib.gffm_mat_download(B.h, hB.data_ptr(), g.capi.U32, n, 0))
-            A2 = g.zeros(np.float32, mloc, n, N, ctx=ctx); B2 = g.zeros(np.float32, n, n, N, ctx=ctx); C2 = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+            A2 = g.zeros(np.float32, mloc, n, N, ctx=ctx); B2 = g.zeros(np.float32, n, ncl, N, ctx=ctx); C2 = g.zeros(np.float32, mloc, ncl, N, ctx=ctx)
 
             def e2e_step():
                 g.capi.check(A2.lib.gffm_mat_upload(A2.h, hA.data_ptr(), g.capi.U32, mloc, 1))
@@ -410,7 +429,7 @@ def main():
             if pipe and pipe["matches"] and pipe["ms_per_step"] < te * 1e3:
                 te = pipe["ms_per_step"] / 1e3
             e2e = {"value": 2.0 * n ** 3 / te / 1e9, "unit": "GOPS", "api": "gffm_gemm_host (pipelined)" if pipe and te * 1e3 == pipe["ms_per_step"] else "upload + mul! + download",
-                   "sequential_api_calls": seq, "pipelined_host_call": pipe, "h2d_bytes_per_step": int(4 * (mloc * n + n * n)), "d2h_bytes_per_step": int(4 * mloc * n),
+                   "sequential_api_calls": seq, "pipelined_host_call": pipe, "h2d_bytes_per_step": int(4 * (mloc * n + n * ncl)), "d2h_bytes_per_step": int(4 * mloc * ncl),
                    "ms_per_step": te * 1e3, "steps": ke, "host_dtype": "uint32 residues (pinned)", "matches_resident_result": same}
             del A2, B2, C2
 
@@ -457,7 +476,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{n}x{n} * {n}x{n} matmul mod {N} ({bits}-bit modulus), A,B resident as uint32 residues", "n": n, "modulus": N,
                        "encoding": "RNS int8 tcgen05" if N > 65536 else "positional int8 limbs tcgen05",
-                       "sharding": "single GPU" if world == 1 else f"row blocks of A over {world} GPUs, B replicated from rank 0 by NCCL ({args.bcast}) every step in {npan} column panels on a communication stream, consumed by gffm_gemm_panels (split/CRT under the GEMM, next step's broadcast under this step's GEMMs)",
+                       "sharding": "single GPU" if world == 1 else f"{pr} row blocks of A x {pc} column range(s) of B over {world} GPUs, B replicated from rank 0 by NCCL ({args.bcast}) every step in {npan} column panels on a communication stream, consumed by gffm_gemm_panels (split/CRT under the GEMM, next step's broadcast under this step's GEMMs)",
                        "shards_match_local_product_on_all_ranks": shard_ok,
                        "gemm_grid_cap": choice[1], "warmup_trials_ms": {f"panels={k[0]},gemm_ctas={k[1]}": round(v, 4) for k, v in tune.items()},
                        "l2_policy": f"inputs larger than L2: A and B are {4 * n * n / 2**20:.0f} MiB each vs 126 MB L2", "checksum_rank0": f"{checksum:016x}",

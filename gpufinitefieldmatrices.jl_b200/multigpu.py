@@ -41,6 +41,57 @@ def col_panels(n: int, npanels: int, align: int = 1) -> List[Tuple[int, int]]:
     return [(c0, min(n, c0 + per)) for c0 in range(0, n, per)]
 
 
+# ---- optional 2-D process grid ------------------------------------------------------------------------------------------
+# Rank r sits at (i, j) = (r // pc, r % pc) of a pr x pc grid: it owns row block i of A and computes the column range j of
+# C = A*B, so it needs only B[:, range j].  Row-block sharding with a full broadcast of B is the pc = 1 case.  With pc > 1 every
+# rank splits 1/pc of B into operand planes instead of all of it (the part of the work that does not shrink with the GPU
+# count) and receives 1/pc of the broadcast bytes; the price is that pc ranks repeat the split of the same A row block.
+def process_grid(world: int, pc: int = 1) -> Tuple[int, int]:
+    """(pr, pc) with pr*pc == world; raises when pc does not divide the world size."""
+    if pc < 1 or world % pc != 0:
+        raise ValueError(f"a grid with {pc} column groups does not tile {world} ranks")
+    return world // pc, pc
+
+
+def grid_coords(rank: int, pr: int, pc: int) -> Tuple[int, int]:
+    return rank // pc, rank % pc
+
+
+def col_range(n: int, pc: int, j: int, align: int = 1) -> Tuple[int, int]:
+    """Columns [c0, c1) of B / C handled by column group j (equal aligned widths; trailing groups may be narrower or empty)."""
+    per = (n + pc - 1) // pc
+    per = ((per + align - 1) // align) * align
+    c0 = min(n, j * per)
+    return c0, min(n, c0 + per)
+
+
+def make_column_groups(dist, world: int, pc: int, src: int = 0):
+    """One communicator per column group j: the ranks of that group plus the source of B.  Collective: every rank must call
+    it, and all ranks create the groups in the same order.  Returns the list of (group, ranks)."""
+    pr, pc = process_grid(world, pc)
+    out = []
+    for j in range(pc):
+        ranks = sorted(set([src] + [i * pc + j for i in range(pr)]))
+        out.append((dist.new_group(ranks=ranks), ranks))
+    return out
+
+
+def grid_deliver(dist, b_colmajor, groups, rank: int, pc: int, n: int, src: int = 0, align: int = 1):
+    """deliver(c0, c1) for `BroadcastMatmul` on a pr x pc grid; [c0, c1) is relative to the column range of the calling rank.
+    The source takes part in the broadcast of every column group (it holds all of B); every other rank only in its own."""
+    my_j = rank % pc
+
+    def deliver(c0, c1):
+        for j in (range(pc) if rank == src else [my_j]):
+            base, end = col_range(n, pc, j, align)
+            lo, hi = min(end, base + c0), min(end, base + c1)
+            group, ranks = groups[j]
+            if hi > lo and len(ranks) > 1:
+                dist.broadcast(b_colmajor[lo:hi], src=src, group=group)
+
+    return deliver
+
+
 def pipelined_broadcast_matmul(dist, b_colmajor, panels, gemm_panel: Callable[[int, int], None], src: int = 0):
     """One sharded product step, compute injected.
 

@@ -68,6 +68,58 @@ def test_broadcast_scatter_allgather(tmp_path, world, rows):
         assert np.array_equal(np.load(tmp_path / f"b_{r}.npy"), want), f"rank {r}"
 
 
+def _worker_grid(rank, world, port, pc, m, k, n, N, npan, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import gffm_b200 as g
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mg = g.multigpu
+    pr, pc = mg.process_grid(world, pc)
+    i, j = mg.grid_coords(rank, pr, pc)
+    r0, r1 = mg.row_block(m, pr, i)
+    c0, c1 = mg.col_range(n, pc, j)
+    A_shard = O.synth_matrix(11, m, k, N)[r0:r1]
+    ld = ((k + 31) // 32) * 32
+    Bt = torch.zeros((n, ld), dtype=torch.int32)
+    if rank == 0:
+        Bt[:, :k] = torch.from_numpy(O.synth_matrix(12, k, n, N).T.astype(np.int32).copy())
+    groups = mg.make_column_groups(dist, world, pc, src=0)
+    deliver = mg.grid_deliver(dist, Bt, groups, rank, pc, n, src=0)
+    C_shard = np.zeros((r1 - r0, c1 - c0), dtype=np.int64)
+    width = max(c1 - c0 for (c0, c1) in [mg.col_range(n, pc, jj) for jj in range(pc)])
+    for (p0, p1) in mg.col_panels(width, npan):          # panel offsets are relative to the column range
+        deliver(p0, p1)
+        lo, hi = min(c1, c0 + p0), min(c1, c0 + p1)
+        if hi > lo:
+            Bp = Bt[lo:hi, :k].numpy().T.astype(np.int64)
+            C_shard[:, lo - c0:hi - c0] = O.matmul_mod(A_shard, Bp, N)
+    np.save(os.path.join(out_dir, f"c_{rank}.npy"), C_shard)
+    if rank != 0:  # ranks never receive columns outside their range
+        other = torch.cat([Bt[:c0], Bt[c1:]])
+        assert not other.any()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,pc,m,k,n,N,npan", [(4, 2, 70, 50, 90, 33554393, 3), (4, 4, 9, 20, 30, 11, 2), (2, 2, 33, 17, 5, 65521, 2), (3, 1, 20, 10, 12, 7, 2)])
+def test_grid_sharded_matmul(tmp_path, world, pc, m, k, n, N, npan):
+    """pr x pc process grid: row block i of A times column range j of B on rank (i, j); B travels only to the ranks that need it."""
+    import gffm_b200 as g
+    mg = g.multigpu
+    port = _free_port()
+    mp.spawn(_worker_grid, args=(world, port, pc, m, k, n, N, npan, str(tmp_path)), nprocs=world, join=True)
+    pr, pc = mg.process_grid(world, pc)
+    A = O.synth_matrix(11, m, k, N); B = O.synth_matrix(12, k, n, N)
+    want = O.matmul_mod(A, B, N)
+    for r in range(world):
+        i, j = mg.grid_coords(r, pr, pc)
+        r0, r1 = mg.row_block(m, pr, i); c0, c1 = mg.col_range(n, pc, j)
+        assert np.array_equal(np.load(tmp_path / f"c_{r}.npy"), want[r0:r1, c0:c1]), f"rank {r}"
+    with pytest.raises(ValueError):
+        mg.process_grid(8, 3)
+
+
 @pytest.mark.parametrize("m,k,n,N,npan", [(70, 50, 90, 33554393, 4), (5, 9, 3, 11, 8)])
 def test_sharded_matmul_world2(tmp_path, m, k, n, N, npan):
     world = 2
