@@ -132,7 +132,8 @@ def run_reference(args):
         "impl": "reference", "metric": "mod-p matmul effective GOPS (2n^3/s)", "value": value, "unit": "GOPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 2.0 * args.n ** 3 / (value * 1e9) * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64 accumulate of u32 residues (host integers)", "data": "synthetic",
-        "config": {"workload": f"{args.n}x{args.n} * {args.n}x{args.n} matmul mod {args.modulus}", "n": args.n, "modulus": args.modulus,
+        "config": {"workload": f"{args.n}x{args.n} * {args.n}x{args.n} matmul mod {args.modulus} ({(args.modulus - 1).bit_length()}-bit modulus), A,B resident as uint32 residues",
+                   "n": args.n, "modulus": args.modulus,
                    "note": "the Julia reference cannot run in this image; this arm is the reference tests' CPU ground truth mod.(A*B,N) restated in C "
                            "(oracle/oracle_c.c) on all host cores; ms_per_step is the n^3-extrapolated time of the full workload"},
         "cpu_baseline": {"value": value, "unit": "GOPS", "cores": cores, "kind": "port", "sample": desc},
