@@ -99,6 +99,7 @@ static void ws_free(gffm_workspace* ws) {
 }
 
 extern "C" int32_t gffm_destroy(gffm_ctx* ctx) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx) return GFFM_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -124,12 +125,14 @@ extern "C" int32_t gffm_destroy(gffm_ctx* ctx) {
 }
 
 extern "C" int32_t gffm_sync(gffm_ctx* ctx) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx) GFFM_FAIL(GFFM_ERR_INVALID, "null ctx");
   GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return GFFM_OK;
 }
 
 extern "C" int32_t gffm_set_stream(gffm_ctx* ctx, void* s) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx) GFFM_FAIL(GFFM_ERR_INVALID, "null ctx");
   GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -138,17 +141,20 @@ extern "C" int32_t gffm_set_stream(gffm_ctx* ctx, void* s) {
   return GFFM_OK;
 }
 extern "C" int32_t gffm_get_stream(gffm_ctx* ctx, void** s) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx || !s) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   *s = (void*)ctx->stream;
   return GFFM_OK;
 }
 extern "C" int32_t gffm_set_profiling(gffm_ctx* ctx, int32_t on) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx) GFFM_FAIL(GFFM_ERR_INVALID, "null ctx");
   ctx->profile = on != 0;
   ctx->n_ev = 0;
   return GFFM_OK;
 }
 extern "C" int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t cap, int32_t* n) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx) GFFM_FAIL(GFFM_ERR_INVALID, "null ctx");
   ctx->timings.clear();
   if (ctx->n_ev == 0 && !ctx->elim_timings.empty()) {
@@ -180,11 +186,13 @@ extern "C" int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t cap, int
   return GFFM_OK;
 }
 extern "C" int32_t gffm_set_gemm_ctas(gffm_ctx* ctx, int32_t ctas) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx || ctas < 0) GFFM_FAIL(GFFM_ERR_INVALID, "bad argument");
   ctx->gemm_ctas = ctas;
   return GFFM_OK;
 }
 extern "C" int32_t gffm_launch_count(gffm_ctx* ctx, int64_t* count) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx || !count) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   *count = ctx->launches;
   return GFFM_OK;
@@ -232,6 +240,7 @@ int32_t gffm_pinned_reserve(gffm_ctx* ctx, size_t bytes) {
 // container
 // ---------------------------------------------------------------------------------------------
 extern "C" int32_t gffm_mat_create(gffm_ctx* ctx, int64_t rows, int64_t cols, uint64_t N, int32_t pad, gffm_mat** out) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx || !out) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (rows < 0 || cols < 0) GFFM_FAIL(GFFM_ERR_INVALID, "negative size");
   if (N > (1ull << 52)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "Modulus is bigger than 2^52");  // CuModMatrix.jl:55-59
@@ -260,6 +269,7 @@ extern "C" int32_t gffm_mat_create(gffm_ctx* ctx, int64_t rows, int64_t cols, ui
 }
 
 extern "C" int32_t gffm_mat_wrap(gffm_ctx* ctx, void* dptr, int64_t rows, int64_t cols, int64_t ld, uint64_t N, gffm_mat** out) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx || !out || !dptr) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (ld < rows) GFFM_FAIL(GFFM_ERR_INVALID, "ld < rows");
   if (N == 0 || N > (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "modulus out of range for uint32 storage");
@@ -285,12 +295,14 @@ static void free_plane_caches(gffm_mat* m) {
 }
 
 extern "C" int32_t gffm_mat_touch(gffm_mat* m) {
+  GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   gffm_touch(m);
   return GFFM_OK;
 }
 
 extern "C" int32_t gffm_mat_drop_cache(gffm_mat* m) {
+  GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   cudaSetDevice(m->ctx->device);
   free_plane_caches(m);
@@ -298,6 +310,7 @@ extern "C" int32_t gffm_mat_drop_cache(gffm_mat* m) {
 }
 
 extern "C" int32_t gffm_mat_destroy(gffm_mat* m) {
+  GFFM_ENTER_MAT(m);
   if (!m) return GFFM_OK;
   // stream-ordered release: the blocks return to the pool after the work already queued on the context's stream (every
   // helper stream of the library is joined to it before an API call returns); safe from a finalizer thread
@@ -385,6 +398,7 @@ static size_t dtype_size(int dt) {
   }
 
 extern "C" int32_t gffm_mat_upload(gffm_mat* m, const void* host, int32_t dtype, int64_t ld, int32_t do_mod) {
+  GFFM_ENTER_MAT(m);
   if (!m || (!host && m->rows * m->cols > 0)) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   const size_t es = dtype_size(dtype);
   if (!es) GFFM_FAIL(GFFM_ERR_INVALID, "bad dtype %d", dtype);
@@ -435,6 +449,7 @@ extern "C" int32_t gffm_mat_upload(gffm_mat* m, const void* host, int32_t dtype,
 }
 
 extern "C" int32_t gffm_mat_download(gffm_mat* m, void* host, int32_t dtype, int64_t ld, int32_t with_padding) {
+  GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   const size_t es = dtype_size(dtype);
   if (!es) GFFM_FAIL(GFFM_ERR_INVALID, "bad dtype %d", dtype);
@@ -539,6 +554,7 @@ int32_t gffm_ew_views(gffm_ctx* ctx, int op, MatView C, MatView A, const MatView
 }
 
 extern "C" int32_t gffm_ewise(int32_t op, gffm_mat* C, gffm_mat* A, gffm_mat* B, int64_t scalar, uint64_t mod_override) {
+  GFFM_ENTER_MAT(C);
   if (!C || !A) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (op < GFFM_EW_MOD || op > GFFM_EW_SDIV) GFFM_FAIL(GFFM_ERR_INVALID, "bad op");
   gffm_touch(C);
@@ -610,12 +626,14 @@ int32_t gffm_fill_view(gffm_ctx* ctx, MatView dst, uint32_t value) {
 }
 
 extern "C" int32_t gffm_mat_copy(gffm_mat* dst, gffm_mat* src) {
+  GFFM_ENTER_MAT(dst);
   if (!dst || !src) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (dst->rows != src->rows || dst->cols != src->cols) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "copy!: sizes differ");
   gffm_touch(dst);
   return gffm_copy_views(dst->ctx, view_of(dst), view_of(src));
 }
 extern "C" int32_t gffm_mat_copy_block(gffm_mat* dst, int64_t dr0, int64_t dc0, gffm_mat* src, int64_t sr0, int64_t sc0, int64_t nr, int64_t nc) {
+  GFFM_ENTER_MAT(dst);
   if (!dst || !src) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (dr0 < 0 || dc0 < 0 || sr0 < 0 || sc0 < 0 || nr < 0 || nc < 0 || dr0 + nr > dst->rows || dc0 + nc > dst->cols ||
       sr0 + nr > src->rows || sc0 + nc > src->cols)
@@ -624,12 +642,14 @@ extern "C" int32_t gffm_mat_copy_block(gffm_mat* dst, int64_t dr0, int64_t dc0, 
   return gffm_copy_views(dst->ctx, sub_view(view_of(dst), dr0, dc0, nr, nc), sub_view(view_of(src), sr0, sc0, nr, nc));
 }
 extern "C" int32_t gffm_mat_fill(gffm_mat* m, int64_t value) {
+  GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   gffm_touch(m);
   return gffm_fill_view(m->ctx, view_of(m), scalar_residue(value, m->N));
 }
 extern "C" int32_t gffm_mat_zero(gffm_mat* m) { return gffm_mat_fill(m, 0); }
 extern "C" int32_t gffm_mat_eye(gffm_mat* m) {
+  GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (m->rows * m->cols == 0) return GFFM_OK;
   gffm_touch(m);
@@ -638,6 +658,7 @@ extern "C" int32_t gffm_mat_eye(gffm_mat* m) {
   return GFFM_OK;
 }
 extern "C" int32_t gffm_mat_synth(gffm_mat* m, uint64_t seed) {
+  GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (m->rows * m->cols == 0) return GFFM_OK;
   gffm_touch(m);
@@ -648,6 +669,7 @@ extern "C" int32_t gffm_mat_synth(gffm_mat* m, uint64_t seed) {
 extern "C" int32_t gffm_mat_rand(gffm_mat* m, uint64_t seed) { return gffm_mat_synth(m, splitmix64(seed ^ 0x5DEECE66Dull)); }
 
 extern "C" int32_t gffm_mat_set_modulus(gffm_mat* m, uint64_t N, int32_t reduce) {
+  GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (N == 0) GFFM_FAIL(GFFM_ERR_INVALID, "modulus must be positive");
   if (N > (1ull << 52)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "Modulus is bigger than 2^52");
@@ -659,6 +681,7 @@ extern "C" int32_t gffm_mat_set_modulus(gffm_mat* m, uint64_t N, int32_t reduce)
 }
 
 extern "C" int32_t gffm_mat_get_elem(gffm_mat* m, int64_t i, int64_t j, int64_t* value) {
+  GFFM_ENTER_MAT(m);
   if (!m || !value) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (i < 0 || j < 0 || i >= m->rows || j >= m->cols) GFFM_FAIL(GFFM_ERR_INVALID, "BoundsError");
   uint32_t v = 0;
@@ -668,12 +691,14 @@ extern "C" int32_t gffm_mat_get_elem(gffm_mat* m, int64_t i, int64_t j, int64_t*
   return GFFM_OK;
 }
 extern "C" int32_t gffm_mat_set_elem(gffm_mat* m, int64_t i, int64_t j, int64_t value) {
+  GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (i < 0 || j < 0 || i >= m->rows || j >= m->cols) GFFM_FAIL(GFFM_ERR_INVALID, "BoundsError");
   gffm_touch(m);
   return gffm_fill_view(m->ctx, sub_view(view_of(m), i, j, 1, 1), scalar_residue(value, m->N));
 }
 extern "C" int32_t gffm_mat_transpose(gffm_mat* dst, gffm_mat* src) {
+  GFFM_ENTER_MAT(dst);
   if (!dst || !src) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (dst->rows != src->cols || dst->cols != src->rows) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "transpose: sizes differ");
   if (src->rows * src->cols == 0) return GFFM_OK;
@@ -719,6 +744,7 @@ static int32_t checksum_impl(gffm_mat* a, gffm_mat* b, unsigned long long out[2]
   return GFFM_OK;
 }
 extern "C" int32_t gffm_mat_equal(gffm_mat* a, gffm_mat* b, int32_t* equal) {
+  GFFM_ENTER_MAT(a);
   if (!a || !b || !equal) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (a->rows != b->rows || a->cols != b->cols) {
     *equal = 0;
@@ -730,6 +756,7 @@ extern "C" int32_t gffm_mat_equal(gffm_mat* a, gffm_mat* b, int32_t* equal) {
   return GFFM_OK;
 }
 extern "C" int32_t gffm_mat_checksum(gffm_mat* a, uint64_t* sum) {
+  GFFM_ENTER_MAT(a);
   if (!a || !sum) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   unsigned long long out[2];
   GFFM_TRY(checksum_impl(a, nullptr, out));
@@ -844,6 +871,7 @@ gemv_kernel(uint32_t* __restrict__ z, const uint32_t* __restrict__ A, int64_t ld
 }
 
 extern "C" int32_t gffm_gemv(gffm_mat* z, gffm_mat* A, gffm_mat* x, uint64_t R, uint64_t P) {
+  GFFM_ENTER_MAT(z);
   if (!z || !A || !x) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (x->cols != 1 || z->cols != 1 || A->cols != x->rows || A->rows != z->rows)
     GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "gemv: A is %lldx%lld, x has %lld rows, z has %lld rows", (long long)A->rows, (long long)A->cols,
@@ -900,6 +928,7 @@ int32_t gffm_gemm_views(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t
 extern "C" int32_t gffm_gemm_block(gffm_mat* C, int64_t cr0, int64_t cc0, gffm_mat* A, int64_t ar0, int64_t ac0, gffm_mat* B,
                                    int64_t br0, int64_t bc0, int64_t m, int64_t n, int64_t k, uint64_t R, uint64_t P, int32_t mode,
                                    int32_t algo) {
+  GFFM_ENTER_MAT(C);
   if (!C || !A || !B) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (cr0 < 0 || cc0 < 0 || ar0 < 0 || ac0 < 0 || br0 < 0 || bc0 < 0 || m < 0 || n < 0 || k < 0 || cr0 + m > C->rows ||
       cc0 + n > C->cols || ar0 + m > A->rows || ac0 + k > A->cols || br0 + k > B->rows || bc0 + n > B->cols)
@@ -917,6 +946,7 @@ extern "C" int32_t gffm_gemm_block(gffm_mat* C, int64_t cr0, int64_t cc0, gffm_m
 }
 
 extern "C" int32_t gffm_gemm(gffm_mat* C, gffm_mat* A, gffm_mat* B, uint64_t R, uint64_t P, int32_t mode, int32_t algo) {
+  GFFM_ENTER_MAT(C);
   if (!C || !A || !B) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   // reference check order: modulus first, then sizes (CuModMatrix.jl:769-783)
   if (!P && (A->N != B->N || A->N != C->N)) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "gemm operands have different moduli");

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/gffm.h"
@@ -40,6 +41,27 @@ void gffm_set_error(const char* fmt, ...);
 struct gffm_workspace {
   void* ptr = nullptr;
   size_t bytes = 0;
+};
+
+// Every ABI entry makes its context's device current first: a process may drive several GPUs (one context each) and the
+// calling thread's current device is whatever the host runtime left there.
+#define GFFM_ENTER_CTX(c) do { if (c) cudaSetDevice((c)->device); } while (0)
+#define GFFM_ENTER_MAT(m) do { if ((m) && (m)->ctx) cudaSetDevice((m)->ctx->device); } while (0)
+
+// Kernel attributes (max dynamic shared memory, non-portable cluster size) are per DEVICE in the CUDA runtime: a process that
+// drives several GPUs must set them once on each.  run(device, f) calls f the first time it sees a device ordinal.
+struct PerDeviceOnce {
+  std::mutex mu;
+  unsigned long long done = 0;
+  template <class F>
+  void run(int device, F&& f) {
+    const unsigned long long bit = 1ull << (device & 63);
+    std::lock_guard<std::mutex> g(mu);
+    if (!(done & bit)) {
+      f();
+      done |= bit;
+    }
+  }
 };
 
 struct gffm_ctx {

@@ -1084,11 +1084,8 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   using C = Cfg<S>;
   if (tmB_half && mcast_mode() == 2 && p.num_m_blk >= 2) {
     using C2 = Cfg2<S>;
-    static bool attr_2 = false;
-    if (!attr_2) {
-      GFFM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel_2cta<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
-      attr_2 = true;
-    }
+    static PerDeviceOnce attr_2;
+    attr_2.run(ctx->device, [] { cudaFuncSetAttribute(gemm_tc_kernel_2cta<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES); });
     const int num_mp = (p.num_m_blk + 1) / 2;
     const int total_c = p.batches * num_mp * p.num_n_blk;
     int clusters = ctx->num_sms / 2;
@@ -1101,11 +1098,8 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
     return GFFM_OK;
   }
   if (tmB_half && mcast_mode() == 1 && p.num_m_blk >= 2) {
-    static bool attr_mc = false;
-    if (!attr_mc) {
-      GFFM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel_mc<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-      attr_mc = true;
-    }
+    static PerDeviceOnce attr_mc;
+    attr_mc.run(ctx->device, [] { cudaFuncSetAttribute(gemm_tc_kernel_mc<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
     const int num_mp = (p.num_m_blk + 1) / 2;
     const int total_c = p.batches * num_mp * p.num_n_blk;
     int clusters = ctx->num_sms / 2;
@@ -1118,11 +1112,8 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
     GFFM_LAUNCH_CHECK(ctx);
     return GFFM_OK;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    GFFM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_set;  // a failed attribute call surfaces as a launch error below (GFFM_LAUNCH_CHECK)
+  attr_set.run(ctx->device, [] { cudaFuncSetAttribute(gemm_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
   const int total = p.batches * p.num_m_blk * p.num_n_blk;
   static const int env_ctas = getenv("GFFM_GEMM_CTAS") ? atoi(getenv("GFFM_GEMM_CTAS")) : 0;
   const int max_ctas = ctx->gemm_ctas > 0 ? ctx->gemm_ctas : env_ctas;  // leave SMs to concurrent kernels (NCCL in the multi-GPU layer)
@@ -1977,6 +1968,7 @@ int32_t gffm_gemm_tiled(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t
 
 extern "C" int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, const void* A_host, int64_t lda, const void* B_host,
                                   int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t dtype, uint64_t N) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx || !C_host || !A_host || !B_host) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (m <= 0 || n <= 0 || k <= 0) GFFM_FAIL(GFFM_ERR_INVALID, "empty product");
   if (lda < m || ldb < k || ldc < m) GFFM_FAIL(GFFM_ERR_INVALID, "leading dimension too small");
@@ -2001,6 +1993,7 @@ extern "C" int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, cons
 // consumed[p] lets the caller start the NEXT step's broadcast of panel p while this step is still multiplying.
 extern "C" int32_t gffm_gemm_panels(gffm_mat* C, gffm_mat* A, gffm_mat* B, int32_t npanels, const int64_t* col_off, void* const* ready,
                                     void* const* consumed, uint64_t R, uint64_t P) {
+  GFFM_ENTER_MAT(C);
   if (!C || !A || !B || !col_off) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (C == A || C == B) GFFM_FAIL(GFFM_ERR_INVALID, "gemm_panels: C must not alias an operand");
   if (!P && (A->N != B->N || A->N != C->N)) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "gemm operands have different moduli");

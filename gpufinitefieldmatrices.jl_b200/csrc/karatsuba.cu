@@ -73,6 +73,7 @@ kara_ewise_kernel(int op, uint32_t* __restrict__ C1, uint32_t* __restrict__ C2, 
 
 extern "C" int32_t gffm_kmat_mul(gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_mat* A2, gffm_mat* B1, gffm_mat* B2, uint64_t N1,
                                  uint64_t N2) {
+  GFFM_ENTER_MAT(C1);
   if (!C1 || !C2 || !A1 || !A2 || !B1 || !B2) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (N1 == 0 || N2 == 0 || N1 % N2 != 0) GFFM_FAIL(GFFM_ERR_INVALID, "Karatsuba product requires N2 | N1");
   if (N1 > (1ull << 26) || N1 * N2 > (1ull << 52)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "N1 <= 2^26 and N1*N2 <= 2^52 required");
@@ -111,6 +112,7 @@ extern "C" int32_t gffm_kmat_mul(gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_
 
 extern "C" int32_t gffm_kmat_ewise(int32_t op, gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_mat* A2, gffm_mat* B1, gffm_mat* B2,
                                    int64_t scalar, uint64_t N1, uint64_t N2) {
+  GFFM_ENTER_MAT(C1);
   if (!C1 || !C2 || !A1 || !A2) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (op != GFFM_EW_ADD && op != GFFM_EW_SUB && op != GFFM_EW_SMUL && op != GFFM_EW_RSSUB) GFFM_FAIL(GFFM_ERR_INVALID, "bad Karatsuba op");
   if ((op == GFFM_EW_ADD || op == GFFM_EW_SUB) && (!B1 || !B2)) GFFM_FAIL(GFFM_ERR_INVALID, "binary op needs B");

@@ -1374,7 +1374,10 @@ int32_t launch_panel_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, i
 
 // cluster size of the panel kernel: 16 CTAs (non-portable size, opt-in) when the device can co-schedule them, else 8
 int panel_cluster_size(gffm_ctx* ctx) {
-  static int chosen = 0;
+  static std::mutex mu;
+  static int chosen_dev[64] = {0};  // per device ordinal: the attributes below are per-device state
+  std::lock_guard<std::mutex> guard(mu);
+  int& chosen = chosen_dev[ctx->device & 63];
   if (chosen) return chosen;
   chosen = PANEL_CLUSTER;
   cudaFuncSetAttribute(pluq_panel_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BUDGET);
@@ -1405,7 +1408,6 @@ int panel_cluster_size(gffm_ctx* ctx) {
     chosen = want;
   }
   cudaGetLastError();
-  (void)ctx;
   return chosen;
 }
 
@@ -1436,12 +1438,11 @@ int panel_arith(const ModP& mp) { return mp.P < 65536 ? 3 : (mp.P == 65536 ? 0 :
 
 template <int ARITH, int PW, int RPT>
 int32_t launch_panel_reg_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int cluster, const PluqBufs& b, const ModP& mp) {
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  attr.run(ctx->device, [] {
     cudaFuncSetAttribute(pluq_panel_reg_kernel<ARITH, PW, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();
-    attr = true;
-  }
+  });
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(cluster);
@@ -1463,12 +1464,11 @@ int32_t launch_panel_reg_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int 
 
 template <int PW, bool PROF>
 int32_t launch_panel_ll_t(gffm_ctx* ctx, gffm_mat* W, gffm_mat* L, int j0, int w, int cluster, const PluqBufs& b, const ModP& mp) {
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  attr.run(ctx->device, [] {
     cudaFuncSetAttribute(pluq_panel_ll_kernel<PW, PROF>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();
-    attr = true;
-  }
+  });
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(cluster);
@@ -1887,6 +1887,7 @@ void fill_row_pairs(const Elim& e, int64_t* pairs, int64_t* n_pairs) {
 // ---------------------------------------------------------------------------------------------------
 extern "C" int32_t gffm_lu(gffm_mat* A, gffm_mat** U, gffm_mat** L, int64_t* prow_pairs, int64_t* n_prow, int64_t* pivcols,
                            int64_t* rank) {
+  GFFM_ENTER_MAT(A);
   if (!A || !U || !L) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   Elim e;
   int32_t st = eliminate(A, &e);
@@ -1905,6 +1906,7 @@ extern "C" int32_t gffm_lu(gffm_mat* A, gffm_mat** U, gffm_mat** L, int64_t* pro
 }
 
 extern "C" int32_t gffm_rank(gffm_mat* A, int64_t* rank) {
+  GFFM_ENTER_MAT(A);
   if (!A || !rank) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   Elim e;
   int32_t st = eliminate(A, &e);
@@ -1920,6 +1922,7 @@ int32_t gffm_pluq_quirk(gffm_mat* A, gffm_mat** U, gffm_mat** L, int64_t* prow_p
 
 extern "C" int32_t gffm_pluq(gffm_mat* A, gffm_mat** U, gffm_mat** L, int64_t* prow_pairs, int64_t* n_prow, int64_t* pcol_pairs,
                              int64_t* n_pcol, int64_t* rank, int32_t col_pivot_mode) {
+  GFFM_ENTER_MAT(A);
   if (!A || !U || !L) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (col_pivot_mode == GFFM_PIVOT_REFERENCE_QUIRK) return gffm_pluq_quirk(A, U, L, prow_pairs, n_prow, pcol_pairs, n_pcol, rank);
   gffm_ctx* ctx = A->ctx;
@@ -1993,6 +1996,7 @@ extern "C" int32_t gffm_pluq(gffm_mat* A, gffm_mat** U, gffm_mat** L, int64_t* p
 }
 
 extern "C" int32_t gffm_rref(gffm_mat* A, gffm_mat** R, int64_t* pivcols, int64_t* rank) {
+  GFFM_ENTER_MAT(A);
   if (!A || !R) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   gffm_ctx* ctx = A->ctx;
   Elim e;
@@ -2042,6 +2046,7 @@ extern "C" int32_t gffm_rref(gffm_mat* A, gffm_mat** R, int64_t* pivcols, int64_
 }
 
 extern "C" int32_t gffm_triinv(gffm_mat* A, int32_t upper, gffm_mat** out) {
+  GFFM_ENTER_MAT(A);
   if (!A || !out) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   gffm_ctx* ctx = A->ctx;
   const int64_t rows = A->rows, cols = A->cols;
@@ -2073,6 +2078,7 @@ extern "C" int32_t gffm_triinv(gffm_mat* A, int32_t upper, gffm_mat** out) {
 }
 
 extern "C" int32_t gffm_apply_perm(gffm_mat* A, const int64_t* pairs, int64_t n_pairs, int32_t on_cols, int32_t inverse) {
+  GFFM_ENTER_MAT(A);
   if (!A || (n_pairs > 0 && !pairs)) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (n_pairs <= 0) return GFFM_OK;
   gffm_touch(A);
@@ -2093,6 +2099,7 @@ extern "C" int32_t gffm_apply_perm(gffm_mat* A, const int64_t* pairs, int64_t n_
 }
 
 extern "C" int32_t gffm_modinv_batch(gffm_ctx* ctx, const uint64_t* in_host, uint64_t* out_host, int64_t n, uint64_t N) {
+  GFFM_ENTER_CTX(ctx);
   if (!ctx || (n > 0 && (!in_host || !out_host))) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (N == 0 || N >= (1ull << 62)) GFFM_FAIL(GFFM_ERR_INVALID, "modulus out of range");
   if (n <= 0) return GFFM_OK;
@@ -2109,6 +2116,7 @@ extern "C" int32_t gffm_modinv_batch(gffm_ctx* ctx, const uint64_t* in_host, uin
 
 // inverse(A) = U^-1 * L^-1 * P  (reference CuModMatrix.jl:480-502: apply_col_inv_perm!(P, L_inv); U_inv * L_inv)
 extern "C" int32_t gffm_inverse(gffm_mat* A, gffm_mat** Ainv, int32_t* invertible) {
+  GFFM_ENTER_MAT(A);
   if (!A || !Ainv || !invertible) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   *Ainv = nullptr;
   *invertible = 0;
