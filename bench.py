@@ -170,10 +170,11 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--modulus", type=int, default=MOD_DEFAULT)
-    ap.add_argument("--panels", default="8,4", help="column panels of B for the pipelined NCCL broadcast (N > 1); several values: "
+    ap.add_argument("--panels", default="8", help="column panels of B for the pipelined NCCL broadcast (N > 1); several values: "
                     "the fastest is picked during the untimed warm-up")
-    ap.add_argument("--gemm-ctas", default="0,140,132", help="cap on the persistent GEMM grid (0 = all SMs) so that the concurrent NCCL "
-                    "kernels find free SMs (N > 1); several values: the fastest is picked during the untimed warm-up")
+    ap.add_argument("--gemm-ctas", default="0", help="cap on the persistent GEMM grid (0 = all SMs) so that the concurrent NCCL "
+                    "kernels find free SMs (N > 1); several values: the fastest is picked during the untimed warm-up (measured on 8 B200: "
+                    "148 > 140 > 132 CTAs, profiles/r01_notes.md, hence the default)")
     ap.add_argument("--grid-cols", type=int, default=1, help="N > 1: column groups of a 2-D process grid (1 = row blocks of A with a full "
                     "broadcast of B; pc > 1: rank (i, j) multiplies row block i of A with column range j of B and receives only that range)")
     ap.add_argument("--bcast", default="broadcast", choices=["broadcast", "scatter_allgather"],
