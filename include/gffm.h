@@ -52,7 +52,7 @@ enum {
 /* host element types for upload/download */
 enum { GFFM_F32 = 0, GFFM_F64 = 1, GFFM_I64 = 2, GFFM_U32 = 3, GFFM_I32 = 4 };
 
-/* elementwise ops, gffm_ewise (src/CuModMatrix/kernel_ops/*.jl) */
+/* elementwise ops, gffm_ewise (src/CuModMatrix/kernel_ops/{add,sub,mul,div,mod}_ops.jl) */
 enum {
   GFFM_EW_MOD = 0,        /* C = mod(A, m)            mod_ops.jl:3-27  (mod_elements!) */
   GFFM_EW_ADD = 1,        /* C = mod(A + B, m)        add_ops.jl:23-30 */
@@ -180,7 +180,7 @@ int32_t gffm_gemm_panels(gffm_mat* C, gffm_mat* A, gffm_mat* B, int32_t npanels,
 /* mul!(z,A,x;R,P) (CuModMatrix.jl:816-836, stripe_mul.jl:82-168): z = A*x mod P, x and z are n x 1 matrices */
 int32_t gffm_gemv(gffm_mat* z, gffm_mat* A, gffm_mat* x, uint64_t in_bound_R, uint64_t mod_P);
 
-/* ---- elementwise (kernel_ops/*.jl; mod_N override semantics of inplace_operations_test.jl:125-191) ----- */
+/* ---- elementwise (kernel_ops/{add,sub,mul,div,mod}_ops.jl; mod_N override semantics of inplace_operations_test.jl:125-191) ----- */
 int32_t gffm_ewise(int32_t op, gffm_mat* C, gffm_mat* A, gffm_mat* B_or_null, int64_t scalar, uint64_t mod_override);
 
 /* ---- elimination ------------------------------------------------------------------------------------ */

@@ -60,3 +60,24 @@ def test_julia_shim_binds_every_symbol():
     used = set(re.findall(r":(gffm_[a-z0-9_]+)", txt))
     missing = set(declared_functions()) - used
     assert not missing, f"Julia shim does not ccall: {sorted(missing)}"
+
+
+def test_plain_c_client_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/gffm.h is valid ISO C (no C++ types anywhere in the boundary) and libgffm.so links from gcc; without a GPU the
+    client reports GFFM_ERR_NO_DEVICE from gffm_create (tools/c_client.c)."""
+    import subprocess
+    import gffm_b200 as g
+    exe = str(tmp_path / "c_client")
+    libdir = os.path.dirname(g.capi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tools", "c_client.c"), "-L" + libdir, "-lgffm", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "libgffm" in run.stdout
+    if not torch.cuda.is_available():
+        assert "no CPU fallback" in run.stdout
+    else:
+        assert "C = [" in run.stdout
