@@ -116,6 +116,18 @@ def broadcast_then(dist, tensors, fn: Callable[[], None], src: int = 0):
     fn()
 
 
+def sharded_kmat_mul(dist, b1_colmajor, b2_colmajor, kmat_mul_local: Callable[[], None], src: int = 0):
+    """Karatsuba product on row blocks: A1, A2 (and C1, C2) are sharded by rows like the plain product, both limbs of
+    B are replicated from `src`, the three sub-products and the recombination run locally (`kmat_mul_local` = gffm_kmat_mul on
+    this rank's shard; the `B1 + B2` planes are derived locally inside it)."""
+    broadcast_then(dist, [b1_colmajor, b2_colmajor], kmat_mul_local, src=src)
+
+
+def sharded_gemv(dist, x, gemv_local: Callable[[], None], src: int = 0):
+    """z = A*x mod P on row blocks: x is tiny and broadcast whole, every rank computes its rows of z."""
+    broadcast_then(dist, [x], gemv_local, src=src)
+
+
 def broadcast_scatter_allgather(dist, panel, src: int = 0):
     """Broadcast of one column panel as scatter + all-gather: `src` sends a different 1/G slice of the panel to every
     rank, then the ranks all-gather the slices in place.  Every NVLink port carries 1/G of the panel per peer instead of

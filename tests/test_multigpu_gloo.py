@@ -42,6 +42,50 @@ def _worker(rank, world, port, m, k, n, N, npan, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_kmat_gemv(rank, world, port, m, k, n, N1, N2, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import gffm_b200 as g
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mg = g.multigpu
+    r0, r1 = mg.row_block(m, world, rank)
+    A1 = O.synth_matrix(21, m, k, N1)[r0:r1]; A2 = O.synth_matrix(22, m, k, N2)[r0:r1]
+    B1t = torch.zeros((n, k), dtype=torch.int64); B2t = torch.zeros((n, k), dtype=torch.int64)
+    x = torch.zeros(k, dtype=torch.int64)
+    if rank == 0:
+        B1t.copy_(torch.from_numpy(O.synth_matrix(23, k, n, N1).T.copy())); B2t.copy_(torch.from_numpy(O.synth_matrix(24, k, n, N2).T.copy()))
+        x.copy_(torch.from_numpy(O.synth_matrix(25, k, 1, N1)[:, 0].copy()))
+    res = {}
+
+    def kmul():
+        res["C1"], res["C2"] = O.karatsuba_matmul(A1, A2, B1t.numpy().T, B2t.numpy().T, N1, N2)
+
+    def gemv():
+        res["z"] = O.matvec_mod(A1, x.numpy(), N1)
+
+    mg.sharded_kmat_mul(dist, B1t, B2t, kmul, src=0)
+    mg.sharded_gemv(dist, x, gemv, src=0)
+    np.savez(os.path.join(out_dir, f"k_{rank}.npz"), C1=res["C1"], C2=res["C2"], z=np.asarray(res["z"]).reshape(-1))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_karatsuba_and_gemv_world2(tmp_path):
+    """Row-block sharding of the Karatsuba product (both limbs of B replicated) and of the GEMV (x replicated)."""
+    world, m, k, n, N1, N2 = 2, 21, 16, 10, 13 ** 4, 13 ** 3
+    port = _free_port()
+    mp.spawn(_worker_kmat_gemv, args=(world, port, m, k, n, N1, N2, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"k_{r}.npz") for r in range(world)]
+    A1 = O.synth_matrix(21, m, k, N1); A2 = O.synth_matrix(22, m, k, N2)
+    B1 = O.synth_matrix(23, k, n, N1); B2 = O.synth_matrix(24, k, n, N2); x = O.synth_matrix(25, k, 1, N1)[:, 0]
+    C1, C2 = O.karatsuba_matmul(A1, A2, B1, B2, N1, N2)
+    assert np.array_equal(np.concatenate([p["C1"] for p in parts]), C1) and np.array_equal(np.concatenate([p["C2"] for p in parts]), C2)
+    full = (A1.astype(object) + N1 * A2.astype(object)).dot(B1.astype(object) + N1 * B2.astype(object)) % (N1 * N2)
+    assert np.array_equal(C1.astype(object) + N1 * C2.astype(object), full)
+    assert np.array_equal(np.concatenate([p["z"] for p in parts]), np.asarray(O.matvec_mod(A1, x, N1)).reshape(-1))
+
+
 def _worker_sag(rank, world, port, rows, cols, out_dir):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

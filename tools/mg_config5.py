@@ -102,7 +102,7 @@ with torch.cuda.stream(stream):
         if world == 1:
             g.KMatMul_(CK, AK, BK)
         else:
-            mg.broadcast_then(dist, [B1t, B2t], lambda: g.KMatMul_(CK, AK, BK), src=0)
+            mg.sharded_kmat_mul(dist, B1t, B2t, lambda: g.KMatMul_(CK, AK, BK), src=0)
 
     ms = timed(step_kara, steps=3, warm=1)
     x = g.synth(n, 1, N1, 78, ctx=ctx)
