@@ -179,6 +179,10 @@ def main():
                     "broadcast of B; pc > 1: rank (i, j) multiplies row block i of A with column range j of B and receives only that range)")
     ap.add_argument("--bcast", default="broadcast", choices=["broadcast", "scatter_allgather"],
                     help="how B is replicated every step (N > 1): ncclBroadcast per panel, or scatter + in-place all-gather per panel")
+    ap.add_argument("--e2e-mode", default="replicated", choices=["replicated", "sliced"],
+                    help="N > 1 end-to-end arm: 'replicated' = every rank uploads its A shard and all of B from its host copy (default); "
+                         "'sliced' additionally times: every rank uploads its A shard and 1/N of each B panel, the panels are completed by an "
+                         "in-place NCCL all-gather and consumed by gffm_gemm_panels (opt-in until measured on 8 GPUs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also time N=11 and N=65521 and PLUQ (reported under config.extras)")
@@ -465,6 +469,50 @@ def main():
             e2e = {"value": 2.0 * n ** 3 / te / 1e9, "unit": "GOPS", "api": "gffm_gemm_host (pipelined)" if pipe and te * 1e3 == pipe["ms_per_step"] else "upload + mul! + download",
                    "sequential_api_calls": seq, "pipelined_host_call": pipe, "h2d_bytes_per_step": int(4 * (mloc * n + n * ncl)), "d2h_bytes_per_step": int(4 * mloc * ncl),
                    "ms_per_step": te * 1e3, "steps": ke, "host_dtype": "uint32 residues (pinned)", "matches_resident_result": same}
+            if world > 1 and pc == 1 and args.e2e_mode == "sliced":
+                try:
+                    C3 = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+                    Bt.zero_()  # nothing of B is resident any more: every byte must come from the host slices + the all-gather
+
+                    def deliver_h(c0, c1):
+                        rows = c1 - c0
+                        if rows % world == 0:
+                            per = rows // world
+                            lo = c0 + rank * per
+                            Bt[lo:lo + per, :n].copy_(hB[lo:lo + per], non_blocking=True)   # H2D: this rank's slice of the panel
+                            dist.all_gather_into_tensor(Bt[c0:c1], Bt[lo:lo + per])         # NVLink: the other N-1 slices, in place
+                        else:
+                            if rank == 0:
+                                Bt[c0:c1, :n].copy_(hB[c0:c1], non_blocking=True)
+                            dist.broadcast(Bt[c0:c1], src=0)
+
+                    bm_h = mg.BroadcastMatmul(torch, dist, C3, A2, B, Bt, panels, deliver=deliver_h)
+
+                    def sliced_step():
+                        g.capi.check(A2.lib.gffm_mat_upload(A2.h, hA.data_ptr(), g.capi.U32, mloc, 1))
+                        bm_h.step()
+                        g.capi.check(C3.lib.gffm_mat_download(C3.h, hC.data_ptr(), g.capi.U32, mloc, 0))
+
+                    sliced_step()
+                    bm_h.finish(); barrier()
+                    t0 = time.perf_counter()
+                    for _ in range(ke):
+                        sliced_step()
+                    bm_h.finish(); barrier()
+                    ts = (time.perf_counter() - t0) / ke
+                    tt = torch.tensor([ts], dtype=torch.float64, device=f"cuda:{local}")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    ts = float(tt.item())
+                    okk = torch.tensor([1 if C3.equals(C) else 0], dtype=torch.int32, device=f"cuda:{local}")
+                    dist.all_reduce(okk, op=dist.ReduceOp.MIN)
+                    e2e["sliced_upload_allgather"] = {"ms_per_step": ts * 1e3, "GOPS": 2.0 * n ** 3 / ts / 1e9, "matches_resident_result": bool(okk.item() == 1),
+                                                      "h2d_bytes_per_step": int(4 * (mloc * n + n * n // world)), "d2h_bytes_per_step": int(4 * mloc * n)}
+                    if okk.item() == 1 and ts < te:
+                        e2e.update({"value": 2.0 * n ** 3 / ts / 1e9, "ms_per_step": ts * 1e3, "api": "upload A shard + 1/N of B, NCCL all-gather, gffm_gemm_panels, download",
+                                    "h2d_bytes_per_step": int(4 * (mloc * n + n * n // world))})
+                    del C3
+                except Exception as ex:  # opt-in arm: never lose the line
+                    e2e["sliced_upload_allgather"] = {"error": str(ex)[:300]}
             del A2, B2, C2
 
         extras = {}
