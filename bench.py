@@ -94,25 +94,36 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_arm(n_full, N, budget_s=20.0, threads=None):
-    """Times the C oracle (oracle/oracle_c.c, pthreads over all host cores) on a bounded sample of the workload:
-    the leading n_s x n_s x n_s sub-product of the same synthetic matrices.  Returns (GOPS, cores, description, seconds)."""
+CPU_SAMPLE_N = 4096  # fixed CPU sample (the same sub-product on every host, so ratios are comparable across runs and GPU counts)
+
+
+def cpu_arm(n_full, N, ns=CPU_SAMPLE_N, threads=None):
+    """Times the C oracle (oracle/oracle_c.c, pthreads over all host cores) on a FIXED bounded sample of the workload: the leading
+    ns x ns x ns sub-product of the same synthetic matrices (ns = 4096: ~2-5 s on 16-32 cores).  Returns (GOPS, cores, description,
+    seconds).  Any time for the full n is an n^3 extrapolation and labelled as such by the callers."""
     import numpy as np
     from oracle import oracle as O
     from oracle import oracle_c as OC
     cores = OC.num_threads() if threads is None else threads
-    ns = 512
-    A = O.synth_matrix(SEED_A, ns, ns, N); B = O.synth_matrix(SEED_B, ns, ns, N)
-    t0 = time.perf_counter(); OC.matmul_mod(A, B, N); t_small = time.perf_counter() - t0
-    rate = 2.0 * ns ** 3 / max(t_small, 1e-6)
-    ns = 1024
-    while ns * 2 <= min(n_full, 8192) and 2.0 * (2 * ns) ** 3 / rate < budget_s:
-        ns *= 2
+    ns = min(ns, n_full)
     A = O.synth_matrix(SEED_A, ns, ns, N); B = O.synth_matrix(SEED_B, ns, ns, N)
     t0 = time.perf_counter(); C = OC.matmul_mod(A, B, N); dt = time.perf_counter() - t0
     chk = int(np.bitwise_xor.reduce(C.reshape(-1)))
     gops = 2.0 * ns ** 3 / dt / 1e9
     return gops, cores, f"{ns}x{ns}x{ns} mod {N} sub-product of the n={n_full} workload, same generator (xor checksum {chk:#x})", dt
+
+
+def cpu_echelon_arm(N, sizes=(1024, 2048)):
+    """CPU baseline of the elimination: the C oracle's echelon form (pluq_kernels.jl:46-157 conventions, one core, scalar) on full-rank
+    synthetic matrices; field mul-adds n^3/3."""
+    from oracle import oracle as O
+    from oracle import oracle_c as OC
+    out = []
+    for n in sizes:
+        A = O.synth_matrix(9, n, n, N)
+        t0 = time.perf_counter(); _, _, _, piv = OC.echelon(A, N); dt = time.perf_counter() - t0
+        out.append({"n": n, "seconds": dt, "rank": len(piv), "field_muladds_per_s": (n ** 3 / 3.0) / dt})
+    return out
 
 
 def stripe_arm(n_full, N, ns=1024):
@@ -129,6 +140,23 @@ def stripe_arm(n_full, N, ns=1024):
             "matches_integer_port": None if ns > 2048 else bool((C == O.exact_matmul_mod(A, B, N)).all())}
 
 
+def nccl_log_lines(limit=12):
+    """The 'nranks' / 'Init COMPLETE' lines NCCL wrote to NCCL_DEBUG_FILE (one file per process); also echoed to stderr."""
+    import glob
+    pat = os.environ.get("NCCL_DEBUG_FILE", "").replace("%h", "*").replace("%p", "*")
+    lines = []
+    for f in sorted(glob.glob(pat)):
+        try:
+            for ln in open(f, errors="replace"):
+                if "nranks" in ln and ("Init COMPLETE" in ln or "ncclCommInitRank" in ln):
+                    lines.append(ln.strip()[:300])
+        except OSError:
+            pass
+    for ln in lines[:64]:
+        print(ln, file=sys.stderr)
+    return {"files": len(glob.glob(pat)), "nranks_lines": lines[:limit], "count": len(lines)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -139,7 +167,7 @@ def run_reference(args):
     for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
         pass
     for i in range(max(1, min(args.steps, 3))):
-        gops, cores, desc, dt = cpu_arm(args.n, args.modulus, budget_s=15.0)
+        gops, cores, desc, dt = cpu_arm(args.n, args.modulus)
         gops_all.append(gops)
     value = statistics.median(gops_all)
     out = {
@@ -149,7 +177,8 @@ def run_reference(args):
         "config": {"workload": f"{args.n}x{args.n} * {args.n}x{args.n} matmul mod {args.modulus} ({(args.modulus - 1).bit_length()}-bit modulus), A,B resident as uint32 residues",
                    "n": args.n, "modulus": args.modulus,
                    "note": "the Julia reference cannot run in this image; this arm is the reference tests' CPU ground truth mod.(A*B,N) restated in C "
-                           "(oracle/oracle_c.c) on all host cores; ms_per_step is the n^3-extrapolated time of the full workload"},
+                           "(oracle/oracle_c.c) on all host cores; every step is the FIXED 4096^3 sub-product (same on every host); "
+                           "ms_per_step is EXTRAPOLATED by n^3 to the full workload", "cpu_sample_n": min(CPU_SAMPLE_N, args.n), "ms_per_step_is_extrapolated": True},
         "cpu_baseline": {"value": value, "unit": "GOPS", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "GOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -185,7 +214,11 @@ def main():
                          "in-place NCCL all-gather and consumed by gffm_gemm_panels (opt-in until measured on 8 GPUs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time N=11 and N=65521 and PLUQ (reported under config.extras)")
+    ap.add_argument("--extras", action="store_true", help="(default at N = 1; kept for compatibility)")
+    ap.add_argument("--no-extras", action="store_true", help="skip config.extras (other moduli, PLUQ / RREF / inverse n = 16384, GEMV, the reference's "
+                    "n = 5000 timing cases) and the PLUQ roofline / CPU echelon baseline")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check of the timed result (parity_check)")
+    ap.add_argument("--parity-rows", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -203,9 +236,14 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.pop("NCCL_DEBUG", None)  # no "NCCL version" banner on stdout: ONE JSON line
+        # NCCL's own log is evidence of the rank count: keep it, but away from stdout (ONE JSON line there).  With NCCL_DEBUG set and no
+        # NCCL_DEBUG_FILE the log goes to gpurun_out/nccl_debug.<host>.<pid>.log; rank 0 copies the "nranks" lines to stderr and into the
+        # JSON line (config.nccl_log) after the run.
         if os.environ.get("GFFM_NCCL_DEBUG"):
             os.environ["NCCL_DEBUG"] = os.environ["GFFM_NCCL_DEBUG"]
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, N = args.n, args.modulus
     W = max(3, args.warmup)
@@ -271,8 +309,8 @@ def main():
         tune = {}
         choice = (pan_cands[0], cta_cands[0])
         if world > 1 and len(pan_cands) * len(cta_cands) > 1:  # untimed: pick (panels, GEMM grid cap) by a short trial of each
-            for pc in pan_cands:
-                panels, bm = make_bm(pc)
+            for npan_c in pan_cands:
+                panels, bm = make_bm(npan_c)
                 for cc in cta_cands:
                     ctx.set_gemm_ctas(cc)
                     for _ in range(2):
@@ -285,7 +323,7 @@ def main():
                     bm.finish(); a1.record(stream); barrier()
                     tt = torch.tensor([a0.elapsed_time(a1) / 6], dtype=torch.float64, device=f"cuda:{local}")
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                    tune[(pc, cc)] = float(tt.item())
+                    tune[(npan_c, cc)] = float(tt.item())
             choice = min(tune, key=tune.get)  # identical on every rank (all-reduced times)
         panels, bm = make_bm(choice[0])
         ctx.set_gemm_ctas(choice[1])
@@ -344,6 +382,34 @@ def main():
             shard_ok = bool(ok.item() == 1)
             del Cref
 
+        # ---- parity of the TIMED result against the CPU oracle: sampled rows of this rank's C (the output of the last timed step),
+        # recomputed by oracle_c.matmul_mod from rows of A rebuilt with the oracle's generator and the B this rank multiplied with
+        # (downloaded; 32 of its columns are checked against the oracle's generator).  Reference criterion: `==` against the host
+        # product, /root/reference/test/CuModMatrix/stripe_mul_test.jl:31-50.
+        parity = None
+        if not args.no_parity:
+            from oracle import sampled as S
+            nrows = max(8, args.parity_rows // world) if world > 1 else args.parity_rows
+            rows_loc = S.pick_rows(mloc, nrows, seed=17 + rank)
+            t0p = time.perf_counter()
+            A_rows = S.synth_rows(SEED_A, rows_loc + r0, n, n, N)
+            gen_ok = bool(np.array_equal(A.gather_rows(rows_loc), A_rows))
+            Bh = B.to_u32()
+            cols_s = S.pick_rows(ncl, 32, seed=99)
+            gen_ok = gen_ok and bool(np.array_equal(Bh[:, cols_s].astype(np.int64), S.synth_cols(SEED_B, cols_s + cl0, n, N)))
+            rep = S.check_product_rows(C.gather_rows(rows_loc), A_rows, Bh, N)
+            del Bh
+            ok_all, rows_all = rep["match"] and gen_ok, rep["rows"]
+            if world > 1:
+                tt = torch.tensor([1 if ok_all else 0, -rep["rows"]], dtype=torch.int64, device=f"cuda:{local}")
+                dist.all_reduce(tt[0:1], op=dist.ReduceOp.MIN)
+                rr = torch.tensor([rep["rows"]], dtype=torch.int64, device=f"cuda:{local}")
+                dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+                ok_all, rows_all = bool(tt[0].item() == 1), int(rr.item())
+            parity = {"rows": rows_all, "cols": rep["cols"], "match": bool(ok_all), "checker": "oracle_c.matmul_mod (exact uint64 host arithmetic)",
+                      "what": "rows of the C produced by the last timed step" + ("" if world == 1 else " (every rank checks rows of its own shard)"),
+                      "inputs_match_oracle_generator": gen_ok, "seconds": time.perf_counter() - t0p}
+
         # ---- roofline of the dominant kernel (tcgen05 GEMM): a few more profiled steps, kernel-only durations --------
         gemm_ms = [phase_ms[1]] if len(phase_ms) >= 2 else []
         ctx.set_profiling(True)
@@ -401,7 +467,7 @@ def main():
                 pass
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
+        if world == 1 and n == N_DEFAULT and os.path.exists(tp):  # the ncu capture is of the full single-GPU launch: meaningless for panel launches
             try:
                 traffic = json.load(open(tp)).get("gemm_tc_kernel_rns_dram_bytes_per_launch")
             except Exception:
@@ -516,40 +582,114 @@ def main():
             del A2, B2, C2
 
         extras = {}
-        if args.extras and world == 1:
+        roofline_pluq = None
+        if world == 1 and not args.no_extras:
+            def dev_time(fn, reps, warm=1):
+                """median / min wall time (s) of fn() bracketed by device synchronisation (the elimination calls block on their own)"""
+                for _ in range(warm):
+                    fn()
+                ts = []
+                for _ in range(reps):
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    fn()
+                    torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+                return statistics.median(ts), min(ts)
+
+            def ev_time(fn, reps, warm=2):
+                """mean device time (ms) of fn() over `reps` back-to-back calls (CUDA events on the library stream)"""
+                for _ in range(warm):
+                    fn()
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for _ in range(reps):
+                    fn()
+                a1.record(stream); torch.cuda.synchronize()
+                return a0.elapsed_time(a1) / reps
+
+            # other moduli of the metric size (fresh product each time)
             for N2 in (11, 65521):
                 A_, B_ = g.synth(n, n, N2, SEED_A, ctx=ctx), g.synth(n, n, N2, SEED_B, ctx=ctx)
                 C_ = g.zeros(np.float32, n, n, N2, ctx=ctx)
-                for _ in range(3):
+
+                def prod():
+                    A_.touch(); B_.touch()
                     g.mul_(C_, A_, B_)
-                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
-                a0.record(stream)
-                for _ in range(5):
-                    A_.touch(); B_.touch()  # fresh product each time (no cached planes)
-                    g.mul_(C_, A_, B_)
-                a1.record(stream); torch.cuda.synchronize()
-                t_ = a0.elapsed_time(a1) / 5
+                t_ = ev_time(prod, 5, warm=3)
                 extras[f"matmul_n{n}_mod{N2}"] = {"ms": t_, "GOPS": 2.0 * n ** 3 / t_ / 1e6}
                 del A_, B_, C_
-            for (np_, Np) in ((n, 65521), (n, N)):
-                A_ = g.synth(np_, np_, Np, 9, ctx=ctx)
-                tp_ = None
-                for rep in range(2):  # first call pays one-off costs (workspaces, inverse table, kernel attributes)
-                    torch.cuda.synchronize(); t0 = time.perf_counter()
-                    U_, L_, pr_, pc_, rk_ = g.pluq_gpu_kernel(A_, return_rank=True)
-                    torch.cuda.synchronize(); tp_ = time.perf_counter() - t0
-                    del U_, L_
-                for rep in range(2):
-                    torch.cuda.synchronize(); t0 = time.perf_counter()
-                    R_ = g.rref(A_)
-                    torch.cuda.synchronize(); tr_ = time.perf_counter() - t0
-                extras[f"pluq_n{np_}_mod{Np}"] = {"seconds": tp_, "rank": rk_, "rref_seconds": tr_}
-                del A_, R_
+            # GEMV at the metric size: HBM-bound, 4 bytes per matrix element
+            z_ = g.zeros(np.float32, n, 1, N, ctx=ctx); x_ = g.synth(n, 1, N, 77, ctx=ctx)
+            t_ = ev_time(lambda: g.gemv_(z_, A, x_), 20, warm=3)
+            extras[f"gemv_n{n}_mod{N}"] = {"ms": t_, "GBps": 4.0 * n * n / (t_ * 1e-3) / 1e9, "hbm_peak_GBps": peaks["hbm_gbs"],
+                                            "frac_of_hbm_peak": 4.0 * n * n / (t_ * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": 4 * n * n,
+                                            "note": "A (1 GiB) is larger than L2; 20 back-to-back products"}
+            del z_, x_
+            # the reference's only published cases (test/CuModMatrix/timing_test.jl:21-52: n = 5000, N = 11; RTX 3070 comments
+            # < 0.001 s add!, < 0.001 s scalar mul!, < 0.2 s mul!, < 0.001 s mat-vec) from our path
+            n5 = 5000
+            A5, B5 = g.synth(n5, n5, 11, 1, ctx=ctx), g.synth(n5, n5, 11, 2, ctx=ctx)
+            C5 = g.zeros(np.float32, n5, n5, 11, ctx=ctx); z5 = g.zeros(np.float32, n5, 1, 11, ctx=ctx); x5 = g.synth(n5, 1, 11, 3, ctx=ctx)
+
+            def mul5():
+                A5.touch(); B5.touch()
+                g.mul_(C5, A5, B5)
+            extras["reference_timing_cases_n5000_mod11"] = {
+                "source": "reference test/CuModMatrix/timing_test.jl:21-52 (author's RTX 3070 comments: add! < 1 ms, scalar mul! < 1 ms, mul! < 200 ms (F32) / < 1000 ms (F64), mat-vec < 1 ms)",
+                "add_ms": ev_time(lambda: g.add_(C5, A5, B5), 20), "scalar_mul_ms": ev_time(lambda: g.capi.check(C5.lib.gffm_ewise(g.capi.EW_SMUL, C5.h, A5.h, None, 2, 0)), 20),
+                "mul_ms": ev_time(mul5, 10), "matvec_ms": ev_time(lambda: g.gemv_(z5, A5, x5), 20)}
+            del A5, B5, C5, z5, x5
+            # elimination at the metric size: PLUQ, RREF, inverse; warm, 3 repetitions, median (BASELINE metric: "PLUQ n=16384 s")
+            for Np in (65521, N):
+                A_ = g.synth(n, n, Np, 9, ctx=ctx)
+                holder = {}
+
+                def do_pluq():
+                    holder["r"] = g.pluq_gpu_kernel(A_, return_rank=True)
+                l0_ = ctx.launch_count()
+                med, best = dev_time(do_pluq, 3)
+                launches_pluq = (ctx.launch_count() - l0_) // 4
+                rk_ = holder["r"][4]
+                holder.clear()
+                med_r, best_r = dev_time(lambda: holder.__setitem__("r", g.rref(A_)), 3)
+                holder.clear()
+                med_i, best_i = dev_time(lambda: holder.__setitem__("r", g.inverse(A_)), 3)
+                holder.clear()
+                ctx.set_profiling(True)
+                do_pluq(); ph = ctx.last_timings(); holder.clear()
+                ctx.set_profiling(False)
+                Lb = 1 if Np <= 256 else (2 if Np <= 65536 else None)
+                extras[f"pluq_n{n}_mod{Np}"] = {"seconds": med, "seconds_best": best, "rank": rk_, "rref_seconds": med_r, "rref_seconds_best": best_r,
+                                                 "inverse_seconds": med_i, "inverse_seconds_best": best_i, "us_per_pivot": med / max(rk_, 1) * 1e6,
+                                                 "kernel_launches_per_factorisation": int(launches_pluq),
+                                                 "phases_ms_profiled_call": {"panels_and_in_block_updates": ph[0] if len(ph) > 0 else None,
+                                                                             "triangular_solves": ph[1] if len(ph) > 1 else None, "schur_gemms": ph[2] if len(ph) > 2 else None},
+                                                 "reps": 3, "timing": "median wall time between device synchronisations, warm (second call onwards)"}
+                if Np == 65521:
+                    fm = n ** 3 / 3.0  # m n r - (m + n) r^2 / 2 + r^3 / 3 for m = n = r (SURVEY 8d)
+                    ip8 = 4542.2
+                    try:
+                        ip8 = float(json.load(open(os.path.join(ROOT, "profiles", "int8_peak.json")))["int8_tops_sustained"])
+                    except Exception:
+                        pass
+                    peak_fm = ip8 * 1e12 / (2.0 * Lb * Lb)  # field mul-adds/s if all of them ran as L^2 int8 MMAs at the tensor peak
+                    roofline_pluq = {"bound": "latency (n sequential pivots; the Schur updates are tensor-bound)", "kernel": "pluq_panel_ll_kernel",
+                                     "workload": f"PLUQ {n}x{n} mod {Np}, full rank", "field_muladds": fm, "achieved": fm / med / 1e12, "peak": peak_fm / 1e12,
+                                     "unit": "T field mul-add/s", "frac": fm / med / peak_fm, "seconds": med, "us_per_pivot": med / max(rk_, 1) * 1e6,
+                                     "note": "peak = measured int8 tensor peak / (2 L^2), L = 2 eight-bit limbs; the panel kernel (one thread-block cluster, "
+                                             "argmax + row exchange per pivot) bounds the factorisation, see DESIGN.md section 6"}
+                del A_
 
     cpu = None
+    cpu_pluq = None
     if rank == 0 and not args.no_cpu:
         gops, cores, desc, dt = cpu_arm(n, N)
-        cpu = {"value": gops, "unit": "GOPS", "cores": cores, "kind": "port", "sample": desc, "seconds": dt}
+        cpu = {"value": gops, "unit": "GOPS", "cores": cores, "kind": "port", "sample": desc, "seconds": dt,
+               "extrapolated_full_workload_seconds": 2.0 * n ** 3 / (gops * 1e9)}
+        if world == 1 and not args.no_extras:
+            ech = cpu_echelon_arm(65521)
+            cpu_pluq = {"kind": "port", "cores": 1, "unit": "seconds", "sample": "oracle_c.echelon (reference pivot rule, scalar C) on full-rank synthetic n x n mod 65521",
+                        "runs": ech, "value": ech[-1]["seconds"],
+                        "extrapolated_n16384_seconds": ech[-1]["seconds"] * (16384.0 / ech[-1]["n"]) ** 3}
 
     if rank == 0:
         out = {
@@ -564,7 +704,14 @@ def main():
                        "l2_policy": f"inputs larger than L2: A and B are {4 * n * n / 2**20:.0f} MiB each vs 126 MB L2", "checksum_rank0": f"{checksum:016x}",
                        "extras": extras},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity_check": parity,
         }
+        if roofline_pluq is not None:
+            out["roofline_pluq"] = roofline_pluq
+        if cpu_pluq is not None:
+            out["cpu_baseline_pluq"] = cpu_pluq
+        if world > 1 and os.environ.get("NCCL_DEBUG_FILE"):
+            out["config"]["nccl_log"] = nccl_log_lines()
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

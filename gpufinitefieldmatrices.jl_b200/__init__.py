@@ -2,7 +2,7 @@
 reference's CuModMatrix / KaratsubaMatrix interface.  Import as `gffm_b200` (see gffm_b200.py at the repo root;
 the directory name contains a dot and cannot be imported directly)."""
 from . import capi
-from .capi import (CuModArrayModulusMismatchException, CuModArraySizeMismatchException, CuModMatrixNotSquareException,
+from .capi import (CuModArrayModulusMismatchException, CuModArraySizeMismatchException, CuModMatrixModulusNotPrimeException, CuModMatrixNotSquareException,
                    GffmError, InexactError, InverseNotDefinedException, MatrixNotInvertibleException)
 from .cumodmatrix import *  # noqa: F401,F403
 from .cumodmatrix import Context, CuModMatrix, CuModVector, default_context

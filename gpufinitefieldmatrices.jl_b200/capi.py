@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libgffm.so")
 
 # status codes / enums (include/gffm.h)
 OK, ERR_INVALID, ERR_SIZE_MISMATCH, ERR_MODULUS_MISMATCH, ERR_MODULUS_TOO_LARGE, ERR_NOT_SQUARE, ERR_NOT_INVERTIBLE, \
-    ERR_INVERSE_NOT_DEFINED, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_INEXACT, ERR_OOM = range(13)
+    ERR_INVERSE_NOT_DEFINED, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_INEXACT, ERR_OOM, ERR_MODULUS_NOT_PRIME = range(14)
 F32, F64, I64, U32, I32 = range(5)
 EW_MOD, EW_ADD, EW_SUB, EW_MUL, EW_SADD, EW_SSUB, EW_RSSUB, EW_SMUL, EW_SDIV = range(9)
 GEMM_STORE, GEMM_ADD, GEMM_SUB = range(3)
@@ -50,6 +50,10 @@ class InexactError(GffmError):
     pass
 
 
+class CuModMatrixModulusNotPrimeException(GffmError):
+    pass
+
+
 _EXC = {
     ERR_SIZE_MISMATCH: CuModArraySizeMismatchException,
     ERR_MODULUS_MISMATCH: CuModArrayModulusMismatchException,
@@ -58,6 +62,7 @@ _EXC = {
     ERR_NOT_INVERTIBLE: MatrixNotInvertibleException,
     ERR_INVERSE_NOT_DEFINED: InverseNotDefinedException,
     ERR_INEXACT: InexactError,
+    ERR_MODULUS_NOT_PRIME: CuModMatrixModulusNotPrimeException,
 }
 
 _vp = C.c_void_p

@@ -110,6 +110,7 @@ extern "C" int32_t gffm_destroy(gffm_ctx* ctx) {
   ws_free(&ctx->ws_misc2);
   ws_free(&ctx->ws_invtab);
   ws_free(&ctx->ws_scratch);
+  ws_free(&ctx->ws_gemv);
   ws_free(&ctx->ws_host);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -832,63 +833,7 @@ int32_t gffm_gemm_simt(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t 
   return GFFM_OK;
 }
 
-// GEMV (reference stripe_mul.jl:82-168): HBM-bound, one pass over A; 128 rows per CTA, K split across 8 warps.
-__global__ void __launch_bounds__(256)
-gemv_kernel(uint32_t* __restrict__ z, const uint32_t* __restrict__ A, int64_t lda, const uint32_t* __restrict__ x, int m, int k,
-            const __grid_constant__ ModP mp) {
-  __shared__ unsigned long long part[8][32 * 4 + 4];
-  const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int i0 = blockIdx.x * 128;
-  unsigned long long acc[4] = {0, 0, 0, 0};
-  int cnt = 0;
-  for (int kk = w; kk < k; kk += 8) {
-    const uint64_t xv = x[kk];
-    const uint32_t* col = A + (int64_t)kk * lda + i0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int i = i0 + tx + 32 * c;
-      if (i < m) acc[c] += (uint64_t)col[tx + 32 * c] * xv;
-    }
-    if (++cnt == 1) {  // products may be up to 2^64: reduce every step when P is large, else every 64 steps
-    }
-    if (mp.P > (1ull << 29) || (cnt & 63) == 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] = mod_u64(acc[c], mp);
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) part[w][tx + 32 * c] = mod_u64(acc[c], mp);
-  __syncthreads();
-  if (w == 0) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      unsigned long long s = 0;
-      for (int ww = 0; ww < 8; ++ww) s += part[ww][tx + 32 * c];
-      const int i = i0 + tx + 32 * c;
-      if (i < m) z[i] = (uint32_t)mod_u64(s, mp);
-    }
-  }
-}
-
-extern "C" int32_t gffm_gemv(gffm_mat* z, gffm_mat* A, gffm_mat* x, uint64_t R, uint64_t P) {
-  GFFM_ENTER_MAT(z);
-  if (!z || !A || !x) GFFM_FAIL(GFFM_ERR_INVALID, "null");
-  if (x->cols != 1 || z->cols != 1 || A->cols != x->rows || A->rows != z->rows)
-    GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "gemv: A is %lldx%lld, x has %lld rows, z has %lld rows", (long long)A->rows, (long long)A->cols,
-              (long long)x->rows, (long long)z->rows);
-  (void)R;
-  if (!P) {
-    if (A->N != x->N || A->N != z->N) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "gemv operands have different moduli");
-    P = z->N;
-  }
-  if (P >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "gemv needs P < 2^32");
-  if (A->rows == 0) return GFFM_OK;
-  gffm_touch(z);
-  gffm_ctx* ctx = A->ctx;
-  gemv_kernel<<<(unsigned)ceil_div(A->rows, 128), 256, 0, ctx->stream>>>(z->data, A->data, A->ld, x->data, (int)A->rows, (int)A->cols, make_modp(P));
-  GFFM_LAUNCH_CHECK(ctx);
-  return GFFM_OK;
-}
+// GEMV: gemv.cu
 
 // ---------------------------------------------------------------------------------------------
 // GEMM dispatcher

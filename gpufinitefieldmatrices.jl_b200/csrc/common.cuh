@@ -72,7 +72,7 @@ struct gffm_ctx {
   int64_t launches = 0;
   int gemm_ctas = 0;  // cap on the persistent GEMM grid (0 = one CTA per SM); leaves SMs to concurrent NCCL kernels (gffm_set_gemm_ctas)
   // grow-only scratch buffers (stream-ordered reuse)
-  gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned, ws_invtab, ws_scratch, ws_host;
+  gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned, ws_invtab, ws_scratch, ws_host, ws_gemv;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;  // copy / helper streams of the tiled GEMM
   std::vector<cudaEvent_t> ev_pool;
   std::vector<cudaEvent_t> tile_events;  // (start, end) pairs around the GEMM launches of the last profiled tiled product
@@ -240,6 +240,9 @@ int32_t gffm_gemm_tc_rns(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_
 bool gffm_tc_available(gffm_ctx* ctx);
 int64_t gffm_gemm_kchunk(uint64_t R, bool rns);
 int32_t gffm_gemm_tiled(gffm_ctx* ctx, MatView C, MatView A, MatView B, uint64_t R, uint64_t P, int mode, bool balanced);
+// z = A*x mod P on raw device pointers (gemv.cu); Karatsuba mat x vec in one pass over A1, A2
+int32_t gffm_gemv_raw(gffm_ctx* ctx, uint32_t* z, const uint32_t* A, int64_t lda, const uint32_t* x, int64_t m, int64_t k, uint64_t R, uint64_t P);
+int32_t gffm_kmat_gemv(gffm_ctx* ctx, gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_mat* A2, gffm_mat* B1, gffm_mat* B2, uint64_t N1, uint64_t N2);
 
 int32_t gffm_ew_views(gffm_ctx* ctx, int op, MatView C, MatView A, const MatView* B, int64_t scalar, uint64_t P);
 int32_t gffm_copy_views(gffm_ctx* ctx, MatView dst, MatView src);

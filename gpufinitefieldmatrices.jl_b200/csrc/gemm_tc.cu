@@ -18,6 +18,8 @@
 //   warp 1      MMA issuer        tcgen05.mma.cta_group::1.kind::i8, tcgen05.commit -> empty[stage] / tmem_full[buf]
 //   warps 2..5  epilogue          tcgen05.ld 32x32b.x16 -> registers -> reduction -> coalesced global stores
 #include <cuda.h>
+#include <algorithm>
+#include <vector>
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -1144,14 +1146,20 @@ int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2,
 #undef GFFM_SPLIT_A
   } else {
     // B is K x n: K along rows of the view
-    const uint32_t* s = X.p + k_off;
-    const uint32_t* s2 = X2 ? X2->p + k_off : nullptr;
-    dim3 grid((unsigned)ceil_div(Kp / 16, 128), (unsigned)X.cols);
-#define GFFM_SPLIT_B(MODE) split_b_kernel<MODE><<<grid, 128, 0, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)X.cols, planes, Kp, rowsP, sp)
-    if (sp.mode == 0) GFFM_SPLIT_B(0);
-    else if (sp.mode == 1) GFFM_SPLIT_B(1);
-    else GFFM_SPLIT_B(2);
+    // gridDim.y carries the column: slabs of at most 65535 columns per launch
+    for (int64_t c0 = 0; c0 < X.cols; c0 += 65535) {
+      const int64_t nc = std::min<int64_t>(65535, X.cols - c0);
+      const uint32_t* s = X.p + k_off + c0 * X.ld;
+      const uint32_t* s2 = X2 ? X2->p + k_off + c0 * X2->ld : nullptr;
+      uint8_t* pl = planes + c0 * Kp;
+      dim3 grid((unsigned)ceil_div(Kp / 16, 128), (unsigned)nc);
+#define GFFM_SPLIT_B(MODE) split_b_kernel<MODE><<<grid, 128, 0, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)nc, pl, Kp, rowsP, sp)
+      if (sp.mode == 0) GFFM_SPLIT_B(0);
+      else if (sp.mode == 1) GFFM_SPLIT_B(1);
+      else GFFM_SPLIT_B(2);
 #undef GFFM_SPLIT_B
+      if (c0 + nc < X.cols) GFFM_LAUNCH_CHECK(ctx);
+    }
   }
   GFFM_LAUNCH_CHECK(ctx);
   return GFFM_OK;
@@ -1381,12 +1389,19 @@ int32_t make_rns_plan(int64_t kc, uint64_t R, uint64_t P, bool balanced, int crt
 
 int32_t launch_crt(gffm_ctx* ctx, cudaStream_t st, const CrtParams& cp, const uint8_t* E, int64_t lde, int64_t e_plane, int64_t m, int64_t n,
                    uint32_t* C, int64_t ldc, uint32_t* hi, int64_t ldhi) {
-  dim3 grid((unsigned)ceil_div(m, 1024), (unsigned)n);
-  if (cp.fast == 2) crt_fast_kernel<true><<<grid, 256, 0, st>>>(E, lde, e_plane, (int)m, (int)n, C, ldc, cp);
-  else if (cp.fast == 1) crt_fast_kernel<false><<<grid, 256, 0, st>>>(E, lde, e_plane, (int)m, (int)n, C, ldc, cp);
-  else if (cp.modP.P >= (1ull << 32)) crt_kernel<true><<<grid, 256, 0, st>>>(E, lde, e_plane, (int)m, (int)n, C, ldc, hi, ldhi, cp);
-  else crt_kernel<false><<<grid, 256, 0, st>>>(E, lde, e_plane, (int)m, (int)n, C, ldc, hi, ldhi, cp);
-  GFFM_LAUNCH_CHECK(ctx);
+  // gridDim.y carries the column: slabs of at most 65535 columns per launch
+  for (int64_t c0 = 0; c0 < n; c0 += 65535) {
+    const int nc = (int)std::min<int64_t>(65535, n - c0);
+    dim3 grid((unsigned)ceil_div(m, 1024), (unsigned)nc);
+    const uint8_t* Es = E + c0 * lde;
+    uint32_t* Cs = C + c0 * ldc;
+    uint32_t* his = hi ? hi + c0 * ldhi : nullptr;
+    if (cp.fast == 2) crt_fast_kernel<true><<<grid, 256, 0, st>>>(Es, lde, e_plane, (int)m, nc, Cs, ldc, cp);
+    else if (cp.fast == 1) crt_fast_kernel<false><<<grid, 256, 0, st>>>(Es, lde, e_plane, (int)m, nc, Cs, ldc, cp);
+    else if (cp.modP.P >= (1ull << 32)) crt_kernel<true><<<grid, 256, 0, st>>>(Es, lde, e_plane, (int)m, nc, Cs, ldc, his, ldhi, cp);
+    else crt_kernel<false><<<grid, 256, 0, st>>>(Es, lde, e_plane, (int)m, nc, Cs, ldc, his, ldhi, cp);
+    GFFM_LAUNCH_CHECK(ctx);
+  }
   return GFFM_OK;
 }
 

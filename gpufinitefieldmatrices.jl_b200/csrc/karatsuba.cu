@@ -71,6 +71,33 @@ kara_ewise_kernel(int op, uint32_t* __restrict__ C1, uint32_t* __restrict__ C2, 
 
 }  // namespace
 
+// one K-chunk (k <= 65536) of the product on views: (C1, C2) = (A1 + N1*A2) * (B1 + N1*B2) mod N1*N2
+static int32_t kmat_mul_chunk(gffm_ctx* ctx, MatView vC1, MatView vC2, MatView vA1, MatView vA2, MatView vB1, MatView vB2, uint64_t N1,
+                              uint64_t N2) {
+  const int64_t m = vA1.rows, n = vB1.cols;
+  // temporaries: carry, P2, P3 (m x n, same leading dimension)
+  const int64_t ldt = round_up(m, 32);
+  GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_misc, (size_t)3 * ldt * n * 4));
+  uint32_t* carry = (uint32_t*)ctx->ws_misc.ptr;
+  uint32_t* P2 = carry + ldt * n;
+  uint32_t* P3 = P2 + ldt * n;
+  MatView vP2{P2, ldt, m, n}, vP3{P3, ldt, m, n};
+  // P1: exact integer product, reduced mod N1*N2 and split into (C1, carry)
+  GFFM_TRY(gffm_gemm_tc_rns_ex(ctx, vC1, vA1, nullptr, vB1, nullptr, N1, N1 * N2, GFFM_GEMM_STORE, /*balanced=*/false, carry, ldt, N1));
+  // P2: limb add fused into the plane split; inputs < N1 + N2 <= 2*N1
+  const uint64_t R2 = N1 + N2;
+  if (R2 <= 65536) GFFM_TRY(gffm_gemm_tc_limb_ex(ctx, vP2, vA1, &vA2, vB1, &vB2, R2, N2, GFFM_GEMM_STORE));
+  else GFFM_TRY(gffm_gemm_tc_rns_ex(ctx, vP2, vA1, &vA2, vB1, &vB2, R2, N2, GFFM_GEMM_STORE, false, nullptr, 0, 0));
+  // P3: inputs < N2, result mod N2 -> balanced residues allowed
+  if (N2 <= 65536) GFFM_TRY(gffm_gemm_tc_limb_ex(ctx, vP3, vA2, nullptr, vB2, nullptr, N2, N2, GFFM_GEMM_STORE));
+  else GFFM_TRY(gffm_gemm_tc_rns_ex(ctx, vP3, vA2, nullptr, vB2, nullptr, N2, N2, GFFM_GEMM_STORE, true, nullptr, 0, 0));
+  int64_t blocks = ceil_div(m * n, 1024);
+  if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
+  kara_recombine_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(vC2.p, vC2.ld, vC1.p, vC1.ld, P2, P3, carry, ldt, m, n, make_modp(N2));
+  GFFM_LAUNCH_CHECK(ctx);
+  return GFFM_OK;
+}
+
 extern "C" int32_t gffm_kmat_mul(gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_mat* A2, gffm_mat* B1, gffm_mat* B2, uint64_t N1,
                                  uint64_t N2) {
   GFFM_ENTER_MAT(C1);
@@ -81,33 +108,51 @@ extern "C" int32_t gffm_kmat_mul(gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_
   if (A2->rows != m || A2->cols != k || B1->rows != k || B2->rows != k || B2->cols != n || C1->rows != m || C1->cols != n ||
       C2->rows != m || C2->cols != n)
     GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "KMatMul!: inconsistent sizes");
+  for (gffm_mat* c : {C1, C2})
+    for (gffm_mat* x : {A1, A2, B1, B2})
+      if (c == x) GFFM_FAIL(GFFM_ERR_INVALID, "KMatMul!: C must not alias an operand");
   gffm_ctx* ctx = A1->ctx;
   if (m == 0 || n == 0) return GFFM_OK;
   gffm_touch(C1);
   gffm_touch(C2);
-  if (k > 65536) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "KMatMul! with inner dimension above 65536");
-  // temporaries: carry, P2, P3 (m x n, same leading dimension)
+  // mat x vec (the only Karatsuba product the reference's tests run, KMatMul_gemv! KaratsubaMatrix.jl:238-300): one HBM pass
+  if (n == 1 && A1->ld == A2->ld) return gffm_kmat_gemv(ctx, C1, C2, A1, A2, B1, B2, N1, N2);
+  const int64_t kmax = 65536;  // one int32 accumulation chunk of the RNS sub-products
+  if (k <= kmax) return kmat_mul_chunk(ctx, view_of(C1), view_of(C2), view_of(A1), view_of(A2), view_of(B1), view_of(B2), N1, N2);
+  // K-chunking: every chunk is a complete two-limb product mod N1*N2; chunks are summed with the two-limb carry add
+  // (reference KaratsubaKernels.jl:2-31 add kernel)
   const int64_t ldt = round_up(m, 32);
-  GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_misc, (size_t)3 * ldt * n * 4));
-  uint32_t* carry = (uint32_t*)ctx->ws_misc.ptr;
-  uint32_t* P2 = carry + ldt * n;
-  uint32_t* P3 = P2 + ldt * n;
-  MatView vA1 = view_of(A1), vA2 = view_of(A2), vB1 = view_of(B1), vB2 = view_of(B2);
-  MatView vP2{P2, ldt, m, n}, vP3{P3, ldt, m, n};
-  // P1: exact integer product, reduced mod N1*N2 and split into (C1, carry)
-  GFFM_TRY(gffm_gemm_tc_rns_ex(ctx, view_of(C1), vA1, nullptr, vB1, nullptr, N1, N1 * N2, GFFM_GEMM_STORE, /*balanced=*/false, carry, ldt, N1));
-  // P2: limb add fused into the plane split; inputs < N1 + N2 <= 2*N1
-  const uint64_t R2 = N1 + N2;
-  if (R2 <= 65536) GFFM_TRY(gffm_gemm_tc_limb_ex(ctx, vP2, vA1, &vA2, vB1, &vB2, R2, N2, GFFM_GEMM_STORE));
-  else GFFM_TRY(gffm_gemm_tc_rns_ex(ctx, vP2, vA1, &vA2, vB1, &vB2, R2, N2, GFFM_GEMM_STORE, false, nullptr, 0, 0));
-  // P3: inputs < N2, result mod N2 -> balanced residues allowed
-  if (N2 <= 65536) GFFM_TRY(gffm_gemm_tc_limb_ex(ctx, vP3, vA2, nullptr, vB2, nullptr, N2, N2, GFFM_GEMM_STORE));
-  else GFFM_TRY(gffm_gemm_tc_rns_ex(ctx, vP3, vA2, nullptr, vB2, nullptr, N2, N2, GFFM_GEMM_STORE, true, nullptr, 0, 0));
-  int64_t blocks = ceil_div(m * n, 1024);
-  if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
-  kara_recombine_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(C2->data, C2->ld, C1->data, C1->ld, P2, P3, carry, ldt, m, n, make_modp(N2));
-  GFFM_LAUNCH_CHECK(ctx);
-  return GFFM_OK;
+  uint32_t* T = nullptr;
+  if (gffm_dev_alloc(ctx, (void**)&T, (size_t)2 * ldt * n * 4) != cudaSuccess) GFFM_FAIL(GFFM_ERR_OOM, "KMatMul!: chunk temporaries");
+  int32_t st = GFFM_OK;
+  for (int64_t k0 = 0; k0 < k && st == GFFM_OK; k0 += kmax) {
+    const int64_t kc = std::min(kmax, k - k0);
+    MatView a1 = sub_view(view_of(A1), 0, k0, m, kc), a2 = sub_view(view_of(A2), 0, k0, m, kc);
+    MatView b1 = sub_view(view_of(B1), k0, 0, kc, n), b2 = sub_view(view_of(B2), k0, 0, kc, n);
+    if (k0 == 0) {
+      st = kmat_mul_chunk(ctx, view_of(C1), view_of(C2), a1, a2, b1, b2, N1, N2);
+    } else {
+      MatView t1{T, ldt, m, n}, t2{T + ldt * n, ldt, m, n};
+      st = kmat_mul_chunk(ctx, t1, t2, a1, a2, b1, b2, N1, N2);
+      if (st != GFFM_OK) break;
+      int64_t blocks = ceil_div(m * n, 1024);
+      if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
+      if (C1->ld != C2->ld) {
+        st = GFFM_ERR_UNSUPPORTED;
+        gffm_set_error("limb pairs must share a leading dimension");
+        break;
+      }
+      kara_ewise_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(GFFM_EW_ADD, C1->data, C2->data, C1->ld, C1->data, C2->data, C1->ld, t1.p, t2.p, ldt,
+                                                                  m, n, 0ull, N1, N2);
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) {
+        st = GFFM_ERR_CUDA;
+        gffm_set_error("kara_ewise_kernel launch failed");
+      }
+    }
+  }
+  gffm_dev_free(ctx, T);
+  return st;
 }
 
 extern "C" int32_t gffm_kmat_ewise(int32_t op, gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_mat* A2, gffm_mat* B1, gffm_mat* B2,

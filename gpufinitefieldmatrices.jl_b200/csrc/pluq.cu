@@ -1802,9 +1802,17 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
   out->pivcol.resize(r0);
   out->swp.resize(r0);
   if (r0 > 0) {
+    std::vector<uint32_t> pinv(r0);
     GFFM_CUDA(cudaMemcpyAsync(out->pivcol.data(), b.pivcol, sizeof(int) * r0, cudaMemcpyDeviceToHost, ctx->stream));
     GFFM_CUDA(cudaMemcpyAsync(out->swp.data(), b.swp, sizeof(int) * r0, cudaMemcpyDeviceToHost, ctx->stream));
+    GFFM_CUDA(cudaMemcpyAsync(pinv.data(), b.pinv, sizeof(uint32_t) * r0, cudaMemcpyDeviceToHost, ctx->stream));
     GFFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    // The pivot rule is "largest residue" (pluq_kernels.jl:189), which over a composite modulus can pick a zero divisor: its
+    // inverse is 0 (mod_inv, pluq_kernels.jl:11-31 has no answer either) and everything scaled by it is garbage.  The reference
+    // declares CuModMatrixModulusNotPrimeException (CuModMatrix.jl:23-25) for this situation; report it instead of a wrong result.
+    for (int t = 0; t < r0; ++t)
+      if (pinv[t] == 0 && N > 1)
+        GFFM_FAIL(GFFM_ERR_MODULUS_NOT_PRIME, "elimination mod %llu: pivot %d is a zero divisor (the modulus is not prime)", (unsigned long long)N, t);
   }
   return GFFM_OK;
 }

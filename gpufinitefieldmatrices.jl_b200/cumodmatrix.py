@@ -226,6 +226,19 @@ class CuModMatrix:
     def to_int(self):
         return self.Array(np.int64)
 
+    def to_u32(self):
+        """Residues as a column-major uint32 host array (half the host memory of `to_int`; used at BASELINE sizes)."""
+        return self.Array(np.uint32)
+
+    def gather_rows(self, rows_idx):
+        """Host copy (int64, len(rows_idx) x cols) of the given 0-based rows: `A[rows_idx, :]` without downloading the matrix
+        (one block copy per row into a small staging matrix, one download)."""
+        idx = [int(i) for i in rows_idx]
+        stage = CuModMatrix._new(len(idx), self.cols, self.N, like=self)
+        for t, i in enumerate(idx):
+            capi.check(self.lib.gffm_mat_copy_block(stage.h, t, 0, self.h, i, 0, 1, self.cols))
+        return stage.Array(np.int64).reshape(len(idx), self.cols)
+
     def __getitem__(self, ij):
         i, j = ij if isinstance(ij, tuple) else (ij, 0)
         v = C.c_int64(0)

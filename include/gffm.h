@@ -46,7 +46,8 @@ enum {
   GFFM_ERR_NO_DEVICE = 9,
   GFFM_ERR_UNSUPPORTED = 10,
   GFFM_ERR_INEXACT = 11,           /* InexactError from convert.(T,A), CuModMatrix.jl:70-86 */
-  GFFM_ERR_OOM = 12
+  GFFM_ERR_OOM = 12,
+  GFFM_ERR_MODULUS_NOT_PRIME = 13  /* CuModMatrixModulusNotPrimeException (CuModMatrix.jl:23-25): a pivot is a zero divisor */
 };
 
 /* host element types for upload/download */

@@ -1,0 +1,11 @@
+"""pytest configuration: the `gpu` marker (tests that need a B200; run with `-m gpu` on the GPU box, deselected with `-m "not gpu"`)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

@@ -62,9 +62,7 @@ def test_julia_shim_binds_every_symbol():
     assert not missing, f"Julia shim does not ccall: {sorted(missing)}"
 
 
-def test_plain_c_client_compiles_links_and_fails_loudly_without_gpu(tmp_path):
-    """include/gffm.h is valid ISO C (no C++ types anywhere in the boundary) and libgffm.so links from gcc; without a GPU the
-    client reports GFFM_ERR_NO_DEVICE from gffm_create (tools/c_client.c)."""
+def _build_c_client(tmp_path):
     import subprocess
     import gffm_b200 as g
     exe = str(tmp_path / "c_client")
@@ -73,11 +71,26 @@ def test_plain_c_client_compiles_links_and_fails_loudly_without_gpu(tmp_path):
                         os.path.join(ROOT, "tools", "c_client.c"), "-L" + libdir, "-lgffm", "-Wl,-rpath," + libdir, "-o", exe],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    return subprocess.run([exe], capture_output=True, text=True)
+
+
+def test_plain_c_client_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/gffm.h is valid ISO C (no C++ types anywhere in the boundary) and libgffm.so links from gcc; without a GPU the
+    client reports GFFM_ERR_NO_DEVICE from gffm_create (tools/c_client.c)."""
     import torch
-    run = subprocess.run([exe], capture_output=True, text=True)
+    run = _build_c_client(tmp_path)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "libgffm" in run.stdout
     if not torch.cuda.is_available():
         assert "no CPU fallback" in run.stdout
     else:
         assert "C = [" in run.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_client_runs_on_the_gpu(tmp_path):
+    """The same plain-C program on a B200: creates a context, uploads, multiplies through gffm_gemm, downloads and prints the product
+    (the reference's 2x3 * 3x2 mod 11 literal, test/CuModMatrix/matmul_operations_test.jl:14-67)."""
+    run = _build_c_client(tmp_path)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "C = [" in run.stdout and "no CPU fallback" not in run.stdout

@@ -619,3 +619,229 @@ def test_karatsuba_array_interface(g):
     assert (K1.N1, K1.N2) == (8191, 8191) and np.array_equal(K1.Array(), (A % 8191).astype(object))
     with pytest.raises(ValueError):
         g.KaratsubaZeros(np.float64, 2, 2, N1, N2, use_gpu=False)
+
+
+# ---------------------------------------------------------------- BASELINE configs pinned to the CPU oracle ----------------------------------------------
+# The properties above (Freivalds, linearity, closed forms, P*A*Q == L*U through our own GEMM) are strong but self-referential.
+# Here sampled ROWS of every BASELINE-size result are recomputed by the oracle (exact uint64 host arithmetic, oracle_c.matmul_mod)
+# from inputs rebuilt with the oracle's own generator and compared bit for bit -- the reference's own criterion
+# (/root/reference/test/CuModMatrix/stripe_mul_test.jl:31-50: `==` against mod.(A*B, N) on the host).
+from oracle import sampled as S  # noqa: E402  (checker only)
+from oracle import oracle_c as OC  # noqa: E402
+
+NROWS = 64
+
+
+def _check_device_generator(Bg, seed, n_rows, N, tag):
+    """Downloads Bg (uint32) after checking on 32 sampled columns that the device generator equals the oracle's."""
+    cols = S.pick_rows(Bg.cols, 32, seed=1000 + seed)
+    Bh = Bg.to_u32()
+    assert np.array_equal(Bh[:, cols].astype(np.int64), S.synth_cols(seed, cols, n_rows, N)), f"device generator != oracle generator ({tag})"
+    return Bh
+
+
+@pytest.mark.parametrize("n,N,sa,sb", [(8192, 33554393, 3, 4), (16384, 33554393, 5, 6), (16384, 65521, 5, 6), (16384, 11, 5, 6)])
+def test_gemm_baseline_sizes_sampled_rows_vs_oracle(g, n, N, sa, sb):
+    """BASELINE config 2 (8192^2 mod 33554393, seeds 3,4) and the n = 16384 metric (seeds 5,6; all three moduli): 64 rows of C bit-exact
+    vs the oracle."""
+    A = g.synth(n, n, N, sa); B = g.synth(n, n, N, sb)
+    C = g.zeros(np.float32, n, n, N); g.mul_(C, A, B)
+    rows = S.pick_rows(n, NROWS, seed=n + N % 1000)
+    A_rows = S.synth_rows(sa, rows, n, n, N)
+    assert np.array_equal(A.gather_rows(rows), A_rows)  # device generator == oracle generator on the sampled rows
+    Bh = _check_device_generator(B, sb, n, N, f"n={n}")
+    rep = S.check_product_rows(C.gather_rows(rows), A_rows, Bh, N)
+    assert rep["match"], rep
+
+
+def test_baseline_config5_plain_32768_sampled_rows_vs_oracle(g):
+    """BASELINE config 5, plain product (seeds 11, 12): 64 rows of the 32768^2 result bit-exact vs the oracle."""
+    n, N = 32768, 33554393
+    A = g.synth(n, n, N, 11); B = g.synth(n, n, N, 12)
+    C = g.zeros(np.float32, n, n, N); g.mul_(C, A, B)
+    rows = S.pick_rows(n, NROWS, seed=55)
+    A_rows = S.synth_rows(11, rows, n, n, N)
+    assert np.array_equal(A.gather_rows(rows), A_rows)
+    Bh = _check_device_generator(B, 12, n, N, "c5 plain")
+    rep = S.check_product_rows(C.gather_rows(rows), A_rows, Bh, N)
+    assert rep["match"], rep
+
+
+def test_baseline_config5_karatsuba_32768_sampled_rows_vs_oracle(g):
+    """BASELINE config 5, Karatsuba product N1 = N2 = 8191 (seeds 13-16): 64 rows of C1 + N1*C2 bit-exact vs the oracle's plain product
+    of the joined values mod N1*N2 (joined values < 2^26, so oracle_c's uint64 accumulation is exact)."""
+    n, N1, N2 = 32768, 8191, 8191
+    M = N1 * N2
+    A1 = g.synth(n, n, N1, 13); A2 = g.synth(n, n, N2, 14); B1 = g.synth(n, n, N1, 15); B2 = g.synth(n, n, N2, 16)
+    CK = g.KaratsubaZeros(np.float64, n, n, N1, N2)
+    g.KMatMul_(CK, g.KaratsubaMatrix(A1, A2, N1, N2), g.KaratsubaMatrix(B1, B2, N1, N2))
+    rows = S.pick_rows(n, NROWS, seed=56)
+    A_rows = S.synth_rows(13, rows, n, n, N1) + N1 * S.synth_rows(14, rows, n, n, N2)
+    assert np.array_equal(A1.gather_rows(rows) + N1 * A2.gather_rows(rows), A_rows)
+    Bh = _check_device_generator(B1, 15, n, N1, "c5 B1")
+    B2h = _check_device_generator(B2, 16, n, N2, "c5 B2")
+    Bh = Bh + np.uint32(N1) * B2h  # joined B, < 2^26
+    del B2h
+    want = S.product_rows(A_rows, Bh, M, in_bound=M)
+    got = CK.data1.gather_rows(rows) + N1 * CK.data2.gather_rows(rows)
+    assert np.array_equal(got, want)
+
+
+def test_baseline_config4_sampled_rows_vs_oracle(g):
+    """BASELINE config 4 (LU + inverse, 8192^2 mod 7): sampled rows of A*A^-1 (== rows of I) and of L*U (== rows of P*A) recomputed by
+    the oracle from the DOWNLOADED factors -- no GEMM of ours in the check."""
+    n, N = 8192, 7
+    lo = O.synth_matrix(9, n, n, N); up = O.synth_matrix(10, n, n, N)
+    Lo = np.tril(lo, -1) + np.eye(n, dtype=np.int64)
+    Up = np.triu(up, 1) + np.diag(1 + (np.diag(up) % 6))
+    rot = [(i + 1, ((i + 4097) % n) + 1) for i in range(0, 64)]
+    Ah = O.apply_row_perm(rot, OC.matmul_mod(Lo, Up, N))  # the input itself comes from the oracle
+    Ag = g.CuModMatrix(Ah, N)
+    ok, inv = g.is_invertible_with_inverse(Ag)
+    assert ok
+    rows = S.pick_rows(n, NROWS, seed=57)
+    rep = S.check_product_rows(np.eye(n, dtype=np.int64)[rows], Ah[rows], inv.to_u32(), N)
+    assert rep["match"], rep
+    U, L, pr, pc, rk = g.pluq_gpu_kernel(Ag, return_rank=True)
+    assert rk == n and pc == []
+    PA = O.apply_row_perm(pr, Ah)
+    rep = S.check_product_rows(PA[rows], L.gather_rows(rows), U.to_u32(), N)
+    assert rep["match"], rep
+
+
+def _config3_matrix(g, n, r, N, zero_cols, dep):
+    X = g.synth(n, r, N, 7); Y = g.synth(r, n, N, 8)
+    Ag = X * Y
+    z = g.zeros(np.float32, n, 1, N)
+    for c in zero_cols:
+        g.capi.check(Ag.lib.gffm_mat_copy_block(Ag.h, 0, c, z.h, 0, 0, n, 1))
+    c17 = g.zeros(np.float32, n, 1, N); c42 = g.zeros(np.float32, n, 1, N)
+    g.capi.check(Ag.lib.gffm_mat_copy_block(c17.h, 0, 0, Ag.h, 0, dep[1], n, 1))
+    g.capi.check(Ag.lib.gffm_mat_copy_block(c42.h, 0, 0, Ag.h, 0, dep[2], n, 1))
+    comb = c17 * 3 + c42
+    g.capi.check(Ag.lib.gffm_mat_copy_block(Ag.h, 0, dep[0], comb.h, 0, 0, n, 1))
+    return Ag
+
+
+def test_baseline_config3_sampled_rows_vs_oracle(g):
+    """BASELINE config 3 (RREF + PLUQ, 16384^2 rank-deficient mod 65521): sampled rows of L*U recomputed by the oracle from the downloaded
+    factors equal the same rows of P*A*Q (permutations applied on the host by the oracle); the RREF annihilates sampled null-space
+    relations: for the dependent column 9000 = 3*col 17 + col 4242 the RREF columns satisfy the same relation."""
+    n, N, r = 16384, 65521, 15360
+    Ag = _config3_matrix(g, n, r, N, (100, 5000, 16383), (9000, 17, 4242))
+    U, L, pr, pc, rk = g.pluq_gpu_kernel(Ag, return_rank=True)
+    Ah = Ag.to_u32()
+    rows = S.pick_rows(n, NROWS, seed=58)
+    rmap, cmap = S.perm_to_map(pr, n), S.perm_to_map(pc, n)
+    PAQ_rows = Ah[rmap[rows]][:, cmap].astype(np.int64)  # rows of P*A*Q, permutations applied on the host (oracle semantics)
+    del Ah
+    rep = S.check_product_rows(PAQ_rows, L.gather_rows(rows), U.to_u32(), N)
+    assert rep["match"], rep
+    R, piv = g.rref(Ag, return_pivots=True)
+    del U, L
+    Rh = R.to_u32().astype(np.int64)
+    assert np.array_equal(Rh[:, 9000], (3 * Rh[:, 17] + Rh[:, 4242]) % N)  # row operations preserve column relations
+    assert not Rh[:, [100, 5000, 16383]].any()
+    assert len(piv) == rk and np.array_equal(Rh[np.arange(rk), piv], np.ones(rk, dtype=np.int64))  # unit pivots ...
+    sub = Rh[:, piv]
+    assert np.count_nonzero(sub) == rk  # ... alone in their columns: reduced form
+
+
+def test_config3_shape_2048_rank_pivots_echelon_vs_oracle(g):
+    """The config-3 construction at n = 2048 (r = 1920, zero columns 100/1000/2047, column 900 = 3*col 17 + col 424), where the C oracle's
+    full echelon elimination takes seconds: rank, pivot columns, row transpositions, U and L are bit-exact vs the oracle, and the RREF is
+    the unique solution of T*R == E (T = pivot-column block of the oracle's echelon form E, unit upper triangular), checked by the oracle."""
+    n, N, r = 2048, 65521, 1920
+    Ag = _config3_matrix(g, n, r, N, (100, 1000, 2047), (900, 17, 424))
+    Ah = Ag.to_int()
+    W, Lh, perm_rows, pivcols = OC.echelon(Ah, N)
+    rk = len(pivcols)
+    assert rk <= r and 100 not in pivcols and 1000 not in pivcols and 900 not in pivcols
+    U, L, pr, piv = g.lu(Ag, return_pivots=True)
+    assert piv == pivcols
+    assert pr == perm_rows
+    assert np.array_equal(U.to_int(), W)
+    assert np.array_equal(L.to_int(), Lh)
+    assert g.rank(Ag) == rk
+    R, piv2 = g.rref(Ag, return_pivots=True)
+    assert piv2 == pivcols
+    Rh = R.to_int()
+    assert not Rh[rk:].any()
+    T = W[:rk][:, pivcols]
+    assert np.array_equal(np.triu(T, 1) + np.eye(rk, dtype=np.int64), T)
+    assert np.array_equal(OC.matmul_mod(T, Rh[:rk], N), W[:rk])
+
+
+# ---------------------------------------------------------------- round-2 additions: GEMV, limits ----------------------------------------------
+@pytest.mark.parametrize("m,k,N,P", [(1000, 3000, 4294967291, 65521), (700, 5000, 33554393, 7), (4100, 4099, 2 ** 26, 2 ** 26), (513, 70000, 65521, 65521),
+                                     (3, 5, 11, 11), (2048, 2048, 4294967291, 4294967291)])
+def test_gemv_modulus_override_and_k_split(g, m, k, N, P):
+    """mul!(z,A,x;R,P) (CuModMatrix.jl:816-836): entries are bounded by the operands' modulus N, the result is reduced mod P -- also when
+    P << N (products near 2^64 must not wrap the accumulator), with the K range split across CTAs and ragged row tails."""
+    A = O.synth_matrix(31, m, k, N); x = O.synth_matrix(32, k, 1, N).reshape(-1)
+    z = g.zeros(np.float64, m, 1, P)
+    g.gemv_(z, g.CuModMatrix(A, N), g.CuModVector(x, N), P=P)
+    want = np.array([int(sum(int(a) * int(b) for a, b in zip(A[i], x)) % P) for i in range(0, m, max(1, m // 7))])
+    assert np.array_equal(z.to_int().reshape(-1)[::max(1, m // 7)], want)
+    if N < 2 ** 31:  # full comparison through the oracle's striped GEMV
+        assert np.array_equal(z.to_int().reshape(-1), OC.matmul_mod(A, x.reshape(-1, 1), P, in_bound=N).reshape(-1))
+
+
+def test_gemv_rejects_aliasing_and_mismatch(g):
+    A = g.synth(8, 8, 11, 1); x = g.synth(8, 1, 11, 2)
+    with pytest.raises(g.GffmError):
+        g.gemv_(x, A, x)
+    with pytest.raises(g.CuModArrayModulusMismatchException):
+        g.gemv_(g.zeros(np.float32, 8, 1, 13), A, x)
+
+
+@pytest.mark.parametrize("n,N1,N2", [(777, 13 ** 4, 13 ** 3), (4096, 8191, 8191), (5, 2 ** 26, 2 ** 26), (1500, 11, 11)])
+def test_karatsuba_matvec_single_pass(g, n, N1, N2):
+    """KMatMul! on vectors / KMatMul_gemv! (KaratsubaMatrix.jl:238-300): the fused one-pass kernel equals the exact product mod N1*N2."""
+    M = N1 * N2
+    rng = np.random.default_rng(n)
+    A = rng.integers(0, M, size=(n, n + 3), dtype=np.int64); x = rng.integers(0, M, size=(n + 3,), dtype=np.int64)
+    A[0, :] = M - 1; x[:] = np.where(np.arange(n + 3) % 5 == 0, M - 1, x)
+    AK = g.KaratsubaMatrix.from_array(A, N1, N2, M); xK = g.KaratsubaMatrix.from_array(x.reshape(-1, 1), N1, N2, M)
+    zK = g.KaratsubaZeros(np.float64, n, 1, N1, N2)
+    g.KMatMul_(zK, AK, xK)
+    want = np.array([int(sum(int(a) * int(b) for a, b in zip(A[i], x)) % M) for i in range(n)], dtype=object)
+    got = np.array([int(v) for v in np.asarray(zK.Array()).reshape(-1)], dtype=object)
+    assert np.array_equal(got, want)
+
+
+def test_karatsuba_inner_dimension_above_65536(g):
+    """KMatMul! has no inner-dimension limit (KaratsubaMatrix.jl:133-204): K = 70000 runs as two chunks joined by the two-limb carry add."""
+    m, k, n, N1, N2 = 130, 70000, 140, 8191, 8191
+    M = N1 * N2
+    rng = np.random.default_rng(7)
+    A = rng.integers(0, M, size=(m, k), dtype=np.int64); B = rng.integers(0, M, size=(k, n), dtype=np.int64)
+    A[:, :100] = M - 1; B[:100, :] = M - 1
+    CK = g.KaratsubaZeros(np.float64, m, n, N1, N2)
+    g.KMatMul_(CK, g.KaratsubaMatrix.from_array(A, N1, N2, M), g.KaratsubaMatrix.from_array(B, N1, N2, M))
+    want = OC.matmul_mod(A, B, M, in_bound=M)
+    assert np.array_equal(np.asarray(CK.Array()).astype(np.int64), want)
+
+
+@pytest.mark.parametrize("N,algo_name", [(33554393, "ALGO_RNS"), (65521, "ALGO_LIMB")])
+def test_gemm_more_than_65535_columns(g, N, algo_name):
+    """Tensor-core paths with n > 65535 (CUDA grid.y limit): split / CRT launches are issued in column slabs."""
+    m, k, n = 130, 256, 66000
+    A = O.synth_matrix(41, m, k, N); B = O.synth_matrix(42, k, n, N)
+    C = g.zeros(np.float32, m, n, N)
+    g.mul_(C, g.CuModMatrix(A, N), g.CuModMatrix(B, N), algo=getattr(g.capi, algo_name))
+    assert np.array_equal(C.to_int(), OC.matmul_mod(A, B, N))
+
+
+def test_elimination_reports_zero_divisor_pivot(g):
+    """Composite modulus whose largest residue is a zero divisor: the reference's rule picks it as pivot (pluq_kernels.jl:189) and has no
+    inverse for it (mod_inv, :11-31); we raise the reference's CuModMatrixModulusNotPrimeException (CuModMatrix.jl:21) instead of returning
+    a wrong factorisation."""
+    A = g.CuModMatrix(np.array([[8, 1], [3, 5]]), 9 + 1)  # mod 10: pivot 8 = max, gcd(8, 10) = 2
+    with pytest.raises(g.CuModMatrixModulusNotPrimeException):
+        g.inverse(A)
+    with pytest.raises(g.CuModMatrixModulusNotPrimeException):
+        g.pluq_gpu_kernel(A)
+    B = np.array([[9, 0], [3, 7]])  # pivots 9 and 7: both units mod 10 -> a valid factorisation over Z/10
+    U, L, pr, pc = g.pluq_gpu_kernel(g.CuModMatrix(B, 10))
+    assert np.array_equal((L.to_int() @ U.to_int()) % 10, O.apply_col_perm(pc, O.apply_row_perm(pr, B)))

@@ -237,3 +237,22 @@ def test_hensel_lift_oracle():
         I = np.eye(n, dtype=object)
         assert np.array_equal(np.array(A, dtype=object).dot(T) % M, I)
         assert np.array_equal(np.array(T % p, dtype=np.int64), T0)
+
+
+def test_sampled_row_helpers_match_full_oracle():
+    """oracle/sampled.py (used by the BASELINE-size GPU tests and bench.py's parity_check) agrees with the full-matrix oracle."""
+    from oracle import sampled as S
+    N = 33554393
+    A = O.synth_matrix(5, 300, 200, N); B = O.synth_matrix(6, 200, 150, N)
+    rows = S.pick_rows(300, 64, seed=1)
+    assert len(rows) == 64 and rows[0] == 0 and rows[-1] == 299 and len(set(rows.tolist())) == 64
+    assert np.array_equal(S.synth_rows(5, rows, 300, 200, N), A[rows])
+    assert np.array_equal(S.synth_cols(6, [0, 7, 149], 200, N), B[:, [0, 7, 149]])
+    C = O.exact_matmul_mod(A, B, N)
+    assert S.check_product_rows(C[rows], A[rows], B, N)["match"]
+    bad = C[rows].copy(); bad[3, 5] ^= 1
+    assert S.check_product_rows(bad, A[rows], B, N) == {"rows": 64, "cols": 150, "mismatches": 1, "match": False}
+    pairs = [(1, 5), (2, 5), (7, 3), (5, 1)]
+    M = O.synth_matrix(9, 8, 8, 97)
+    assert np.array_equal(M[S.perm_to_map(pairs, 8)], O.apply_row_perm(pairs, M))
+    assert np.array_equal(M[:, S.perm_to_map(pairs, 8)], O.apply_col_perm(pairs, M))
