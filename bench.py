@@ -191,6 +191,124 @@ def run_reference(args):
     return 0
 
 
+def run_extras(g, ctx, torch, np, stream, A, n, N, peaks):
+    """config.extras of the single-GPU line: other moduli, GEMV, the reference's n = 5000 timing cases, PLUQ / RREF / inverse at the metric
+    size with the PLUQ roofline entry (BASELINE metric: "...; PLUQ n=16384 s")."""
+    extras = {}
+    roofline_pluq = None
+    def dev_time(fn, reps, warm=1):
+        """median / min wall time (s) of fn() bracketed by device synchronisation (the elimination calls block on their own)"""
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+        return statistics.median(ts), min(ts)
+
+    def ev_time(fn, reps, warm=2):
+        """mean device time (ms) of fn() over `reps` back-to-back calls (CUDA events on the library stream)"""
+        for _ in range(warm):
+            fn()
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(reps):
+            fn()
+        a1.record(stream); torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps
+
+    # other moduli of the metric size (fresh product each time)
+    for N2 in (11, 65521):
+        A_, B_ = g.synth(n, n, N2, SEED_A, ctx=ctx), g.synth(n, n, N2, SEED_B, ctx=ctx)
+        C_ = g.zeros(np.float32, n, n, N2, ctx=ctx)
+
+        def prod():
+            A_.touch(); B_.touch()
+            g.mul_(C_, A_, B_)
+        t_ = ev_time(prod, 5, warm=3)
+        extras[f"matmul_n{n}_mod{N2}"] = {"ms": t_, "GOPS": 2.0 * n ** 3 / t_ / 1e6}
+        del A_, B_, C_
+    # GEMV at the metric size: HBM-bound, 4 bytes per matrix element
+    z_ = g.zeros(np.float32, n, 1, N, ctx=ctx); x_ = g.synth(n, 1, N, 77, ctx=ctx)
+    t_ = ev_time(lambda: g.gemv_(z_, A, x_), 20, warm=3)
+    extras[f"gemv_n{n}_mod{N}"] = {"ms": t_, "GBps": 4.0 * n * n / (t_ * 1e-3) / 1e9, "hbm_peak_GBps": peaks["hbm_gbs"],
+                                    "frac_of_hbm_peak": 4.0 * n * n / (t_ * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": 4 * n * n,
+                                    "note": "A (1 GiB) is larger than L2; 20 back-to-back products"}
+    del z_, x_
+    # the reference's only published cases (test/CuModMatrix/timing_test.jl:21-52: n = 5000, N = 11; RTX 3070 comments
+    # < 0.001 s add!, < 0.001 s scalar mul!, < 0.2 s mul!, < 0.001 s mat-vec) from our path
+    n5 = 5000
+    A5, B5 = g.synth(n5, n5, 11, 1, ctx=ctx), g.synth(n5, n5, 11, 2, ctx=ctx)
+    C5 = g.zeros(np.float32, n5, n5, 11, ctx=ctx); z5 = g.zeros(np.float32, n5, 1, 11, ctx=ctx); x5 = g.synth(n5, 1, 11, 3, ctx=ctx)
+
+    def mul5():
+        A5.touch(); B5.touch()
+        g.mul_(C5, A5, B5)
+    extras["reference_timing_cases_n5000_mod11"] = {
+        "source": "reference test/CuModMatrix/timing_test.jl:21-52 (author's RTX 3070 comments: add! < 1 ms, scalar mul! < 1 ms, mul! < 200 ms (F32) / < 1000 ms (F64), mat-vec < 1 ms)",
+        "add_ms": ev_time(lambda: g.add_(C5, A5, B5), 20), "scalar_mul_ms": ev_time(lambda: g.capi.check(C5.lib.gffm_ewise(g.capi.EW_SMUL, C5.h, A5.h, None, 2, 0)), 20),
+        "mul_ms": ev_time(mul5, 10), "matvec_ms": ev_time(lambda: g.gemv_(z5, A5, x5), 20)}
+    del A5, B5, C5, z5, x5
+    # elimination at the metric size: PLUQ, RREF, inverse; warm, 3 repetitions, median (BASELINE metric: "PLUQ n=16384 s")
+    for Np in (65521, N):
+        A_ = g.synth(n, n, Np, 9, ctx=ctx)
+        holder = {}
+
+        def do_pluq():
+            holder["r"] = g.pluq_gpu_kernel(A_, return_rank=True)
+        l0_ = ctx.launch_count()
+        med, best = dev_time(do_pluq, 3)
+        launches_pluq = (ctx.launch_count() - l0_) // 4
+        rk_ = holder["r"][4]
+        holder.clear()
+        med_r, best_r = dev_time(lambda: holder.__setitem__("r", g.rref(A_)), 3)
+        holder.clear()
+        med_i, best_i = dev_time(lambda: holder.__setitem__("r", g.inverse(A_)), 3)
+        holder.clear()
+        ctx.set_profiling(True)
+        do_pluq(); ph = ctx.last_timings(); holder.clear()
+        ctx.set_profiling(False)
+        Lb = 1 if Np <= 256 else (2 if Np <= 65536 else None)
+        extras[f"pluq_n{n}_mod{Np}"] = {"seconds": med, "seconds_best": best, "rank": rk_, "rref_seconds": med_r, "rref_seconds_best": best_r,
+                                         "inverse_seconds": med_i, "inverse_seconds_best": best_i, "us_per_pivot": med / max(rk_, 1) * 1e6,
+                                         "kernel_launches_per_factorisation": int(launches_pluq),
+                                         "phases_ms_profiled_call": {"panels_and_in_block_updates": ph[0] if len(ph) > 0 else None,
+                                                                     "triangular_solves": ph[1] if len(ph) > 1 else None, "schur_gemms": ph[2] if len(ph) > 2 else None},
+                                         "reps": 3, "timing": "median wall time between device synchronisations, warm (second call onwards)"}
+        if Np == 65521:
+            fm = n ** 3 / 3.0  # m n r - (m + n) r^2 / 2 + r^3 / 3 for m = n = r (SURVEY 8d)
+            ip8 = 4542.2
+            try:
+                ip8 = float(json.load(open(os.path.join(ROOT, "profiles", "int8_peak.json")))["int8_tops_sustained"])
+            except Exception:
+                pass
+            peak_fm = ip8 * 1e12 / (2.0 * Lb * Lb)  # field mul-adds/s if all of them ran as L^2 int8 MMAs at the tensor peak
+            roofline_pluq = {"bound": "latency (n sequential pivots; the Schur updates are tensor-bound)", "kernel": "pluq_panel_ll_kernel",
+                             "workload": f"PLUQ {n}x{n} mod {Np}, full rank", "field_muladds": fm, "achieved": fm / med / 1e12, "peak": peak_fm / 1e12,
+                             "unit": "T field mul-add/s", "frac": fm / med / peak_fm, "seconds": med, "us_per_pivot": med / max(rk_, 1) * 1e6,
+                             "note": "peak = measured int8 tensor peak / (2 L^2), L = 2 eight-bit limbs; the panel kernel (one thread-block cluster, "
+                                     "argmax + row exchange per pivot) bounds the factorisation, see DESIGN.md section 6"}
+        del A_
+
+    return extras, roofline_pluq
+
+
+def int8_units(n, R, P, kara=False):
+    """int8 MMA units per inner-dimension step of one product with inputs < R (1 / 4 for one / two positional limbs, else the RNS modulus count)."""
+    if not kara and R <= 256:
+        return 1
+    if not kara and R <= 65536:
+        return 4
+    need = (n * (R - 1) ** 2) if kara else 2 * n * (R // 2) ** 2
+    need += (need >> 6) + 2
+    mods = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197]
+    prod, units = 1, 0
+    while prod <= need:
+        prod *= mods[units]; units += 1
+    return units
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,19 +317,17 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--modulus", type=int, default=MOD_DEFAULT)
-    ap.add_argument("--panels", default="8", help="column panels of B for the pipelined NCCL broadcast (N > 1); several values: "
-                    "the fastest is picked during the untimed warm-up")
-    ap.add_argument("--gemm-ctas", default="0", help="cap on the persistent GEMM grid (0 = all SMs) so that the concurrent NCCL "
-                    "kernels find free SMs (N > 1); several values: the fastest is picked during the untimed warm-up (measured on 8 B200: "
-                    "148 > 140 > 132 CTAs, profiles/r01_notes.md, hence the default)")
-    ap.add_argument("--grid-cols", type=int, default=1, help="N > 1: column groups of a 2-D process grid (1 = row blocks of A with a full "
-                    "broadcast of B; pc > 1: rank (i, j) multiplies row block i of A with column range j of B and receives only that range)")
-    ap.add_argument("--bcast", default="broadcast", choices=["broadcast", "scatter_allgather"],
-                    help="how B is replicated every step (N > 1): ncclBroadcast per panel, or scatter + in-place all-gather per panel")
-    ap.add_argument("--e2e-mode", default="replicated", choices=["replicated", "sliced"],
-                    help="N > 1 end-to-end arm: 'replicated' = every rank uploads its A shard and all of B from its host copy (default); "
-                         "'sliced' additionally times: every rank uploads its A shard and 1/N of each B panel, the panels are completed by an "
-                         "in-place NCCL all-gather and consumed by gffm_gemm_panels (opt-in until measured on 8 GPUs)")
+    ap.add_argument("--workload", default="matmul", choices=["matmul", "karatsuba"],
+                    help="matmul: C = A*B mod N (the BASELINE metric); karatsuba: two-limb product mod N1*N2 (BASELINE config 5 with --n 32768)")
+    ap.add_argument("--n1", type=int, default=8191, help="Karatsuba limb modulus N1 (SURVEY 8d: N1 = N2 = 8191)")
+    ap.add_argument("--n2", type=int, default=8191)
+    ap.add_argument("--mg", default="cabi", choices=["cabi", "python"],
+                    help="N > 1: 'cabi' = the library's multi-GPU layer (gffm_mg_gemm / gffm_mg_kmat_mul, csrc/mg.cu); 'python' = the round-1 driver "
+                         "(torch.distributed broadcast of B in panels + gffm_gemm_panels), kept for A/B comparisons")
+    ap.add_argument("--transport", default="tune",
+                    help="N > 1, --mg cabi: p2p_planes | nccl_planes | nccl_bcast | auto, or 'tune' (default): each available transport is tried for a few "
+                         "untimed steps and the fastest is used for the timed region (trial times in config.warmup_trials_ms)")
+    ap.add_argument("--panels", type=int, default=8, help="--mg python: column panels of B per broadcast")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extras", action="store_true", help="(default at N = 1; kept for compatibility)")
@@ -223,6 +339,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # the multi-GPU layer's streams must not share hardware queues (flag waits)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -246,211 +363,279 @@ def main():
             os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, N = args.n, args.modulus
+    kara = args.workload == "karatsuba"
+    N1, N2 = args.n1, args.n2
     W = max(3, args.warmup)
     K = max(1, args.steps)
     ctx = g.Context(local)
     stream = torch.cuda.Stream(device=local)
     ctx.set_stream(stream.cuda_stream)
     peaks = load_peaks()
+    dev = f"cuda:{local}"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
-        # ---- resident inputs: A row block of this rank, B (broadcast from rank 0 each step when world > 1) -----------
-        mg = g.multigpu
-        pr, pc = mg.process_grid(world, args.grid_cols if world > 1 else 1)
-        gi, gj = mg.grid_coords(rank, pr, pc)
-        r0, r1 = mg.row_block(n, pr, gi)
-        mloc = r1 - r0
-        cl0, cl1 = mg.col_range(n, pc, gj, align=mg.PANEL_ALIGN)
-        ncl = cl1 - cl0  # columns of B / C this rank works on (all of them unless --grid-cols > 1)
+    def allmax(x):
         if world == 1:
-            A = g.synth(n, n, N, SEED_A, ctx=ctx)
-        else:
-            Afull = g.synth(n, n, N, SEED_A, ctx=ctx)
-            A = g.zeros(np.float32, mloc, n, N, ctx=ctx)
-            g.capi.check(A.lib.gffm_mat_copy_block(A.h, 0, 0, Afull.h, r0, 0, mloc, n))
-            ctx.sync()
-            del Afull
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allmin_flag(ok):
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() == 1)
+
+    with torch.cuda.stream(stream):
+        mg = g.multigpu
+        r0, r1 = mg.row_block(n, world, rank)
+        mloc = r1 - r0
         ldb = ((n + 31) // 32) * 32
-        Bt = torch.zeros((n, ldb), dtype=torch.int32, device=f"cuda:{local}")  # column-major n x n, leading dim ldb
-        Ball = g.CuModMatrix.wrap_device(Bt.data_ptr(), n, n, ldb, N, ctx=ctx)
-        B = Ball if pc == 1 else g.CuModMatrix.wrap_device(Bt.data_ptr() + 4 * cl0 * ldb, n, ncl, ldb, N, ctx=ctx)  # this rank's column range
-        if rank == 0:
-            Bs = g.synth(n, n, N, SEED_B, ctx=ctx)
-            g.copy_(Ball, Bs)
+
+        def shard_of(seed, modulus):
+            """this rank's row block of the synthetic n x n matrix (device generator, checked against the oracle's by parity_check)"""
+            if world == 1:
+                return g.synth(n, n, modulus, seed, ctx=ctx)
+            full = g.synth(n, n, modulus, seed, ctx=ctx)
+            sh = g.zeros(np.float32, mloc, n, modulus, ctx=ctx)
+            g.capi.check(sh.lib.gffm_mat_copy_block(sh.h, 0, 0, full.h, r0, 0, mloc, n))
             ctx.sync()
-            del Bs
-        C = g.zeros(np.float32, mloc, ncl, N, ctx=ctx)
-        col_groups = mg.make_column_groups(dist, world, pc, src=0) if pc > 1 else None
-        # N > 1: NCCL broadcast of B in column panels on a communication stream; ONE gffm_gemm_panels call per step consumes them
-        # (split of panel p+1 / CRT of panel p under the GEMM of panel p; the next step's broadcast runs under this step's GEMMs)
-        pan_cands = [int(x) for x in str(args.panels).split(",")] if world > 1 else [1]
-        cta_cands = [int(x) for x in str(args.gemm_ctas).split(",")] if world > 1 else [0]
+            del full
+            return sh
+
+        def b_matrix(seed, modulus):
+            """B: column-major n x n in a torch buffer (so that torch.distributed can replicate it for the verification); data on rank 0 only"""
+            t = torch.zeros((n, ldb), dtype=torch.int32, device=dev)
+            m_ = g.CuModMatrix.wrap_device(t.data_ptr(), n, n, ldb, modulus, ctx=ctx)
+            if rank == 0:
+                src = g.synth(n, n, modulus, seed, ctx=ctx)
+                g.copy_(m_, src)
+                ctx.sync()
+                del src
+            return t, m_
+
+        if not kara:
+            A = shard_of(SEED_A, N)
+            Bt, B = b_matrix(SEED_B, N)
+            C = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+            touch_inputs = lambda: A.touch()  # noqa: E731  every step is a FRESH product: the cached 8-bit planes of A are rebuilt; B is external memory (never cached)
+        else:
+            A1 = shard_of(13, N1); A2 = shard_of(14, N2)
+            B1t, B1 = b_matrix(15, N1); B2t, B2 = b_matrix(16, N2)
+            AK = g.KaratsubaMatrix(A1, A2, N1, N2); BK = g.KaratsubaMatrix(B1, B2, N1, N2)
+            CK = g.KaratsubaZeros(np.float64, mloc, n, N1, N2, ctx=ctx)
+            C = CK.data1
+
+            def touch_inputs():
+                A1.touch(); A2.touch()
+        torch.cuda.synchronize()
+        b_ready = torch.cuda.Event()
+        b_ready.record(stream)  # B is complete from here on: the distribution of step t+1 may run under the GEMMs of step t
+        torch.cuda.synchronize()
+
+        mgpu = None
         bm = None
-
-        def make_bm(npanels):
-            pans = mg.col_panels(ncl, npanels, align=mg.PANEL_ALIGN)  # relative to this rank's column range
-            if world == 1:
-                return pans, None
-            deliver = mg.grid_deliver(dist, Bt, col_groups, rank, pc, n, src=0, align=mg.PANEL_ALIGN) if pc > 1 else None
-            return pans, mg.BroadcastMatmul(torch, dist, C, A, B, Bt, pans, src=0, collective=args.bcast, deliver=deliver)
-
-        def step():
-            A.touch()  # every step is a FRESH product: the cached 8-bit planes of A are rebuilt (B is external memory, never cached)
-            if world == 1:
-                g.mul_(C, A, B)
-            else:
-                bm.step()
-
         tune = {}
-        choice = (pan_cands[0], cta_cands[0])
-        if world > 1 and len(pan_cands) * len(cta_cands) > 1:  # untimed: pick (panels, GEMM grid cap) by a short trial of each
-            for npan_c in pan_cands:
-                panels, bm = make_bm(npan_c)
-                for cc in cta_cands:
-                    ctx.set_gemm_ctas(cc)
+        transport_used = None
+        if world > 1 and args.mg == "cabi":
+            mgpu = mg.MultiGpu.from_torch_distributed(dist, ctx)
+
+            def step():
+                touch_inputs()
+                if kara:
+                    mgpu.kmat_mul(CK, AK, BK, root=0, b_ready=b_ready.cuda_event)
+                else:
+                    mgpu.gemm(C, A, B, root=0, b_ready=b_ready.cuda_event)
+
+            names = {"p2p_planes": g.capi.MG_P2P_PLANES, "nccl_planes": g.capi.MG_NCCL_PLANES, "nccl_bcast": g.capi.MG_NCCL_BCAST, "auto": g.capi.MG_AUTO}
+            cands = ["p2p_planes", "nccl_planes", "nccl_bcast"] if args.transport == "tune" else [t.strip() for t in args.transport.split(",")]
+            best = None
+            for tname in cands:
+                ok_t = True
+                try:
+                    mgpu.set_transport(names[tname])
                     for _ in range(2):
                         step()
-                    bm.finish(); barrier()
-                    a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
-                    a0.record(stream)
-                    for _ in range(6):
-                        step()
-                    bm.finish(); a1.record(stream); barrier()
-                    tt = torch.tensor([a0.elapsed_time(a1) / 6], dtype=torch.float64, device=f"cuda:{local}")
-                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                    tune[(npan_c, cc)] = float(tt.item())
-            choice = min(tune, key=tune.get)  # identical on every rank (all-reduced times)
-        panels, bm = make_bm(choice[0])
-        ctx.set_gemm_ctas(choice[1])
-        npan = len(panels)
-        pan = panels[0][1] - panels[0][0]
+                    mgpu.barrier()
+                except g.GffmError as ex:
+                    ok_t = False
+                    tune[tname] = f"unavailable: {str(ex)[:160]}"
+                if not allmin_flag(ok_t):  # a transport is used only if every rank can use it
+                    tune.setdefault(tname, "unavailable on another rank")
+                    continue
+                if len(cands) == 1:
+                    best = tname
+                    break
+                barrier()
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for _ in range(8):
+                    step()
+                a1.record(stream); barrier()
+                tune[tname] = allmax(a0.elapsed_time(a1) / 8)
+                if best is None or tune[tname] < tune[best]:
+                    best = tname
+            if best is None:
+                raise SystemExit("no multi-GPU transport is usable: " + json.dumps(tune))
+            mgpu.set_transport(names[best])
+            transport_used = best
+        elif world > 1:
+            if kara:
+                def step():
+                    touch_inputs()
+                    mg.sharded_kmat_mul(dist, B1t, B2t, lambda: g.KMatMul_(CK, AK, BK), src=0)
+                transport_used = "python: dist.broadcast(B1, B2) then gffm_kmat_mul"
+            else:
+                panels = mg.col_panels(n, args.panels, align=mg.PANEL_ALIGN)
+                bm = mg.BroadcastMatmul(torch, dist, C, A, B, Bt, panels, src=0)
+
+                def step():
+                    touch_inputs()
+                    bm.step()
+                transport_used = f"python: dist.broadcast in {len(panels)} panels + gffm_gemm_panels"
+        else:
+            def step():
+                touch_inputs()
+                if kara:
+                    g.KMatMul_(CK, AK, BK)
+                else:
+                    g.mul_(C, A, B)
+
+        def drain():
+            if bm is not None:
+                bm.finish()
 
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         for _ in range(W):
             step()
-        barrier()
+        drain(); barrier()
         if rank == 0:
             sampler.mark()
-        ctx.set_profiling(True)
+        ctx.set_profiling(not kara)  # CUDA events around every tensor-core GEMM launch of the timed steps (the Karatsuba product has three kinds)
         l0 = ctx.launch_count()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
         for _ in range(K):
             step()
-        if bm is not None:
-            bm.finish()
+        drain()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1) / K
         launches = ctx.launch_count() - l0
-        phase_ms = ctx.last_timings()  # phases of the LAST timed step: [split, tcgen05 gemm, crt]
+        phase_ms = ctx.last_timings() if not kara else []  # phases of the LAST timed step: [split, tcgen05 gemm, crt] or [0, sum of GEMM launches, launches]
         clocks = sampler.stop() if rank == 0 else None
         ctx.set_profiling(False)
+        mg_error = None
+        if mgpu is not None:
+            try:
+                mgpu.barrier()
+            except g.GffmError as ex:
+                mg_error = str(ex)[:300]
+        ms = allmax(ms)
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local}")
+            lt = torch.tensor([launches], dtype=torch.int64, device=dev)
             dist.all_reduce(lt, op=dist.ReduceOp.SUM)
             launches = int(lt.item())
         checksum = C.checksum()
         value = 2.0 * n ** 3 / (ms * 1e-3) / 1e9
+
+        # ---- every rank: the sharded result == the single-GPU product of its row block with the whole B (replicated here for the check) ----
         shard_ok = None
-        if world > 1:  # every rank: the pipelined, broadcast-fed shard == the plain product of its row block with the B it received
-            Cref = g.zeros(np.float32, mloc, ncl, N, ctx=ctx)
-            g.mul_(Cref, A, B)
-            same_c = C.equals(Cref)
-            # ... and the B it received is the source's: rank 0 publishes the checksum of every column range
-            src_sums = torch.zeros(pc, dtype=torch.int64, device=f"cuda:{local}")
-            if rank == 0:
-                for j in range(pc):
-                    a, b = mg.col_range(n, pc, j, align=mg.PANEL_ALIGN)
-                    Bj = Ball if pc == 1 else g.CuModMatrix.wrap_device(Bt.data_ptr() + 4 * a * ldb, n, b - a, ldb, N, ctx=ctx)
-                    src_sums[j] = Bj.checksum() & 0x7FFFFFFFFFFFFFFF
-            dist.broadcast(src_sums, src=0)
-            same_b = int(src_sums[gj].item()) == (B.checksum() & 0x7FFFFFFFFFFFFFFF)
-            ok = torch.tensor([1 if (same_c and same_b) else 0], dtype=torch.int32, device=f"cuda:{local}")
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            shard_ok = bool(ok.item() == 1)
-            del Cref
+        if world > 1:
+            if kara:
+                dist.broadcast(B1t, src=0); dist.broadcast(B2t, src=0)
+                torch.cuda.synchronize()
+                B1.touch(); B2.touch()
+                CR = g.KaratsubaZeros(np.float64, mloc, n, N1, N2, ctx=ctx)
+                g.KMatMul_(CR, AK, BK)
+                same_c = CK.data1.equals(CR.data1) and CK.data2.equals(CR.data2)
+                del CR
+            else:
+                dist.broadcast(Bt, src=0)
+                torch.cuda.synchronize()
+                B.touch()
+                Cref = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+                g.mul_(Cref, A, B)
+                same_c = C.equals(Cref)
+                del Cref
+            shard_ok = allmin_flag(same_c and mg_error is None)
 
         # ---- parity of the TIMED result against the CPU oracle: sampled rows of this rank's C (the output of the last timed step),
-        # recomputed by oracle_c.matmul_mod from rows of A rebuilt with the oracle's generator and the B this rank multiplied with
-        # (downloaded; 32 of its columns are checked against the oracle's generator).  Reference criterion: `==` against the host
-        # product, /root/reference/test/CuModMatrix/stripe_mul_test.jl:31-50.
+        # recomputed by oracle_c.matmul_mod from rows of A rebuilt with the oracle's generator and the B held by rank 0 (downloaded;
+        # 32 of its columns are checked against the oracle's generator).  Reference criterion: `==` against the host product,
+        # /root/reference/test/CuModMatrix/stripe_mul_test.jl:31-50.
         parity = None
         if not args.no_parity:
             from oracle import sampled as S
             nrows = max(8, args.parity_rows // world) if world > 1 else args.parity_rows
             rows_loc = S.pick_rows(mloc, nrows, seed=17 + rank)
             t0p = time.perf_counter()
-            A_rows = S.synth_rows(SEED_A, rows_loc + r0, n, n, N)
-            gen_ok = bool(np.array_equal(A.gather_rows(rows_loc), A_rows))
-            Bh = B.to_u32()
-            cols_s = S.pick_rows(ncl, 32, seed=99)
-            gen_ok = gen_ok and bool(np.array_equal(Bh[:, cols_s].astype(np.int64), S.synth_cols(SEED_B, cols_s + cl0, n, N)))
-            rep = S.check_product_rows(C.gather_rows(rows_loc), A_rows, Bh, N)
+            cols_s = S.pick_rows(n, 32, seed=99)
+            if not kara:
+                A_rows = S.synth_rows(SEED_A, rows_loc + r0, n, n, N)
+                gen_ok = bool(np.array_equal(A.gather_rows(rows_loc), A_rows))
+                Bh = B.to_u32()  # every rank holds B after the shard check (world > 1) / owns it (world == 1)
+                gen_ok = gen_ok and bool(np.array_equal(Bh[:, cols_s].astype(np.int64), S.synth_cols(SEED_B, cols_s, n, N)))
+                rep = S.check_product_rows(C.gather_rows(rows_loc), A_rows, Bh, N)
+            else:
+                M_ = N1 * N2
+                A_rows = S.synth_rows(13, rows_loc + r0, n, n, N1) + N1 * S.synth_rows(14, rows_loc + r0, n, n, N2)
+                gen_ok = bool(np.array_equal(A1.gather_rows(rows_loc) + N1 * A2.gather_rows(rows_loc), A_rows))
+                B1h = B1.to_u32(); B2h = B2.to_u32()
+                gen_ok = gen_ok and bool(np.array_equal(B1h[:, cols_s].astype(np.int64), S.synth_cols(15, cols_s, n, N1)))
+                gen_ok = gen_ok and bool(np.array_equal(B2h[:, cols_s].astype(np.int64), S.synth_cols(16, cols_s, n, N2)))
+                Bh = B1h + np.uint32(N1) * B2h
+                del B1h, B2h
+                rep = S.check_product_rows(CK.data1.gather_rows(rows_loc) + N1 * CK.data2.gather_rows(rows_loc), A_rows, Bh, M_, in_bound=M_)
             del Bh
             ok_all, rows_all = rep["match"] and gen_ok, rep["rows"]
             if world > 1:
-                tt = torch.tensor([1 if ok_all else 0, -rep["rows"]], dtype=torch.int64, device=f"cuda:{local}")
-                dist.all_reduce(tt[0:1], op=dist.ReduceOp.MIN)
-                rr = torch.tensor([rep["rows"]], dtype=torch.int64, device=f"cuda:{local}")
+                ok_all = allmin_flag(ok_all)
+                rr = torch.tensor([rep["rows"]], dtype=torch.int64, device=dev)
                 dist.all_reduce(rr, op=dist.ReduceOp.SUM)
-                ok_all, rows_all = bool(tt[0].item() == 1), int(rr.item())
+                rows_all = int(rr.item())
             parity = {"rows": rows_all, "cols": rep["cols"], "match": bool(ok_all), "checker": "oracle_c.matmul_mod (exact uint64 host arithmetic)",
                       "what": "rows of the C produced by the last timed step" + ("" if world == 1 else " (every rank checks rows of its own shard)"),
                       "inputs_match_oracle_generator": gen_ok, "seconds": time.perf_counter() - t0p}
 
-        # ---- roofline of the dominant kernel (tcgen05 GEMM): a few more profiled steps, kernel-only durations --------
-        gemm_ms = [phase_ms[1]] if len(phase_ms) >= 2 else []
-        ctx.set_profiling(True)
-        for _ in range(3):
-            if world == 1:
-                g.mul_(C, A, B)
-            else:
-                g.capi.check(C.lib.gffm_gemm_block(C.h, 0, 0, A.h, 0, 0, B.h, 0, 0, mloc, pan, n, 0, 0, g.capi.GEMM_STORE, g.capi.ALGO_AUTO))
-            pm = ctx.last_timings()
-            if len(pm) >= 2:
-                gemm_ms.append(pm[1])
-        ctx.set_profiling(False)
-        bits = (N - 1).bit_length()
-        if N <= 256:
-            units = 1
-        elif N <= 65536:
-            units = 4
-        else:  # RNS: number of 8-bit moduli with product > 2*K*(N/2)^2
-            need = 2 * n * (N // 2) ** 2
-            need += (need >> 16) + 2
-            mods = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197]
-            prod, units = 1, 0
-            while prod <= need:
-                prod *= mods[units]; units += 1
-        cols_per_launch = ncl if world == 1 else pan
-        int8_ops = units * 2.0 * mloc * cols_per_launch * n
-        # launch duration of the dominant kernel INSIDE the timed region (CUDA events of the last timed step): one launch per step
-        # at N = 1; at N > 1 the per-panel launches of the last step (phase_ms = [0, sum of the launch durations, launches]).
-        # The stand-alone launches after the region are kept as a second, informational figure.
-        after_region = statistics.mean(gemm_ms[1:]) if len(gemm_ms) > 1 else None
-        gemm_avg = None
+        # ---- roofline of the dominant kernel (tcgen05 GEMM) -------------------------------------------------------------------------
+        if kara:
+            units = int8_units(n, N1, N1 * N2, kara=True) + int8_units(n, N1 + N2, N2) + int8_units(n, N2, N2)
+        else:
+            units = int8_units(n, N, N)
+        per_rank_ops = units * 2.0 * mloc * n * n
+        gemm_ms_step = None   # device time of the tensor-core GEMM launches of ONE step on this rank
+        n_gemm_launches = None
         try:
-            if world == 1 and len(phase_ms) >= 2 and phase_ms[1] > 0:
-                gemm_avg = float(phase_ms[1])
-            elif world > 1 and len(phase_ms) >= 3 and phase_ms[1] > 0 and phase_ms[2] >= 1:
-                gemm_avg = float(phase_ms[1]) / float(phase_ms[2])
+            if not kara and world == 1 and len(phase_ms) >= 2 and phase_ms[1] > 0:
+                gemm_ms_step, n_gemm_launches = float(phase_ms[1]), 1
+            elif not kara and len(phase_ms) >= 3 and phase_ms[1] > 0 and phase_ms[2] >= 1:
+                gemm_ms_step, n_gemm_launches = float(phase_ms[1]), int(phase_ms[2])
         except Exception:
-            gemm_avg = None
-        if gemm_avg is None:
-            gemm_avg = after_region if after_region else (statistics.mean(gemm_ms) if gemm_ms else None)
-        achieved = int8_ops / (gemm_avg * 1e-3) / 1e12 if gemm_avg else None
+            gemm_ms_step = None
+        after_region = None
+        if not kara and world == 1:  # stand-alone launches after the region: second, informational figure
+            ctx.set_profiling(True)
+            ts_ = []
+            for _ in range(3):
+                g.mul_(C, A, B)
+                pm = ctx.last_timings()
+                if len(pm) >= 2:
+                    ts_.append(pm[1])
+            ctx.set_profiling(False)
+            after_region = statistics.mean(ts_) if ts_ else None
+        if gemm_ms_step is None and kara:
+            gemm_ms_step = ms  # the three sub-product GEMMs are ~all of the step; per-kernel split in profiles/
+        achieved = per_rank_ops / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step else None
         int8_peak = 2.0 * peaks["bf16"]
         sustained_random = None
         peak_src = f"2 x bf16 dense {peaks['bf16']} TFLOP/s, {peaks['src']} (proxy: no int8 entry in MEASURED_PEAKS.json)"
@@ -467,58 +652,51 @@ def main():
                 pass
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if world == 1 and n == N_DEFAULT and os.path.exists(tp):  # the ncu capture is of the full single-GPU launch: meaningless for panel launches
+        if world == 1 and n == N_DEFAULT and not kara and os.path.exists(tp):  # the ncu capture is of the full single-GPU launch
             try:
                 traffic = json.load(open(tp)).get("gemm_tc_kernel_rns_dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<SchemeRNS>" if N > 65536 else "gemm_tc_kernel<limb>",
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<SchemeRNS>" if (kara or N > 65536) else "gemm_tc_kernel<limb>",
                     "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": (achieved / int8_peak) if achieved else None,
-                    "traffic": traffic, "launch_ms": gemm_avg, "launch_ms_standalone_after_region": after_region,
-                    "int8_mma_units_per_k_step": units,
+                    "traffic": traffic, "launch_ms": (gemm_ms_step / n_gemm_launches) if (gemm_ms_step and n_gemm_launches) else gemm_ms_step,
+                    "gemm_launches_per_step_per_rank": n_gemm_launches, "gemm_ms_per_step_per_rank": gemm_ms_step,
+                    "launch_ms_standalone_after_region": after_region, "int8_mma_units_per_k_step": units,
+                    "achieved_is": "per GPU (rank 0): executed int8 ops of this rank's GEMM launches of the last timed step / their CUDA-event durations",
                     "peak_source": peak_src,
-                    # same microbenchmark with uniformly random operand bytes, run back to back for seconds: what the tensor pipe
-                    # sustains under the board power cap when NOTHING but MMAs runs (informational; frac uses the higher peak)
                     "peak_sustained_random_operands": sustained_random,
                     "frac_of_sustained_random": (achieved / sustained_random) if (achieved and sustained_random) else None,
                     "phases_ms_last_step": phase_ms}
 
-        # ---- e2e through the public API with host buffers (rank-local shard; H2D A,B + GEMM + D2H C per step) --------
+        # ---- e2e through the public API with HOST buffers (pinned): per step H2D of the inputs, the product, D2H of the result ----------
         e2e = None
-        if not args.no_e2e:
-            hA = torch.empty((n, mloc), dtype=torch.int32).pin_memory()   # column-major mloc x n
-            hB = torch.empty((ncl, n), dtype=torch.int32).pin_memory()   # column-major n x ncl
-            hC = torch.empty((ncl, mloc), dtype=torch.int32).pin_memory()
-            g.capi.check(A.lib.gffm_mat_download(A.h, hA.data_ptr(), g.capi.U32, mloc, 0))
-            g.capi.check(B.lib.gffm_mat_download(B.h, hB.data_ptr(), g.capi.U32, n, 0))
-            A2 = g.zeros(np.float32, mloc, n, N, ctx=ctx); B2 = g.zeros(np.float32, n, ncl, N, ctx=ctx); C2 = g.zeros(np.float32, mloc, ncl, N, ctx=ctx)
-
-            def e2e_step():
-                g.capi.check(A2.lib.gffm_mat_upload(A2.h, hA.data_ptr(), g.capi.U32, mloc, 1))
-                g.capi.check(B2.lib.gffm_mat_upload(B2.h, hB.data_ptr(), g.capi.U32, n, 1))
-                g.mul_(C2, A2, B2)
-                g.capi.check(C2.lib.gffm_mat_download(C2.h, hC.data_ptr(), g.capi.U32, mloc, 0))
-
-            e2e_step()
+        if not args.no_e2e and not kara:
             ke = max(1, min(K, 3))
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(ke):
-                e2e_step()
-            barrier()
-            te = (time.perf_counter() - t0) / ke
-            if world > 1:
-                t = torch.tensor([te], dtype=torch.float64, device=f"cuda:{local}")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                te = float(t.item())
-            same = bool(C2.equals(C))
-            # the same product through the single pipelined host-to-host call (gffm_gemm_host): H2D, plane split, GEMM tiles and
-            # D2H overlap on three streams.  Only at N == 1 GPU (one process owns the whole product).
-            pipe = None
             if world == 1:
+                hA = torch.empty((n, n), dtype=torch.int32).pin_memory()
+                hB = torch.empty((n, n), dtype=torch.int32).pin_memory()
+                hC = torch.empty((n, n), dtype=torch.int32).pin_memory()
+                g.capi.check(A.lib.gffm_mat_download(A.h, hA.data_ptr(), g.capi.U32, n, 0))
+                g.capi.check(B.lib.gffm_mat_download(B.h, hB.data_ptr(), g.capi.U32, n, 0))
+                A2_ = g.zeros(np.float32, n, n, N, ctx=ctx); B2_ = g.zeros(np.float32, n, n, N, ctx=ctx); C2_ = g.zeros(np.float32, n, n, N, ctx=ctx)
+
+                def e2e_step():
+                    g.capi.check(A2_.lib.gffm_mat_upload(A2_.h, hA.data_ptr(), g.capi.U32, n, 1))
+                    g.capi.check(B2_.lib.gffm_mat_upload(B2_.h, hB.data_ptr(), g.capi.U32, n, 1))
+                    g.mul_(C2_, A2_, B2_)
+                    g.capi.check(C2_.lib.gffm_mat_download(C2_.h, hC.data_ptr(), g.capi.U32, n, 0))
+
+                e2e_step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(ke):
+                    e2e_step()
+                torch.cuda.synchronize()
+                te = (time.perf_counter() - t0) / ke
+                same = bool(C2_.equals(C))
                 hC2 = torch.empty((n, n), dtype=torch.int32).pin_memory()
 
-                def pipe_step():
+                def pipe_step():  # the same product through the single pipelined host-to-host call: H2D, plane split, GEMM tiles and D2H overlap
                     g.capi.check(ctx.lib.gffm_gemm_host(ctx.h, hC2.data_ptr(), n, hA.data_ptr(), n, hB.data_ptr(), n, n, n, n, g.capi.U32, N))
 
                 pipe_step()
@@ -527,180 +705,103 @@ def main():
                 for _ in range(ke):
                     pipe_step()
                 torch.cuda.synchronize()
-                tp = (time.perf_counter() - t0) / ke
-                pipe = {"ms_per_step": tp * 1e3, "GOPS": 2.0 * n ** 3 / tp / 1e9, "matches": bool(torch.equal(hC2, hC))}
-            seq = {"ms_per_step": te * 1e3, "GOPS": 2.0 * n ** 3 / te / 1e9}
-            if pipe and pipe["matches"] and pipe["ms_per_step"] < te * 1e3:
-                te = pipe["ms_per_step"] / 1e3
-            e2e = {"value": 2.0 * n ** 3 / te / 1e9, "unit": "GOPS", "api": "gffm_gemm_host (pipelined)" if pipe and te * 1e3 == pipe["ms_per_step"] else "upload + mul! + download",
-                   "sequential_api_calls": seq, "pipelined_host_call": pipe, "h2d_bytes_per_step": int(4 * (mloc * n + n * ncl)), "d2h_bytes_per_step": int(4 * mloc * ncl),
-                   "ms_per_step": te * 1e3, "steps": ke, "host_dtype": "uint32 residues (pinned)", "matches_resident_result": same}
-            if world > 1 and pc == 1 and args.e2e_mode == "sliced":
+                tp_ = (time.perf_counter() - t0) / ke
+                pipe = {"ms_per_step": tp_ * 1e3, "GOPS": 2.0 * n ** 3 / tp_ / 1e9, "matches": bool(torch.equal(hC2, hC))}
+                seq = {"ms_per_step": te * 1e3, "GOPS": 2.0 * n ** 3 / te / 1e9}
+                use_pipe = pipe["matches"] and pipe["ms_per_step"] < te * 1e3
+                tbest = tp_ if use_pipe else te
+                e2e = {"value": 2.0 * n ** 3 / tbest / 1e9, "unit": "GOPS", "api": "gffm_gemm_host (pipelined)" if use_pipe else "upload + mul! + download",
+                       "sequential_api_calls": seq, "pipelined_host_call": pipe, "h2d_bytes_per_step": int(8 * n * n), "d2h_bytes_per_step": int(4 * n * n),
+                       "ms_per_step": tbest * 1e3, "steps": ke, "host_dtype": "uint32 residues (pinned)", "matches_resident_result": same}
+                del A2_, B2_, C2_
+            elif mgpu is not None:
+                # every rank uploads its row block of A and ITS OWN column range of B over its own PCIe link (B distributed: root =
+                # GFFM_MG_DISTRIBUTED), the operand planes are exchanged over NVLink, every rank downloads its row block of C
+                off = mg.owner_ranges(n, world)
+                c0, c1 = off[rank], off[rank + 1]
+                hA = torch.empty((n, mloc), dtype=torch.int32).pin_memory()            # column-major mloc x n
+                hB = torch.empty((max(c1 - c0, 1), n), dtype=torch.int32).pin_memory()  # column-major n x (c1 - c0)
+                hC = torch.empty((n, mloc), dtype=torch.int32).pin_memory()
+                g.capi.check(A.lib.gffm_mat_download(A.h, hA.data_ptr(), g.capi.U32, mloc, 0))
+                Bq = g.zeros(np.float32, n, c1 - c0, N, ctx=ctx)
+                if c1 > c0:
+                    g.capi.check(Bq.lib.gffm_mat_copy_block(Bq.h, 0, 0, B.h, 0, c0, n, c1 - c0))  # B was replicated for the shard check above
+                    g.capi.check(Bq.lib.gffm_mat_download(Bq.h, hB.data_ptr(), g.capi.U32, n, 0))
+                A2_ = g.zeros(np.float32, mloc, n, N, ctx=ctx); C2_ = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+                g.fill_(Bq, 0)
+
+                def e2e_step():
+                    g.capi.check(A2_.lib.gffm_mat_upload(A2_.h, hA.data_ptr(), g.capi.U32, mloc, 1))
+                    if c1 > c0:
+                        g.capi.check(Bq.lib.gffm_mat_upload(Bq.h, hB.data_ptr(), g.capi.U32, n, 1))
+                    mgpu.gemm(C2_, A2_, Bq, root=g.capi.MG_DISTRIBUTED)
+                    g.capi.check(C2_.lib.gffm_mat_download(C2_.h, hC.data_ptr(), g.capi.U32, mloc, 0))
+
+                err = None
                 try:
-                    C3 = g.zeros(np.float32, mloc, n, N, ctx=ctx)
-                    Bt.zero_()  # nothing of B is resident any more: every byte must come from the host slices + the all-gather
-
-                    def deliver_h(c0, c1):
-                        rows = c1 - c0
-                        if rows % world == 0:
-                            per = rows // world
-                            lo = c0 + rank * per
-                            Bt[lo:lo + per, :n].copy_(hB[lo:lo + per], non_blocking=True)   # H2D: this rank's slice of the panel
-                            dist.all_gather_into_tensor(Bt[c0:c1], Bt[lo:lo + per])         # NVLink: the other N-1 slices, in place
-                        else:
-                            if rank == 0:
-                                Bt[c0:c1, :n].copy_(hB[c0:c1], non_blocking=True)
-                            dist.broadcast(Bt[c0:c1], src=0)
-
-                    bm_h = mg.BroadcastMatmul(torch, dist, C3, A2, B, Bt, panels, deliver=deliver_h)
-
-                    def sliced_step():
-                        g.capi.check(A2.lib.gffm_mat_upload(A2.h, hA.data_ptr(), g.capi.U32, mloc, 1))
-                        bm_h.step()
-                        g.capi.check(C3.lib.gffm_mat_download(C3.h, hC.data_ptr(), g.capi.U32, mloc, 0))
-
-                    sliced_step()
-                    bm_h.finish(); barrier()
+                    e2e_step()
+                    barrier()
                     t0 = time.perf_counter()
                     for _ in range(ke):
-                        sliced_step()
-                    bm_h.finish(); barrier()
-                    ts = (time.perf_counter() - t0) / ke
-                    tt = torch.tensor([ts], dtype=torch.float64, device=f"cuda:{local}")
-                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                    ts = float(tt.item())
-                    okk = torch.tensor([1 if C3.equals(C) else 0], dtype=torch.int32, device=f"cuda:{local}")
-                    dist.all_reduce(okk, op=dist.ReduceOp.MIN)
-                    e2e["sliced_upload_allgather"] = {"ms_per_step": ts * 1e3, "GOPS": 2.0 * n ** 3 / ts / 1e9, "matches_resident_result": bool(okk.item() == 1),
-                                                      "h2d_bytes_per_step": int(4 * (mloc * n + n * n // world)), "d2h_bytes_per_step": int(4 * mloc * n)}
-                    if okk.item() == 1 and ts < te:
-                        e2e.update({"value": 2.0 * n ** 3 / ts / 1e9, "ms_per_step": ts * 1e3, "api": "upload A shard + 1/N of B, NCCL all-gather, gffm_gemm_panels, download",
-                                    "h2d_bytes_per_step": int(4 * (mloc * n + n * n // world))})
-                    del C3
-                except Exception as ex:  # opt-in arm: never lose the line
-                    e2e["sliced_upload_allgather"] = {"error": str(ex)[:300]}
-            del A2, B2, C2
+                        e2e_step()
+                    barrier()
+                    te = allmax((time.perf_counter() - t0) / ke)
+                    mgpu.barrier()
+                    same = allmin_flag(bool(C2_.equals(C)))
+                except g.GffmError as ex:
+                    err = str(ex)[:300]
+                    te, same = None, False
+                tot = torch.tensor([4 * (mloc * n + n * (c1 - c0)), 4 * mloc * n], dtype=torch.int64, device=dev)
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+                e2e = {"value": (2.0 * n ** 3 / te / 1e9) if te else None, "unit": "GOPS",
+                       "api": "per rank: gffm_mat_upload(A row block), gffm_mat_upload(own column range of B), gffm_mg_gemm(root = GFFM_MG_DISTRIBUTED), gffm_mat_download(C row block)",
+                       "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
+                       "h2d_bytes_per_step_per_rank": int(4 * (mloc * n + n * (c1 - c0))), "d2h_bytes_per_step_per_rank": int(4 * mloc * n),
+                       "ms_per_step": te * 1e3 if te else None, "steps": ke, "host_dtype": "uint32 residues (pinned)", "matches_resident_result": same, "error": err}
+                del A2_, C2_, Bq
+            else:
+                e2e = {"value": None, "unit": "GOPS", "note": "--mg python has no end-to-end arm (use the default --mg cabi)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
-        extras = {}
-        roofline_pluq = None
-        if world == 1 and not args.no_extras:
-            def dev_time(fn, reps, warm=1):
-                """median / min wall time (s) of fn() bracketed by device synchronisation (the elimination calls block on their own)"""
-                for _ in range(warm):
-                    fn()
-                ts = []
-                for _ in range(reps):
-                    torch.cuda.synchronize(); t0 = time.perf_counter()
-                    fn()
-                    torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
-                return statistics.median(ts), min(ts)
-
-            def ev_time(fn, reps, warm=2):
-                """mean device time (ms) of fn() over `reps` back-to-back calls (CUDA events on the library stream)"""
-                for _ in range(warm):
-                    fn()
-                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
-                a0.record(stream)
-                for _ in range(reps):
-                    fn()
-                a1.record(stream); torch.cuda.synchronize()
-                return a0.elapsed_time(a1) / reps
-
-            # other moduli of the metric size (fresh product each time)
-            for N2 in (11, 65521):
-                A_, B_ = g.synth(n, n, N2, SEED_A, ctx=ctx), g.synth(n, n, N2, SEED_B, ctx=ctx)
-                C_ = g.zeros(np.float32, n, n, N2, ctx=ctx)
-
-                def prod():
-                    A_.touch(); B_.touch()
-                    g.mul_(C_, A_, B_)
-                t_ = ev_time(prod, 5, warm=3)
-                extras[f"matmul_n{n}_mod{N2}"] = {"ms": t_, "GOPS": 2.0 * n ** 3 / t_ / 1e6}
-                del A_, B_, C_
-            # GEMV at the metric size: HBM-bound, 4 bytes per matrix element
-            z_ = g.zeros(np.float32, n, 1, N, ctx=ctx); x_ = g.synth(n, 1, N, 77, ctx=ctx)
-            t_ = ev_time(lambda: g.gemv_(z_, A, x_), 20, warm=3)
-            extras[f"gemv_n{n}_mod{N}"] = {"ms": t_, "GBps": 4.0 * n * n / (t_ * 1e-3) / 1e9, "hbm_peak_GBps": peaks["hbm_gbs"],
-                                            "frac_of_hbm_peak": 4.0 * n * n / (t_ * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": 4 * n * n,
-                                            "note": "A (1 GiB) is larger than L2; 20 back-to-back products"}
-            del z_, x_
-            # the reference's only published cases (test/CuModMatrix/timing_test.jl:21-52: n = 5000, N = 11; RTX 3070 comments
-            # < 0.001 s add!, < 0.001 s scalar mul!, < 0.2 s mul!, < 0.001 s mat-vec) from our path
-            n5 = 5000
-            A5, B5 = g.synth(n5, n5, 11, 1, ctx=ctx), g.synth(n5, n5, 11, 2, ctx=ctx)
-            C5 = g.zeros(np.float32, n5, n5, 11, ctx=ctx); z5 = g.zeros(np.float32, n5, 1, 11, ctx=ctx); x5 = g.synth(n5, 1, 11, 3, ctx=ctx)
-
-            def mul5():
-                A5.touch(); B5.touch()
-                g.mul_(C5, A5, B5)
-            extras["reference_timing_cases_n5000_mod11"] = {
-                "source": "reference test/CuModMatrix/timing_test.jl:21-52 (author's RTX 3070 comments: add! < 1 ms, scalar mul! < 1 ms, mul! < 200 ms (F32) / < 1000 ms (F64), mat-vec < 1 ms)",
-                "add_ms": ev_time(lambda: g.add_(C5, A5, B5), 20), "scalar_mul_ms": ev_time(lambda: g.capi.check(C5.lib.gffm_ewise(g.capi.EW_SMUL, C5.h, A5.h, None, 2, 0)), 20),
-                "mul_ms": ev_time(mul5, 10), "matvec_ms": ev_time(lambda: g.gemv_(z5, A5, x5), 20)}
-            del A5, B5, C5, z5, x5
-            # elimination at the metric size: PLUQ, RREF, inverse; warm, 3 repetitions, median (BASELINE metric: "PLUQ n=16384 s")
-            for Np in (65521, N):
-                A_ = g.synth(n, n, Np, 9, ctx=ctx)
-                holder = {}
-
-                def do_pluq():
-                    holder["r"] = g.pluq_gpu_kernel(A_, return_rank=True)
-                l0_ = ctx.launch_count()
-                med, best = dev_time(do_pluq, 3)
-                launches_pluq = (ctx.launch_count() - l0_) // 4
-                rk_ = holder["r"][4]
-                holder.clear()
-                med_r, best_r = dev_time(lambda: holder.__setitem__("r", g.rref(A_)), 3)
-                holder.clear()
-                med_i, best_i = dev_time(lambda: holder.__setitem__("r", g.inverse(A_)), 3)
-                holder.clear()
-                ctx.set_profiling(True)
-                do_pluq(); ph = ctx.last_timings(); holder.clear()
-                ctx.set_profiling(False)
-                Lb = 1 if Np <= 256 else (2 if Np <= 65536 else None)
-                extras[f"pluq_n{n}_mod{Np}"] = {"seconds": med, "seconds_best": best, "rank": rk_, "rref_seconds": med_r, "rref_seconds_best": best_r,
-                                                 "inverse_seconds": med_i, "inverse_seconds_best": best_i, "us_per_pivot": med / max(rk_, 1) * 1e6,
-                                                 "kernel_launches_per_factorisation": int(launches_pluq),
-                                                 "phases_ms_profiled_call": {"panels_and_in_block_updates": ph[0] if len(ph) > 0 else None,
-                                                                             "triangular_solves": ph[1] if len(ph) > 1 else None, "schur_gemms": ph[2] if len(ph) > 2 else None},
-                                                 "reps": 3, "timing": "median wall time between device synchronisations, warm (second call onwards)"}
-                if Np == 65521:
-                    fm = n ** 3 / 3.0  # m n r - (m + n) r^2 / 2 + r^3 / 3 for m = n = r (SURVEY 8d)
-                    ip8 = 4542.2
-                    try:
-                        ip8 = float(json.load(open(os.path.join(ROOT, "profiles", "int8_peak.json")))["int8_tops_sustained"])
-                    except Exception:
-                        pass
-                    peak_fm = ip8 * 1e12 / (2.0 * Lb * Lb)  # field mul-adds/s if all of them ran as L^2 int8 MMAs at the tensor peak
-                    roofline_pluq = {"bound": "latency (n sequential pivots; the Schur updates are tensor-bound)", "kernel": "pluq_panel_ll_kernel",
-                                     "workload": f"PLUQ {n}x{n} mod {Np}, full rank", "field_muladds": fm, "achieved": fm / med / 1e12, "peak": peak_fm / 1e12,
-                                     "unit": "T field mul-add/s", "frac": fm / med / peak_fm, "seconds": med, "us_per_pivot": med / max(rk_, 1) * 1e6,
-                                     "note": "peak = measured int8 tensor peak / (2 L^2), L = 2 eight-bit limbs; the panel kernel (one thread-block cluster, "
-                                             "argmax + row exchange per pivot) bounds the factorisation, see DESIGN.md section 6"}
-                del A_
+        extras, roofline_pluq = ({}, None)
+        if world == 1 and not args.no_extras and not kara:
+            extras, roofline_pluq = run_extras(g, ctx, torch, np, stream, A, n, N, peaks)
 
     cpu = None
     cpu_pluq = None
     if rank == 0 and not args.no_cpu:
-        gops, cores, desc, dt = cpu_arm(n, N)
+        gops, cores, desc, dt = cpu_arm(n, N if not kara else N1 * N2)
         cpu = {"value": gops, "unit": "GOPS", "cores": cores, "kind": "port", "sample": desc, "seconds": dt,
                "extrapolated_full_workload_seconds": 2.0 * n ** 3 / (gops * 1e9)}
-        if world == 1 and not args.no_extras:
+        if world == 1 and not args.no_extras and not kara:
             ech = cpu_echelon_arm(65521)
             cpu_pluq = {"kind": "port", "cores": 1, "unit": "seconds", "sample": "oracle_c.echelon (reference pivot rule, scalar C) on full-rank synthetic n x n mod 65521",
                         "runs": ech, "value": ech[-1]["seconds"],
                         "extrapolated_n16384_seconds": ech[-1]["seconds"] * (16384.0 / ech[-1]["n"]) ** 3}
 
     if rank == 0:
+        if kara:
+            wl = f"{n}x{n} * {n}x{n} Karatsuba two-limb product mod N1*N2, N1 = {N1}, N2 = {N2} (KMatMul!), limbs resident as uint32 residues"
+            metric = "Karatsuba mod-(N1*N2) matmul effective GOPS (2n^3/s)"
+        else:
+            wl = f"{n}x{n} * {n}x{n} matmul mod {N} ({(N - 1).bit_length()}-bit modulus), A,B resident as uint32 residues"
+            metric = "mod-p matmul effective GOPS (2n^3/s)"
+        if world == 1:
+            sharding = "single GPU"
+        elif mgpu is not None:
+            sharding = (f"{world} row blocks of A and C over {world} GPUs; B lives on rank 0 and is distributed EVERY step by the library's multi-GPU layer "
+                        f"(gffm_mg_{'kmat_mul' if kara else 'gemm'}, transport {transport_used}): each rank splits 1/{world} of B's columns into 8-bit planes, the planes "
+                        f"are exchanged over NVLink while the GEMMs of the ranges that have arrived run; the distribution of step t+1 overlaps the GEMMs of step t")
+        else:
+            sharding = f"{world} row blocks of A over {world} GPUs, {transport_used}"
         out = {
-            "metric": "mod-p matmul effective GOPS (2n^3/s)", "value": value, "unit": "GOPS", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric, "value": value, "unit": "GOPS", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s8 residue limbs, int32 accumulate (exact)",
             "data": "synthetic",
-            "config": {"workload": f"{n}x{n} * {n}x{n} matmul mod {N} ({bits}-bit modulus), A,B resident as uint32 residues", "n": n, "modulus": N,
-                       "encoding": "RNS int8 tcgen05" if N > 65536 else "positional int8 limbs tcgen05",
-                       "sharding": "single GPU" if world == 1 else f"{pr} row blocks of A x {pc} column range(s) of B over {world} GPUs, B replicated from rank 0 by NCCL ({args.bcast}) every step in {npan} column panels on a communication stream, consumed by gffm_gemm_panels (split/CRT under the GEMM, next step's broadcast under this step's GEMMs)",
-                       "shards_match_local_product_on_all_ranks": shard_ok,
-                       "gemm_grid_cap": choice[1], "warmup_trials_ms": {f"panels={k[0]},gemm_ctas={k[1]}": round(v, 4) for k, v in tune.items()},
+            "config": {"workload": wl, "n": n, "modulus": N if not kara else N1 * N2,
+                       "encoding": "RNS int8 tcgen05" if (kara or N > 65536) else "positional int8 limbs tcgen05",
+                       "sharding": sharding, "multi_gpu_transport": transport_used, "multi_gpu_info": mgpu.info() if mgpu is not None else None,
+                       "shards_match_local_product_on_all_ranks": shard_ok, "multi_gpu_error": mg_error,
+                       "warmup_trials_ms": {k_: (round(v, 4) if isinstance(v, float) else v) for k_, v in tune.items()},
                        "l2_policy": f"inputs larger than L2: A and B are {4 * n * n / 2**20:.0f} MiB each vs 126 MB L2", "checksum_rank0": f"{checksum:016x}",
                        "extras": extras},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -713,6 +814,8 @@ def main():
         if world > 1 and os.environ.get("NCCL_DEBUG_FILE"):
             out["config"]["nccl_log"] = nccl_log_lines()
         print(json.dumps(out))
+    if mgpu is not None:
+        mgpu.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -17,6 +17,8 @@ EW_MOD, EW_ADD, EW_SUB, EW_MUL, EW_SADD, EW_SSUB, EW_RSSUB, EW_SMUL, EW_SDIV = r
 GEMM_STORE, GEMM_ADD, GEMM_SUB = range(3)
 ALGO_AUTO, ALGO_SIMT, ALGO_LIMB, ALGO_RNS = range(4)
 PIVOT_CORRECT, PIVOT_REFERENCE_QUIRK = range(2)
+MG_AUTO, MG_NCCL_BCAST, MG_NCCL_PLANES, MG_P2P_PLANES = range(4)
+MG_DISTRIBUTED = -1
 
 
 class GffmError(RuntimeError):
@@ -113,6 +115,16 @@ SIGNATURES = {
     "gffm_gemm_host": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _u64],
     "gffm_gemm_panels": [_vp, _vp, _vp, _i32, _pi64, _pvp, _pvp, _u64, _u64],
     "gffm_gemv": [_vp, _vp, _vp, _u64, _u64],
+    "gffm_mg_unique_id": [_vp],
+    "gffm_mg_create": [_vp, _vp, _i32, _i32, _pvp],
+    "gffm_mg_destroy": [_vp],
+    "gffm_mg_info": [_vp, _pi32, _pi32, _pi32, _pi32],
+    "gffm_mg_set_transport": [_vp, _i32],
+    "gffm_mg_barrier": [_vp],
+    "gffm_mg_owner_ranges": [_i64, _i32, _pi64],
+    "gffm_mg_gemm": [_vp, _vp, _vp, _vp, _i32, _vp, _u64, _u64],
+    "gffm_mg_kmat_mul": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _i32, _vp],
+    "gffm_mg_gemv": [_vp, _vp, _vp, _vp, _i32, _u64, _u64],
     "gffm_ewise": [_i32, _vp, _vp, _vp, _i64, _u64],
     "gffm_pluq": [_vp, _pvp, _pvp, _pi64, _pi64, _pi64, _pi64, _pi64, _i32],
     "gffm_lu": [_vp, _pvp, _pvp, _pi64, _pi64, _pi64, _pi64],

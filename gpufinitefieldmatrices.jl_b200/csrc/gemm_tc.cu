@@ -2049,3 +2049,171 @@ extern "C" int32_t gffm_gemm_panels(gffm_mat* C, gffm_mat* A, gffm_mat* B, int32
   // B is never taken from / put into the plane cache here: its residues change behind the library's back every step
   return tiled_gemm(ctx, view_of(C), cached_view_of(A), view_of(B), nullptr, m, n, k, R, P, GFFM_GEMM_STORE, rns && (R % P) == 0, &feed);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// B planes produced elsewhere (multi-GPU layer, mg.cu): plan / split / multiply as three separate steps (gemm_internal.cuh)
+// ---------------------------------------------------------------------------------------------------
+#include "gemm_internal.cuh"
+
+struct GemmBPlan {
+  bool rns = false;
+  int L = 1;
+  int64_t kc = 0, Kp = 0;
+  uint64_t R = 0, P = 0, kara_N1 = 0;
+  bool balanced = false;
+  int mode = GFFM_GEMM_STORE;
+  RnsPlan plan;
+  SplitParams sp;
+  BPlaneSpec spec;
+};
+
+int32_t gffm_bplan_create(int64_t kc, uint64_t R, uint64_t P, bool balanced, int crt_mode, uint64_t kara_N1, GemmBPlan** out) {
+  if (!out) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  if (kc < 1) GFFM_FAIL(GFFM_ERR_INVALID, "empty inner dimension");
+  if (R == 0 || R >= (1ull << 32) || P == 0 || P > (1ull << 52)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "product plan needs R < 2^32, P <= 2^52");
+  GemmBPlan* g = new GemmBPlan();
+  g->kc = kc;
+  g->Kp = round_up(kc, 128);
+  g->R = R;
+  g->P = P;
+  g->kara_N1 = kara_N1;
+  g->mode = crt_mode;
+  g->rns = kara_N1 != 0 || R > 65536 || P >= (1ull << 32);
+  if (!kara_N1 && P >= (1ull << 32)) {
+    delete g;
+    GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "uint32 output needs P < 2^32");
+  }
+  if (g->rns) {
+    if (kc > 65536) {
+      delete g;
+      GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "one RNS chunk covers at most 65536 inner columns");
+    }
+    g->balanced = balanced;
+    const int32_t st = make_rns_plan(kc, R, P, balanced, crt_mode, kara_N1, &g->plan);
+    if (st != GFFM_OK) {
+      delete g;
+      return st;
+    }
+    g->sp = g->plan.sp;
+    g->spec = BPlaneSpec{g->plan.s, SchemeRNS::BN, g->Kp, 1};
+  } else {
+    g->L = R <= 256 ? 1 : 2;
+    if (kc > limb_kmax(R)) {
+      delete g;
+      GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "inner dimension %lld exceeds one limb accumulation chunk (%lld)", (long long)kc, (long long)limb_kmax(R));
+    }
+    memset(&g->sp, 0, sizeof(g->sp));
+    g->sp.nplanes = g->L;
+    g->sp.mode = 0;
+    g->spec = BPlaneSpec{g->L, g->L == 1 ? SchemeL1::BN : SchemeL2::BN, g->Kp, 0};
+  }
+  *out = g;
+  return GFFM_OK;
+}
+
+void gffm_bplan_destroy(GemmBPlan* plan) { delete plan; }
+const BPlaneSpec* gffm_bplan_spec(const GemmBPlan* plan) { return &plan->spec; }
+
+int32_t gffm_bplan_split(gffm_ctx* ctx, const GemmBPlan* g, MatView B, const MatView* B2, uint8_t* planes, int64_t rowsPB, int64_t row0,
+                         cudaStream_t st) {
+  if (B.rows != g->kc) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "plane split: %lld rows, plan has %lld", (long long)B.rows, (long long)g->kc);
+  if (B.cols == 0) return GFFM_OK;
+  if (row0 < 0 || row0 + B.cols > rowsPB) GFFM_FAIL(GFFM_ERR_INVALID, "plane split: rows [%lld, %lld) outside the buffer", (long long)row0, (long long)(row0 + B.cols));
+  return run_split(ctx, false, B, B2, 0, g->kc, planes + row0 * g->Kp, g->Kp, rowsPB, g->sp, st);
+}
+
+int32_t gffm_bplan_gemm(gffm_ctx* ctx, const GemmBPlan* g, MatView Cv, MatView A, const MatView* A2, int64_t n, const ExtBPlanes& ext,
+                        uint32_t* kara_hi, int64_t ldhi) {
+  const int64_t m = A.rows;
+  if (A.cols != g->kc || Cv.rows != m || Cv.cols != n) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "external-plane GEMM: inconsistent shapes");
+  if (m == 0 || n == 0) return GFFM_OK;
+  if (!ext.planes || !ext.off || ext.npanels < 1 || ext.off[ext.npanels] != n) GFFM_FAIL(GFFM_ERR_INVALID, "external-plane GEMM: bad panel list");
+  if ((g->kara_N1 != 0) != (kara_hi != nullptr)) GFFM_FAIL(GFFM_ERR_INVALID, "external-plane GEMM: carry output does not match the plan");
+  const int BN = g->spec.BN, nplanes = g->spec.nplanes;
+  const int64_t Kp = g->Kp, rowsPA = round_up(m, BM);
+  for (int p = 0; p < ext.npanels; ++p)
+    if (ext.off[p] % BN != 0 || ext.off[p + 1] < ext.off[p]) GFFM_FAIL(GFFM_ERR_INVALID, "external-plane GEMM: panel offsets must be multiples of %d", BN);
+  if (ext.rowsPB < round_up(n, BN)) GFFM_FAIL(GFFM_ERR_INVALID, "external-plane GEMM: plane buffer has too few rows");
+  uint8_t* pa = nullptr;
+  GFFM_TRY(acquire_planes(ctx, 0, A, A2, 0, g->kc, Kp, rowsPA, g->sp, g->balanced ? 1 : 0, g->R, &ctx->ws_planes_a, &pa));
+  const int64_t lde = round_up(m, 128), e_plane = lde * n;
+  uint8_t* E = nullptr;
+  if (g->rns) {
+    GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_eplanes, (size_t)nplanes * e_plane));
+    E = (uint8_t*)ctx->ws_eplanes.ptr;
+  }
+  if (!ctx->s_aux) GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+  cudaStream_t sc = ctx->stream, sx = ctx->s_aux;
+  const size_t need_ev = 2 + (size_t)ext.npanels + 4;
+  while (ctx->ev_pool.size() < need_ev) {
+    cudaEvent_t e;
+    GFFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ev_pool.push_back(e);
+  }
+  size_t evi = 0;
+  cudaEvent_t ev0 = ctx->ev_pool[evi++], ev_end = ctx->ev_pool[evi++];
+  GFFM_CUDA(cudaEventRecord(ev0, sc));
+  GFFM_CUDA(cudaStreamWaitEvent(sx, ev0, 0));
+  CUtensorMap tmA, tmB, tmBh;
+  GFFM_TRY(make_plane_tmap(&tmA, pa, Kp, rowsPA, nplanes, BM));
+  GFFM_TRY(make_plane_tmap(&tmB, (void*)ext.planes, Kp, ext.rowsPB, nplanes, BN));
+  GFFM_TRY(make_plane_tmap(&tmBh, (void*)ext.planes, Kp, ext.rowsPB, nplanes, BN / 2));
+  const ModP mpP = make_modp(g->P);
+  for (int idx = 0; idx < ext.npanels; ++idx) {
+    const int p = ext.order ? ext.order[idx] : idx;
+    const int64_t j0 = ext.off[p], nj = ext.off[p + 1] - j0;
+    if (nj <= 0) continue;
+    if (ext.ready && ext.ready[p]) GFFM_CUDA(cudaStreamWaitEvent(sc, ext.ready[p], 0));
+    GemmParams q;
+    memset(&q, 0, sizeof(q));
+    q.m = (int)m;
+    q.n = (int)nj;
+    q.num_kb = (int)(Kp / 128);
+    q.num_m_blk = (int)(rowsPA / BM);
+    q.num_n_blk = (int)ceil_div(nj, BN);
+    q.nb0 = (int)(j0 / BN);
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ctx->profile) {
+      GFFM_CUDA(cudaEventCreate(&t0));
+      GFFM_CUDA(cudaEventCreate(&t1));
+      GFFM_CUDA(cudaEventRecord(t0, sc));
+    }
+    if (g->rns) {
+      memcpy(q.mods, g->plan.mods, sizeof(q.mods));
+      q.batches = g->plan.s;
+      q.E = E + j0 * lde;
+      q.lde = lde;
+      q.e_plane_stride = e_plane;
+      GFFM_TRY(launch_gemm<SchemeRNS>(ctx, tmA, tmB, q, sc, &tmBh));
+    } else {
+      q.batches = 1;
+      q.C = Cv.p + j0 * Cv.ld;
+      q.ldc = Cv.ld;
+      q.mode = g->mode;
+      q.modP = mpP;
+      if (g->L == 1) GFFM_TRY(launch_gemm<SchemeL1>(ctx, tmA, tmB, q, sc, &tmBh));
+      else GFFM_TRY(launch_gemm<SchemeL2>(ctx, tmA, tmB, q, sc, &tmBh));
+    }
+    if (ctx->profile) {
+      GFFM_CUDA(cudaEventRecord(t1, sc));
+      ctx->tile_events.push_back(t0);
+      ctx->tile_events.push_back(t1);
+    }
+    if (g->rns) {
+      cudaEvent_t e = ctx->ev_pool[evi++];
+      GFFM_CUDA(cudaEventRecord(e, sc));
+      GFFM_CUDA(cudaStreamWaitEvent(sx, e, 0));
+      GFFM_TRY(launch_crt(ctx, sx, g->plan.cp, E + j0 * lde, lde, e_plane, m, nj, Cv.p + j0 * Cv.ld, Cv.ld, kara_hi ? kara_hi + j0 * ldhi : nullptr, ldhi));
+    }
+  }
+  GFFM_CUDA(cudaEventRecord(ev_end, sx));
+  GFFM_CUDA(cudaStreamWaitEvent(sc, ev_end, 0));
+  return GFFM_OK;
+}
+
+// profiling hook of the multi-GPU layer: forget the GEMM launch events of earlier products
+void gffm_profile_reset_tiles(gffm_ctx* ctx) {
+  for (auto e : ctx->tile_events) cudaEventDestroy(e);
+  ctx->tile_events.clear();
+  ctx->n_ev = 0;
+}

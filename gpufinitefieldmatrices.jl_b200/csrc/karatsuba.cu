@@ -71,6 +71,18 @@ kara_ewise_kernel(int op, uint32_t* __restrict__ C1, uint32_t* __restrict__ C2, 
 
 }  // namespace
 
+// C2 = (P2 - P1 - P3 + carry) mod N2 on raw buffers (used by the multi-GPU Karatsuba product, mg.cu)
+int32_t gffm_kara_recombine(gffm_ctx* ctx, MatView vC2, MatView vC1, const uint32_t* P2, const uint32_t* P3, const uint32_t* carry, int64_t ldt,
+                            uint64_t N2) {
+  const int64_t m = vC1.rows, n = vC1.cols;
+  if (m == 0 || n == 0) return GFFM_OK;
+  int64_t blocks = ceil_div(m * n, 1024);
+  if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
+  kara_recombine_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(vC2.p, vC2.ld, vC1.p, vC1.ld, P2, P3, carry, ldt, m, n, make_modp(N2));
+  GFFM_LAUNCH_CHECK(ctx);
+  return GFFM_OK;
+}
+
 // one K-chunk (k <= 65536) of the product on views: (C1, C2) = (A1 + N1*A2) * (B1 + N1*B2) mod N1*N2
 static int32_t kmat_mul_chunk(gffm_ctx* ctx, MatView vC1, MatView vC2, MatView vA1, MatView vA2, MatView vB1, MatView vB2, uint64_t N1,
                               uint64_t N2) {

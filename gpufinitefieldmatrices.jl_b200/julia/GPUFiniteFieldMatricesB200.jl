@@ -16,14 +16,14 @@ const TILE_WIDTH = 32            # reference CuModMatrix.jl:2
 const DEFAULT_TYPE = Float32     # reference CuModMatrix.jl:3
 
 # ---- exceptions (reference CuModMatrix.jl:5-31; MatrixNotInvertibleException is used but never defined there, :485)
-struct CuModArraySizeMismatchException <: Exception; msg::String; end
-struct CuModArrayModulusMismatchException <: Exception; msg::String; end
-struct CuModMatrixTooLargeException <: Exception; msg::String; end
-struct CuModMatrixNotSquareException <: Exception; msg::String; end
-struct CuModMatrixModulusNotPrimeException <: Exception; msg::String; end
-struct InverseOverflowError <: Exception; msg::String; end
-struct InverseNotDefinedException <: Exception; msg::String; end
-struct MatrixNotInvertibleException <: Exception; msg::String; end
+struct CuModArraySizeMismatchException <: Exception; message::String; end
+struct CuModArrayModulusMismatchException <: Exception; message::String; end
+struct CuModMatrixTooLargeException <: Exception; message::String; end
+struct CuModMatrixNotSquareException <: Exception; message::String; end
+struct CuModMatrixModulusNotPrimeException <: Exception; message::String; end
+struct InverseOverflowError <: Exception; message::String; end
+struct InverseNotDefinedException <: Exception; message::String; end
+struct MatrixNotInvertibleException <: Exception; message::String; end
 
 last_error() = unsafe_string(ccall((:gffm_last_error, libgffm), Cstring, ()))
 version() = unsafe_string(ccall((:gffm_version, libgffm), Cstring, ()))
@@ -37,6 +37,7 @@ function check(st::Int32)
     st == 6 && throw(MatrixNotInvertibleException(msg))
     st == 7 && throw(InverseNotDefinedException(msg))
     st == 11 && throw(InexactError(:convert, Integer, msg))
+    st == 13 && throw(CuModMatrixModulusNotPrimeException(msg))
     st == 1 && throw(ArgumentError(msg))
     error("libgffm status $st: $msg")
 end
@@ -47,11 +48,13 @@ mutable struct Context
     function Context(device::Integer=0)
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:gffm_create, libgffm), Int32, (Int32, Ref{Ptr{Cvoid}}), device, r))
-        c = new(r[])
-        finalizer(x -> ccall((:gffm_destroy, libgffm), Int32, (Ptr{Cvoid},), x.h), c)
-        return c
+        # No finalizer: Julia does not order finalizers, and a matrix finalizer (gffm_mat_destroy) needs its context's stream.
+        # Every CuModArray holds a reference to its Context, so an unreachable Context has no live matrices; its few MB of
+        # workspaces are released by close(ctx) or at process exit.
+        return new(r[])
     end
 end
+Base.close(c::Context) = (c.h == C_NULL || ccall((:gffm_destroy, libgffm), Int32, (Ptr{Cvoid},), c.h); c.h = C_NULL; nothing)
 const _ctx = Ref{Union{Nothing,Context}}(nothing)
 default_context() = (_ctx[] === nothing && (_ctx[] = Context(0)); _ctx[])
 device_count() = (r = Ref{Int32}(0); check(ccall((:gffm_device_count, libgffm), Int32, (Ref{Int32},), r)); Int(r[]))
@@ -71,7 +74,7 @@ end
 _dtype(::Type{Float32}) = Int32(0); _dtype(::Type{Float64}) = Int32(1); _dtype(::Type{Int64}) = Int32(2)
 _dtype(::Type{UInt32}) = Int32(3); _dtype(::Type{Int32}) = Int32(4)
 
-mutable struct CuModArray{T,D}
+mutable struct CuModArray{T,D} <: AbstractArray{T,D}      # reference CuModMatrix.jl:42
     h::Ptr{Cvoid}      # gffm_mat*
     N::Int
     ctx::Context
@@ -141,6 +144,8 @@ function getindex(A::CuModArray{T}, i::Integer, j::Integer=1) where {T}
 end
 setindex!(A::CuModArray, v, i::Integer, j::Integer=1) = check(ccall((:gffm_mat_set_elem, libgffm), Int32, (Ptr{Cvoid}, Int64, Int64, Int64), A.h, i - 1, j - 1, Int64(v)))
 show(io::IO, A::CuModArray{T}) where {T} = print(io, "$(rows(A))x$(cols(A)) CuModMatrix{$T} modulo $(A.N)")
+show(io::IO, ::MIME"text/plain", A::CuModArray) = show(io, A)      # AbstractArray's default display would fetch element by element
+Base.IndexStyle(::Type{<:CuModArray}) = IndexCartesian()
 
 # zeros / eye / rand (reference CuModMatrix.jl:510-556)
 zeros(::Type{T}, r::Integer, c::Integer, N::Integer) where {T} = _create(T, 2, r, c, N)
@@ -365,14 +370,56 @@ function hensel_pseudoinverse!(steps::Integer, A::KaratsubaArray{E,2}, T::Karats
     T
 end
 
-export CuModArray, CuModMatrix, CuModVector, rows, cols, unsafe_Array, eye, zeros, rand, zero!, add!, sub!, elementwise_multiply!,
-       negate!, scalar_add!, scalar_sub!, mod_elements!, change_modulus, change_modulus_no_alloc!, mulN!, stripe_mul!,
-       mat_mul_gpu_type, mat_mul_type_inplace!, pluq_gpu_kernel, pluq, lu, rref, rank, inverse, is_invertible, is_invertible_with_inverse,
-       upper_triangular_inverse_no_copy, lower_triangular_inverse_no_copy, forward_sub_gpu_type_32, backward_sub_gpu_type_32,
-       apply_col_perm!, apply_col_inv_perm!, apply_row_perm!, apply_row_inv_perm!, perm_array_to_matrix, mod_inv,
-       hensel_pseudoinverse, hensel_pseudoinverse!, mul_panels!, mul_host!,
-       KaratsubaArray, KaratsubaMatrix, KaratsubaVector, KaratsubaZeros, MatToKMat, KMatToMat, Karatsubacopy, KMatMul!, KMatMul_gemv!, initialize_plan!, scalar_multiply!,
-       CuModArraySizeMismatchException, CuModArrayModulusMismatchException, CuModMatrixTooLargeException, CuModMatrixNotSquareException,
-       CuModMatrixModulusNotPrimeException, InverseOverflowError, InverseNotDefinedException, MatrixNotInvertibleException
+# ---- multi-GPU layer of the C ABI (new; include/gffm.h gffm_mg_*): one rank per GPU (Distributed.jl worker or thread), products on row
+# blocks of A and C, B on `root`; the 128-byte id travels by any channel (e.g. remotecall / MPI.bcast) -------------------------------
+mutable struct MultiGpu
+    h::Ptr{Cvoid}; ctx::Context; rank::Int; nranks::Int
+end
+mg_unique_id() = (id = Base.zeros(UInt8, 128); check(ccall((:gffm_mg_unique_id, libgffm), Int32, (Ptr{UInt8},), id)); id)
+function MultiGpu(id::Vector{UInt8}, nranks::Integer, rank::Integer; ctx::Context=default_context())      # rank is 0-based like NCCL's
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gffm_mg_create, libgffm), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Ref{Ptr{Cvoid}}), ctx.h, id, nranks, rank, r))
+    MultiGpu(r[], ctx, rank, nranks)
+end
+Base.close(m::MultiGpu) = (m.h == C_NULL || ccall((:gffm_mg_destroy, libgffm), Int32, (Ptr{Cvoid},), m.h); m.h = C_NULL; nothing)
+function mg_info(m::MultiGpu)
+    a = Ref{Int32}(0); b = Ref{Int32}(0); t = Ref{Int32}(0); p = Ref{Int32}(0)
+    check(ccall((:gffm_mg_info, libgffm), Int32, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ref{Int32}), m.h, a, b, t, p))
+    (rank=Int(a[]), nranks=Int(b[]), transport=Int(t[]), peer_memory=p[] != 0)
+end
+mg_set_transport!(m::MultiGpu, t::Integer) = check(ccall((:gffm_mg_set_transport, libgffm), Int32, (Ptr{Cvoid}, Int32), m.h, t))
+mg_barrier(m::MultiGpu) = check(ccall((:gffm_mg_barrier, libgffm), Int32, (Ptr{Cvoid},), m.h))
+mg_owner_ranges(n::Integer, nranks::Integer) = (off = Base.zeros(Int64, nranks + 1); check(ccall((:gffm_mg_owner_ranges, libgffm), Int32, (Int64, Int32, Ptr{Int64}), n, nranks, off)); off)
+# mul!(C, A, B) on row blocks: C, A = this rank's row blocks, B = the matrix on root (a same-shape matrix elsewhere)
+function mg_mul!(m::MultiGpu, C::CuModArray{T,2}, A::CuModArray{T,2}, B::CuModArray{T,2}; root::Integer=0, b_ready::Ptr{Cvoid}=C_NULL, R::Integer=0, P::Integer=0) where {T}
+    check(ccall((:gffm_mg_gemm, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, UInt64, UInt64), m.h, C.h, A.h, B.h, root, b_ready, R, P)); C
+end
+function mg_KMatMul!(m::MultiGpu, C::KaratsubaArray, A::KaratsubaArray, B::KaratsubaArray; root::Integer=0, b_ready::Ptr{Cvoid}=C_NULL)
+    check(ccall((:gffm_mg_kmat_mul, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt64, Int32, Ptr{Cvoid}),
+                m.h, C.data1.h, C.data2.h, A.data1.h, A.data2.h, B.data1.h, B.data2.h, A.N1, A.N2, root, b_ready)); C
+end
+function mg_mul!(m::MultiGpu, z::CuModArray{T,1}, A::CuModArray{T,2}, x::CuModArray{T,1}; root::Integer=0, R::Integer=0, P::Integer=0) where {T}
+    check(ccall((:gffm_mg_gemv, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, UInt64, UInt64), m.h, z.h, A.h, x.h, root, R, P)); z
+end
+
+# Exactly the reference's export list (src/GPUFiniteFieldMatrices.jl:36-60).  Like there, `zeros`, `rand`, `add!`, `sub!`, `zero!`, `rank`
+# (and everything this build adds: rref, lu, hensel_pseudoinverse, mul_host!, MultiGpu, mg_*, the Karatsuba helpers, the exception types)
+# stay unexported and are reached as GPUFiniteFieldMatricesB200.name -- they would clash with Base / LinearAlgebra / AbstractAlgebra.
+export CuModArray, CuModMatrix, CuModVector
+export inverse
+export KaratsubaArray, KaratsubaMatrix, KaratsubaVector
+export eye
+export change_modulus, change_modulus_no_alloc!
+export elementwise_multiply!, negate!
+export scalar_add!, scalar_sub!, rmul!, lmul!
+export mod_elements!, fill!
+export mat_mul_gpu_type, mat_mul_type_inplace!
+export perm_array_to_matrix
+export is_invertible, inverse, is_invertible_with_inverse
+export apply_col_perm!, apply_row_perm!
+export mod_inv
+export pluq_gpu_kernel
+export upper_triangular_inverse_no_copy, lower_triangular_inverse_no_copy
+export forward_sub_gpu_type_32, backward_sub_gpu_type_32
 
 end # module

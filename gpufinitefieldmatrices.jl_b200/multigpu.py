@@ -211,3 +211,81 @@ class BroadcastMatmul:
     def finish(self):
         """Make the current stream wait for the communication stream (before the buffers are reused or freed)."""
         self.torch.cuda.current_stream().wait_stream(self.comm)
+
+
+# ---- the multi-GPU layer of the C ABI (gffm_mg_*, csrc/mg.cu) ---------------------------------------------------------------------
+TRANSPORT_NAMES = {capi.MG_AUTO: "auto", capi.MG_NCCL_BCAST: "nccl_bcast", capi.MG_NCCL_PLANES: "nccl_planes", capi.MG_P2P_PLANES: "p2p_planes"}
+
+
+def owner_ranges(n: int, nranks: int) -> List[int]:
+    """Column offsets off[0..nranks] of the ranges of B owned by the ranks (gffm_mg_owner_ranges; no GPU needed)."""
+    off = (ctypes.c_int64 * (nranks + 1))()
+    capi.check(capi.load().gffm_mg_owner_ranges(int(n), int(nranks), off))
+    return [int(v) for v in off]
+
+
+class MultiGpu:
+    """One rank of the library's own multi-GPU layer: sharded products through `gffm_mg_gemm` / `gffm_mg_kmat_mul` /
+    `gffm_mg_gemv`.  The 128-byte id comes from `MultiGpu.unique_id()` on one rank and reaches the others by any channel
+    (`from_torch_distributed` uses torch.distributed's object broadcast)."""
+
+    def __init__(self, ctx, rank: int, nranks: int, unique_id: bytes):
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL unique id has 128 bytes")
+        self.ctx, self.lib = ctx, ctx.lib
+        self.rank, self.nranks = int(rank), int(nranks)
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        capi.check(self.lib.gffm_mg_create(ctx.h, buf, self.nranks, self.rank, ctypes.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        capi.check(capi.load().gffm_mg_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, dist, ctx):
+        """Bootstrap over an initialised torch.distributed process group (any backend): rank 0 creates the id."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(ctx, rank, world, box[0])
+
+    def info(self):
+        r, n, t, p = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        capi.check(self.lib.gffm_mg_info(self.h, ctypes.byref(r), ctypes.byref(n), ctypes.byref(t), ctypes.byref(p)))
+        return {"rank": r.value, "nranks": n.value, "transport": TRANSPORT_NAMES.get(t.value, str(t.value)), "peer_memory": bool(p.value)}
+
+    def set_transport(self, transport: int):
+        capi.check(self.lib.gffm_mg_set_transport(self.h, int(transport)))
+
+    def barrier(self):
+        capi.check(self.lib.gffm_mg_barrier(self.h))
+
+    def gemm(self, C, A, B, root: int = 0, b_ready=None, R: int = 0, P: int = 0):
+        """C_shard = A_shard * B mod P; `b_ready` is a raw cudaEvent_t (int) or None."""
+        capi.check(self.lib.gffm_mg_gemm(self.h, C.h, A.h, B.h, int(root), ctypes.c_void_p(b_ready) if b_ready else None, int(R), int(P)))
+        return C
+
+    def kmat_mul(self, CK, AK, BK, root: int = 0, b_ready=None):
+        """Karatsuba product on row blocks (KMatMul!, KaratsubaMatrix.jl:133-204)."""
+        capi.check(self.lib.gffm_mg_kmat_mul(self.h, CK.data1.h, CK.data2.h, AK.data1.h, AK.data2.h, BK.data1.h, BK.data2.h, int(AK.N1), int(AK.N2),
+                                             int(root), ctypes.c_void_p(b_ready) if b_ready else None))
+        return CK
+
+    def gemv(self, z, A, x, root: int = 0, R: int = 0, P: int = 0):
+        capi.check(self.lib.gffm_mg_gemv(self.h, z.h, A.h, x.h, int(root), int(R), int(P)))
+        return z
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gffm_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

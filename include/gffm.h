@@ -178,6 +178,43 @@ int32_t gffm_gemm_host(gffm_ctx* ctx, void* C_host, int64_t ldc, const void* A_h
  * step's data.  Semantics of the result are those of mul!(C,A,B) (CuModMatrix.jl:767-787). */
 int32_t gffm_gemm_panels(gffm_mat* C, gffm_mat* A, gffm_mat* B, int32_t npanels, const int64_t* col_off, void* const* ready,
                          void* const* consumed, uint64_t in_bound_R, uint64_t mod_P);
+/* ---- multi-GPU layer through the C ABI (new): one rank per GPU, NCCL for the bootstrap and as a transport,
+ * copy engines over NVLink peer memory as the default transport.  Products shard by row blocks of A and C; B lives on `root`.
+ * What travels is B's 8-bit operand planes: the column range owned by rank q is split by rank q only and collected by the
+ * others while their GEMMs already run (csrc/mg.cu).  All calls are collective (every rank, same order, same shapes). ---- */
+typedef struct gffm_mg gffm_mg;
+enum {
+  GFFM_MG_AUTO = 0,         /* peer-memory planes where CUDA IPC / peer access works between all ranks, else NCCL planes */
+  GFFM_MG_NCCL_BCAST = 1,   /* ncclBroadcast of B's uint32 column ranges, every rank splits all of B */
+  GFFM_MG_NCCL_PLANES = 2,  /* grouped ncclSend/ncclRecv scatter of the ranges, owner split, grouped in-place ncclAllGather of the planes */
+  GFFM_MG_P2P_PLANES = 3    /* copy-engine push of the ranges / pull of the planes through peer memory, epoch flags, no SM used */
+};
+/* root argument of gffm_mg_gemm for a B that is ALREADY distributed: every rank passes its own column range
+ * [off[rank], off[rank+1]) (gffm_mg_owner_ranges) as a k x width matrix -- e.g. uploaded from the host over that GPU's own PCIe link */
+enum { GFFM_MG_DISTRIBUTED = -1 };
+/* 128-byte NCCL unique id: create on one rank, hand to the others by any channel (MPI, a file, Distributed.jl, torch.distributed) */
+int32_t gffm_mg_unique_id(void* id128);
+/* ctx = this rank's context (its device).  NCCL is dlopen'ed (libnccl.so.2, or $GFFM_NCCL_LIB) */
+int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nranks, int32_t rank, gffm_mg** out);
+int32_t gffm_mg_destroy(gffm_mg* mg);
+int32_t gffm_mg_info(gffm_mg* mg, int32_t* rank, int32_t* nranks, int32_t* transport, int32_t* peer_memory);
+int32_t gffm_mg_set_transport(gffm_mg* mg, int32_t transport);
+/* drains this rank's streams, meets the other ranks, reports a peer-flag time-out of an earlier product */
+int32_t gffm_mg_barrier(gffm_mg* mg);
+/* column ranges of B owned by the ranks: off[0..nranks] (equal widths, multiples of 256) -- pure function, no GPU needed */
+int32_t gffm_mg_owner_ranges(int64_t n, int32_t nranks, int64_t* off);
+/* C_shard = A_shard * B mod P: mul!(C,A,B) (CuModMatrix.jl:767-787) on row blocks.  B holds the matrix on `root`; on the other
+ * ranks it is a same-shape matrix created the same way (receive buffer of the broadcast transport, otherwise untouched).
+ * b_ready_event: cudaEvent_t recorded after B's last modification on root, or NULL = B is ready in context-stream order.  With an
+ * event the distribution of this product may run under the GEMMs of the previous one.  Asynchronous like gffm_gemm. */
+int32_t gffm_mg_gemm(gffm_mg* mg, gffm_mat* C, gffm_mat* A, gffm_mat* B, int32_t root, void* b_ready_event, uint64_t in_bound_R, uint64_t mod_P);
+/* KMatMul!(C,A,B) (KaratsubaMatrix.jl:133-204) on row blocks: A1, A2, C1, C2 are this rank's row blocks, B1, B2 live on root;
+ * inner dimension at most 65536 (and within one limb chunk for the P2 / P3 sub-products) */
+int32_t gffm_mg_kmat_mul(gffm_mg* mg, gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_mat* A2, gffm_mat* B1, gffm_mat* B2, uint64_t N1,
+                         uint64_t N2, int32_t root, void* b_ready_event);
+/* z_shard = A_shard * x mod P: mul!(z,A,x) (CuModMatrix.jl:816-836) on row blocks; x (n x 1 on every rank) is broadcast from root */
+int32_t gffm_mg_gemv(gffm_mg* mg, gffm_mat* z, gffm_mat* A, gffm_mat* x, int32_t root, uint64_t in_bound_R, uint64_t mod_P);
+
 /* mul!(z,A,x;R,P) (CuModMatrix.jl:816-836, stripe_mul.jl:82-168): z = A*x mod P, x and z are n x 1 matrices */
 int32_t gffm_gemv(gffm_mat* z, gffm_mat* A, gffm_mat* x, uint64_t in_bound_R, uint64_t mod_P);
 

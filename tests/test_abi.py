@@ -94,3 +94,16 @@ def test_plain_c_client_runs_on_the_gpu(tmp_path):
     run = _build_c_client(tmp_path)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "C = [" in run.stdout and "no CPU fallback" not in run.stdout
+
+
+def test_mg_owner_ranges_is_a_pure_function():
+    """Column ranges of B owned by the ranks (gffm_mg_owner_ranges): equal widths, multiples of 256, covering [0, n) -- no GPU needed."""
+    import gffm_b200 as g
+    assert g.multigpu.owner_ranges(16384, 8) == [2048 * q for q in range(9)]
+    assert g.multigpu.owner_ranges(32768, 4) == [8192 * q for q in range(5)]
+    assert g.multigpu.owner_ranges(1000, 4) == [0, 256, 512, 768, 1000]
+    assert g.multigpu.owner_ranges(300, 4) == [0, 256, 300, 300, 300]
+    assert g.multigpu.owner_ranges(0, 3) == [0, 0, 0, 0]
+    with pytest.raises(g.GffmError):
+        g.multigpu.owner_ranges(10, 0)
+    assert len(g.multigpu.MultiGpu.unique_id()) == 128  # NCCL is dlopen'ed on demand, no link-time dependency
