@@ -361,17 +361,25 @@ def main():
         if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # torch.distributed is plumbing only (id exchange, barriers, max over ranks): the gloo (CPU) backend.  The data path's NCCL
+        # communicator lives inside the library (gffm_mg_create).  Not using torch's NCCL backend / stream pool also keeps the process below
+        # CUDA_DEVICE_MAX_CONNECTIONS streams, so the multi-GPU layer's streams never share a hardware queue (profiles/r02_notes.md).
+        dist.init_process_group("nccl" if args.mg == "python" else "gloo", **({"device_id": torch.device("cuda", local)} if args.mg == "python" else {}))
     n, N = args.n, args.modulus
     kara = args.workload == "karatsuba"
     N1, N2 = args.n1, args.n2
     W = max(3, args.warmup)
     K = max(1, args.steps)
+    g.set_default_device(local)
     ctx = g.Context(local)
-    stream = torch.cuda.Stream(device=local)
-    ctx.set_stream(stream.cuda_stream)
+    if world > 1 and args.mg == "python":
+        stream = torch.cuda.Stream(device=local)
+        ctx.set_stream(stream.cuda_stream)
+    else:
+        stream = torch.cuda.ExternalStream(ctx.get_stream(), device=local)  # the library's own stream (torch only records events on it)
     peaks = load_peaks()
     dev = f"cuda:{local}"
+    rdev = dev if (world > 1 and args.mg == "python") else "cpu"  # where the reduction tensors of the plumbing live
 
     def barrier():
         if world > 1:
@@ -381,14 +389,14 @@ def main():
     def allmax(x):
         if world == 1:
             return float(x)
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        t = torch.tensor([x], dtype=torch.float64, device=rdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def allmin_flag(ok):
         if world == 1:
             return bool(ok)
-        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=rdev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item() == 1)
 
@@ -542,7 +550,7 @@ def main():
                 mg_error = str(ex)[:300]
         ms = allmax(ms)
         if world > 1:
-            lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+            lt = torch.tensor([launches], dtype=torch.int64, device=rdev)
             dist.all_reduce(lt, op=dist.ReduceOp.SUM)
             launches = int(lt.item())
         checksum = C.checksum()
@@ -551,23 +559,42 @@ def main():
         # ---- every rank: the sharded result == the single-GPU product of its row block with the whole B (replicated here for the check) ----
         shard_ok = None
         if world > 1:
+            def replicate(*ts):
+                """B on every rank (for the checks below)"""
+                if mgpu is None:
+                    for t_ in ts:
+                        dist.broadcast(t_, src=0)
             if kara:
-                dist.broadcast(B1t, src=0); dist.broadcast(B2t, src=0)
+                CR = g.KaratsubaZeros(np.float64, mloc, n, N1, N2, ctx=ctx)
+                same_t = True
+                if mgpu is not None:  # the same product through the OTHER data path (NCCL broadcast of the uint32 limbs; replicates B1, B2 as a side effect)
+                    mgpu.set_transport(g.capi.MG_NCCL_BCAST)
+                    mgpu.kmat_mul(CR, AK, BK, root=0)
+                    mgpu.barrier()
+                    same_t = CK.data1.equals(CR.data1) and CK.data2.equals(CR.data2)
+                replicate(B1t, B2t)
                 torch.cuda.synchronize()
                 B1.touch(); B2.touch()
-                CR = g.KaratsubaZeros(np.float64, mloc, n, N1, N2, ctx=ctx)
-                g.KMatMul_(CR, AK, BK)
-                same_c = CK.data1.equals(CR.data1) and CK.data2.equals(CR.data2)
+                g.KMatMul_(CR, AK, BK)  # ... and through the single-GPU entry point on this rank's row block
+                same_c = same_t and CK.data1.equals(CR.data1) and CK.data2.equals(CR.data2)
                 del CR
             else:
-                dist.broadcast(Bt, src=0)
+                Cref = g.zeros(np.float32, mloc, n, N, ctx=ctx)
+                same_t = True
+                if mgpu is not None:
+                    mgpu.set_transport(g.capi.MG_NCCL_BCAST)
+                    mgpu.gemm(Cref, A, B, root=0)
+                    mgpu.barrier()
+                    same_t = C.equals(Cref)
+                replicate(Bt)
                 torch.cuda.synchronize()
                 B.touch()
-                Cref = g.zeros(np.float32, mloc, n, N, ctx=ctx)
                 g.mul_(Cref, A, B)
-                same_c = C.equals(Cref)
+                same_c = same_t and C.equals(Cref)
                 del Cref
             shard_ok = allmin_flag(same_c and mg_error is None)
+            if mgpu is not None:
+                mgpu.set_transport(names[transport_used])  # back to the transport of the timed region (the end-to-end arm below uses it)
 
         # ---- parity of the TIMED result against the CPU oracle: sampled rows of this rank's C (the output of the last timed step),
         # recomputed by oracle_c.matmul_mod from rows of A rebuilt with the oracle's generator and the B held by rank 0 (downloaded;
@@ -600,7 +627,7 @@ def main():
             ok_all, rows_all = rep["match"] and gen_ok, rep["rows"]
             if world > 1:
                 ok_all = allmin_flag(ok_all)
-                rr = torch.tensor([rep["rows"]], dtype=torch.int64, device=dev)
+                rr = torch.tensor([rep["rows"]], dtype=torch.int64, device=rdev)
                 dist.all_reduce(rr, op=dist.ReduceOp.SUM)
                 rows_all = int(rr.item())
             parity = {"rows": rows_all, "cols": rep["cols"], "match": bool(ok_all), "checker": "oracle_c.matmul_mod (exact uint64 host arithmetic)",
@@ -751,7 +778,7 @@ def main():
                 except g.GffmError as ex:
                     err = str(ex)[:300]
                     te, same = None, False
-                tot = torch.tensor([4 * (mloc * n + n * (c1 - c0)), 4 * mloc * n], dtype=torch.int64, device=dev)
+                tot = torch.tensor([4 * (mloc * n + n * (c1 - c0)), 4 * mloc * n], dtype=torch.int64, device=rdev)
                 dist.all_reduce(tot, op=dist.ReduceOp.SUM)
                 e2e = {"value": (2.0 * n ** 3 / te / 1e9) if te else None, "unit": "GOPS",
                        "api": "per rank: gffm_mat_upload(A row block), gffm_mat_upload(own column range of B), gffm_mg_gemm(root = GFFM_MG_DISTRIBUTED), gffm_mat_download(C row block)",

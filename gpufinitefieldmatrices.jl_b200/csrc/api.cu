@@ -61,6 +61,7 @@ extern "C" int32_t gffm_create(int32_t device, gffm_ctx** out) {
     cudaGetLastError();
   }
   for (int i = 0; i < 8; ++i) GFFM_CUDA(cudaEventCreate(&ctx->ev[i]));
+  ctx->trace = getenv("GFFM_TRACE") != nullptr && atoi(getenv("GFFM_TRACE")) != 0;
   *out = ctx;
   return GFFM_OK;
 }
@@ -123,6 +124,34 @@ extern "C" int32_t gffm_destroy(gffm_ctx* ctx) {
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return GFFM_OK;
+}
+
+// prints the most recent trace records (GFFM_TRACE_LAST, default 160) as a timeline relative to the earliest of them and clears the trace
+void gffm_trace_dump(gffm_ctx* ctx, int rank) {
+  if (!ctx->trace || ctx->trace_recs.empty()) return;
+  cudaDeviceSynchronize();
+  const size_t last = getenv("GFFM_TRACE_LAST") ? (size_t)atoi(getenv("GFFM_TRACE_LAST")) : 160;
+  const size_t n = ctx->trace_recs.size(), first = n > last ? n - last : 0;
+  // reference: the earliest begin among the printed records
+  size_t ref = first;
+  for (size_t i = first; i < n; ++i) {
+    float d = 0.f;
+    if (cudaEventElapsedTime(&d, ctx->trace_recs[ref].a, ctx->trace_recs[i].a) == cudaSuccess && d < 0.f) ref = i;
+  }
+  static const char* snames[] = {"compute", "aux", "dist", "pull", "push", "comm"};
+  for (size_t i = first; i < n; ++i) {
+    const gffm_ctx::TraceRec& r = ctx->trace_recs[i];
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, ctx->trace_recs[ref].a, r.a);
+    cudaEventElapsedTime(&b, ctx->trace_recs[ref].a, r.b);
+    fprintf(stderr, "[gffm trace r%d] %-8s %-12s %4d  %9.3f -> %9.3f  (%.3f ms)\n", rank, snames[r.sid < 6 ? r.sid : 0], r.what, r.idx, a, b, b - a);
+  }
+  for (auto& r : ctx->trace_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->trace_recs.clear();
+  cudaGetLastError();
 }
 
 extern "C" int32_t gffm_sync(gffm_ctx* ctx) {

@@ -80,6 +80,15 @@ struct gffm_ctx {
   std::vector<double> timings;
   std::vector<double> elim_timings;  // {inner panels, U12 = L11^-1 A12, trailing GEMM} ms of the last profiled elimination
   bool profile = false;
+  // GFFM_TRACE=1: timing events around the kernels / copies of the multi-stream pipelines (external-plane GEMM, multi-GPU layer);
+  // dumped as a timeline by gffm_trace_dump (called from gffm_mg_barrier / gffm_sync).  Diagnostics only.
+  bool trace = false;
+  struct TraceRec {
+    const char* what;
+    int idx, sid;
+    cudaEvent_t a, b;
+  };
+  std::vector<TraceRec> trace_recs;
   int n_ev = 0;  // events recorded by the last profiled call
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -109,6 +118,22 @@ struct gffm_mat {
   gffm_plane_cache cache[2];    // [0] = as A operand (transposed planes), [1] = as B operand
 };
 static inline void gffm_touch(gffm_mat* m) { m->version++; }
+
+static inline cudaEvent_t gffm_trace_begin(gffm_ctx* ctx, cudaStream_t st) {
+  if (!ctx->trace) return nullptr;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  return e;
+}
+static inline void gffm_trace_end(gffm_ctx* ctx, const char* what, int idx, int sid, cudaEvent_t a, cudaStream_t st) {
+  if (!a) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  ctx->trace_recs.push_back(gffm_ctx::TraceRec{what, idx, sid, a, e});
+}
+void gffm_trace_dump(gffm_ctx* ctx, int rank);
 
 int32_t gffm_ws_reserve(gffm_ctx* ctx, gffm_workspace* ws, size_t bytes);
 // Stream-ordered device memory for matrices and plane caches (cudaMallocAsync on the device's default pool, which is told to

@@ -2132,10 +2132,14 @@ int32_t gffm_bplan_gemm(gffm_ctx* ctx, const GemmBPlan* g, MatView Cv, MatView A
   const int BN = g->spec.BN, nplanes = g->spec.nplanes;
   const int64_t Kp = g->Kp, rowsPA = round_up(m, BM);
   for (int p = 0; p < ext.npanels; ++p)
-    if (ext.off[p] % BN != 0 || ext.off[p + 1] < ext.off[p]) GFFM_FAIL(GFFM_ERR_INVALID, "external-plane GEMM: panel offsets must be multiples of %d", BN);
+    if ((ext.off[p + 1] > ext.off[p] && ext.off[p] % BN != 0) || ext.off[p + 1] < ext.off[p]) GFFM_FAIL(GFFM_ERR_INVALID, "external-plane GEMM: panel offsets must be multiples of %d", BN);
   if (ext.rowsPB < round_up(n, BN)) GFFM_FAIL(GFFM_ERR_INVALID, "external-plane GEMM: plane buffer has too few rows");
   uint8_t* pa = nullptr;
-  GFFM_TRY(acquire_planes(ctx, 0, A, A2, 0, g->kc, Kp, rowsPA, g->sp, g->balanced ? 1 : 0, g->R, &ctx->ws_planes_a, &pa));
+  {
+    cudaEvent_t ta = gffm_trace_begin(ctx, ctx->stream);
+    GFFM_TRY(acquire_planes(ctx, 0, A, A2, 0, g->kc, Kp, rowsPA, g->sp, g->balanced ? 1 : 0, g->R, &ctx->ws_planes_a, &pa));
+    gffm_trace_end(ctx, "splitA", 0, 0, ta, ctx->stream);
+  }
   const int64_t lde = round_up(m, 128), e_plane = lde * n;
   uint8_t* E = nullptr;
   if (g->rns) {
@@ -2163,7 +2167,10 @@ int32_t gffm_bplan_gemm(gffm_ctx* ctx, const GemmBPlan* g, MatView Cv, MatView A
     const int p = ext.order ? ext.order[idx] : idx;
     const int64_t j0 = ext.off[p], nj = ext.off[p + 1] - j0;
     if (nj <= 0) continue;
+    cudaEvent_t tw = gffm_trace_begin(ctx, sc);
     if (ext.ready && ext.ready[p]) GFFM_CUDA(cudaStreamWaitEvent(sc, ext.ready[p], 0));
+    gffm_trace_end(ctx, "waitB", p, 0, tw, sc);
+    cudaEvent_t tg = gffm_trace_begin(ctx, sc);
     GemmParams q;
     memset(&q, 0, sizeof(q));
     q.m = (int)m;
@@ -2199,11 +2206,14 @@ int32_t gffm_bplan_gemm(gffm_ctx* ctx, const GemmBPlan* g, MatView Cv, MatView A
       ctx->tile_events.push_back(t0);
       ctx->tile_events.push_back(t1);
     }
+    gffm_trace_end(ctx, "gemm", p, 0, tg, sc);
     if (g->rns) {
       cudaEvent_t e = ctx->ev_pool[evi++];
       GFFM_CUDA(cudaEventRecord(e, sc));
       GFFM_CUDA(cudaStreamWaitEvent(sx, e, 0));
+      cudaEvent_t tc = gffm_trace_begin(ctx, sx);
       GFFM_TRY(launch_crt(ctx, sx, g->plan.cp, E + j0 * lde, lde, e_plane, m, nj, Cv.p + j0 * Cv.ld, Cv.ld, kara_hi ? kara_hi + j0 * ldhi : nullptr, ldhi));
+      gffm_trace_end(ctx, "crt", p, 1, tc, sx);
     }
   }
   GFFM_CUDA(cudaEventRecord(ev_end, sx));

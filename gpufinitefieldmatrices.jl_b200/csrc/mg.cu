@@ -8,9 +8,13 @@
 //   GFFM_MG_P2P_PLANES  (default where peer access works)  copy engines over NVLink peer memory, no SM of any GPU is used for
 //                       communication: the root PUSHES each rank's uint32 column range into that rank's staging buffer, every
 //                       rank splits its range into planes, every rank PULLS the other ranges' planes from their owners.  Ranks
-//                       synchronise through 32-bit epoch flags in each other's memory (written by a one-warp kernel after a
-//                       system fence, awaited by a one-warp polling kernel with a time-out) -- stream-ordered on both sides, no
-//                       host round trip, no NCCL kernel competing with the persistent GEMM for SMs.
+//                       synchronise through 32-bit epoch flags in each other's memory, written and awaited with STREAM MEMORY
+//                       OPERATIONS (cuStreamWriteValue32 / cuStreamWaitValue32: executed by the GPU front end, not by an SM) --
+//                       stream-ordered on both sides, no host round trip, no NCCL or polling kernel competing with the persistent
+//                       GEMM (measured: a one-warp polling kernel sharing an SM with a GEMM CTA doubled that launch's duration
+//                       through the static tile schedule; profiles/r02_notes.md).  Kernel-based flags (bounded polling) remain as
+//                       the fallback where the memory operations are not available (GFFM_MG_FLAGS=kernel forces them).
+//                       Transfers are spread over several copy streams (one copy engine each).
 //   GFFM_MG_NCCL_PLANES the same data flow with NCCL: grouped ncclSend/ncclRecv scatter of the uint32 ranges, one grouped
 //                       in-place ncclAllGather of the planes.
 //   GFFM_MG_NCCL_BCAST  ncclBroadcast of B's uint32 column ranges, every rank splits all of B (round-1 data flow).
@@ -18,6 +22,7 @@
 // Plane buffers and staging are double-buffered by epoch parity, so the distribution of product e+1 runs entirely under the
 // GEMMs of product e when the caller says that B is ready (b_ready event).  NCCL is loaded with dlopen (libnccl.so.2): the
 // library has no link-time dependency on it and shares the copy a host runtime (e.g. torch) has already loaded.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdlib.h>
@@ -30,7 +35,7 @@ namespace {
 constexpr int MG_MAX_RANKS = 32;
 constexpr size_t MG_CTL_BYTES = 4096;
 // control words (uint32) at the start of every rank's arena
-enum { F_STAGED = 0, F_READY = 64, F_PULLED = 128, F_SPLIT_DONE = 192, F_ERROR = 256 };
+enum { F_STAGED = 0, F_READY = 64, F_PULLED = 128, F_SPLIT_DONE = 192, F_ERROR = 256, F_PROBE = 320 };
 
 struct NcclApi {
   void* h = nullptr;
@@ -81,6 +86,28 @@ NcclApi* nccl_api() {
   return &api;
 }
 
+// stream memory operations of the driver API, resolved through the runtime (no link-time dependency on libcuda)
+struct MemOps {
+  CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+};
+MemOps* mem_ops() {
+  static MemOps ops;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *w = nullptr, *v = nullptr;
+    cudaDriverEntryPointQueryResult q1, q2;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+        cudaGetDriverEntryPoint("cuStreamWriteValue32", &v, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess) {
+      ops.wait32 = reinterpret_cast<decltype(ops.wait32)>(w);
+      ops.write32 = reinterpret_cast<decltype(ops.write32)>(v);
+    }
+    cudaGetLastError();
+  }
+  return (ops.wait32 && ops.write32) ? &ops : nullptr;
+}
+
 #define MG_NCCL(expr)                                                                                              \
   do {                                                                                                             \
     ncclResult_t _r = (expr);                                                                                      \
@@ -111,15 +138,18 @@ __global__ void mg_wait_kernel(const uint32_t* __restrict__ flags, uint32_t mask
   const int lane = threadIdx.x;
   bool ok = ((mask >> lane) & 1u) == 0;
   const unsigned long long t0 = global_timer_ns();
+  const volatile uint32_t* vf = flags;
   for (;;) {
-    if (!ok) ok = (int32_t)(ld_acquire_sys(flags + lane) - target) >= 0;
+    if (!ok) ok = (int32_t)(vf[lane] - target) >= 0;  // relaxed polling; one acquire fence at the end
     if (__all_sync(0xffffffffu, ok)) break;
     if (global_timer_ns() - t0 > timeout_ns) {
       if (!ok) atomicExch(err, 1u + (uint32_t)lane);
       break;
     }
-    __nanosleep(256);
+    __nanosleep(2000);
   }
+  (void)ld_acquire_sys(flags + lane);
+  __threadfence_system();
 }
 
 struct MgTargets {
@@ -153,7 +183,11 @@ struct gffm_mg {
   int transport = 0;  // resolved GFFM_MG_*
   int requested = 0;
   bool p2p_ok = false;
-  cudaStream_t s_comm = nullptr, s_dist = nullptr, s_pull = nullptr, s_push = nullptr;
+  static constexpr int NCOPY = 4;  // parallel copy streams (one copy engine each) for the pulls and for the root's pushes
+  cudaStream_t s_comm = nullptr, s_dist = nullptr, s_pull[NCOPY] = {}, s_push[NCOPY] = {};
+  cudaEvent_t copy_ev[2][NCOPY] = {};  // joins of the copy streams (0: pulls, 1: pushes)
+  int ncopy = NCOPY;
+  bool wait_memops = false, signal_memops = false;  // flags through stream memory operations instead of one-warp kernels
   // arena: [control words | staging 0 | staging 1 | planes 0 | planes 1], one cudaMalloc, exported through CUDA IPC
   char* base = nullptr;
   size_t arena_bytes = 0, stage_bytes = 0, planes_bytes = 0;
@@ -189,8 +223,10 @@ int32_t mg_sync_streams(gffm_mg* mg) {
   GFFM_CUDA(cudaStreamSynchronize(mg->ctx->stream));
   if (mg->ctx->s_aux) GFFM_CUDA(cudaStreamSynchronize(mg->ctx->s_aux));
   GFFM_CUDA(cudaStreamSynchronize(mg->s_dist));
-  GFFM_CUDA(cudaStreamSynchronize(mg->s_pull));
-  GFFM_CUDA(cudaStreamSynchronize(mg->s_push));
+  for (int j = 0; j < gffm_mg::NCOPY; ++j) {
+    GFFM_CUDA(cudaStreamSynchronize(mg->s_pull[j]));
+    GFFM_CUDA(cudaStreamSynchronize(mg->s_push[j]));
+  }
   GFFM_CUDA(cudaStreamSynchronize(mg->s_comm));
   return GFFM_OK;
 }
@@ -297,6 +333,36 @@ int32_t mg_ensure_arena(gffm_mg* mg, size_t stage_bytes, size_t planes_bytes) {
   GFFM_CUDA(cudaMemcpy(word, &zero, sizeof(int), cudaMemcpyHostToDevice));
   mg->p2p_ok = all_ok == 1;
   if (!mg->p2p_ok) mg_close_peers(mg);
+  // can a stream memory operation write a flag into PEER memory?  Every rank writes a token into a test word of every peer, all
+  // ranks meet, every rank checks its own test words; one failure anywhere -> everybody signals with the one-warp kernel instead.
+  mg->signal_memops = false;
+  {
+    const char* f = getenv("GFFM_MG_FLAGS");
+    int mine_ok = (mg->p2p_ok && mg->wait_memops && mem_ops() && !(f && !strcmp(f, "kernel"))) ? 1 : 0;
+    const uint32_t token = 0xC0FFEE00u + (uint32_t)(mg->arena_bytes >> 20);
+    if (mine_ok) {
+      for (int q = 0; q < mg->nranks; ++q) {
+        if (q == mg->rank) continue;
+        if (mem_ops()->write32((CUstream)mg->s_comm, (CUdeviceptr)(uintptr_t)(mg->ctl(q) + F_PROBE + mg->rank), token, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS) mine_ok = 0;
+      }
+      if (cudaStreamSynchronize(mg->s_comm) != cudaSuccess) mine_ok = 0;
+      cudaGetLastError();
+    }
+    GFFM_TRY(mg_barrier_impl(mg));
+    if (mine_ok) {
+      uint32_t got[MG_MAX_RANKS] = {};
+      GFFM_CUDA(cudaMemcpy(got, mg->ctl(mg->rank) + F_PROBE, sizeof(uint32_t) * mg->nranks, cudaMemcpyDeviceToHost));
+      for (int q = 0; q < mg->nranks; ++q)
+        if (q != mg->rank && got[q] != token) mine_ok = 0;
+    }
+    GFFM_CUDA(cudaMemcpy(word, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+    MG_NCCL(nc->AllReduce(word, word, 1, ncclInt32, ncclMin, mg->comm, mg->s_comm));
+    GFFM_CUDA(cudaStreamSynchronize(mg->s_comm));
+    int all_sig = 0;
+    GFFM_CUDA(cudaMemcpy(&all_sig, word, sizeof(int), cudaMemcpyDeviceToHost));
+    GFFM_CUDA(cudaMemcpy(word, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    mg->signal_memops = all_sig == 1;
+  }
   if (mg->requested == GFFM_MG_P2P_PLANES && !mg->p2p_ok)
     GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "GFFM_MG_P2P_PLANES requested but peer memory (CUDA IPC / peer access) is not available between all ranks");
   mg->transport = mg->requested != GFFM_MG_AUTO ? mg->requested : (mg->p2p_ok ? GFFM_MG_P2P_PLANES : GFFM_MG_NCCL_PLANES);
@@ -304,16 +370,47 @@ int32_t mg_ensure_arena(gffm_mg* mg, size_t stage_bytes, size_t planes_bytes) {
   return GFFM_OK;
 }
 
+int mg_sid(gffm_mg* mg, cudaStream_t st) {
+  if (st == mg->s_dist) return 2;
+  if (st == mg->s_comm) return 5;
+  for (int j = 0; j < gffm_mg::NCOPY; ++j) {
+    if (st == mg->s_pull[j]) return 3;
+    if (st == mg->s_push[j]) return 4;
+  }
+  return 0;
+}
+
 int32_t mg_wait(gffm_mg* mg, cudaStream_t st, int word0, uint32_t mask, uint32_t target) {
   if (!mask) return GFFM_OK;
   uint32_t* ctl = mg->ctl(mg->rank);
-  mg_wait_kernel<<<1, 32, 0, st>>>(ctl + word0, mask, target, ctl + F_ERROR, mg->timeout_ns);
-  GFFM_LAUNCH_CHECK(mg->ctx);
+  cudaEvent_t tw = gffm_trace_begin(mg->ctx, st);
+  if (mg->wait_memops) {
+    MemOps* mo = mem_ops();
+    for (int i = 0; i < 32; ++i) {
+      if (!((mask >> i) & 1u)) continue;
+      const CUresult cr = mo->wait32((CUstream)st, (CUdeviceptr)(uintptr_t)(ctl + word0 + i), target, CU_STREAM_WAIT_VALUE_GEQ);
+      if (cr != CUDA_SUCCESS) GFFM_FAIL(GFFM_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult %d", (int)cr);
+    }
+  } else {
+    mg_wait_kernel<<<1, 32, 0, st>>>(ctl + word0, mask, target, ctl + F_ERROR, mg->timeout_ns);
+    GFFM_LAUNCH_CHECK(mg->ctx);
+  }
+  gffm_trace_end(mg->ctx, word0 == F_STAGED ? "wait:staged" : word0 == F_READY ? "wait:ready" : word0 == F_PULLED ? "wait:pulled" : "wait:splitdn", (int)target,
+                 mg_sid(mg, st), tw, st);
   return GFFM_OK;
 }
 
 int32_t mg_signal(gffm_mg* mg, cudaStream_t st, const MgTargets& t, int n, uint32_t value) {
   if (n <= 0) return GFFM_OK;
+  if (mg->signal_memops) {
+    MemOps* mo = mem_ops();
+    for (int i = 0; i < n; ++i) {
+      if (!t.p[i]) continue;
+      const CUresult cr = mo->write32((CUstream)st, (CUdeviceptr)(uintptr_t)t.p[i], value, CU_STREAM_WRITE_VALUE_DEFAULT);
+      if (cr != CUDA_SUCCESS) GFFM_FAIL(GFFM_ERR_CUDA, "cuStreamWriteValue32 failed with CUresult %d", (int)cr);
+    }
+    return GFFM_OK;
+  }
   mg_signal_kernel<<<1, 64, 0, st>>>(t, n, value);
   GFFM_LAUNCH_CHECK(mg->ctx);
   return GFFM_OK;
@@ -379,6 +476,11 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
   auto split_own = [&](int q, bool from_stage, int64_t ld_stage) -> int32_t {
     const int64_t c0 = out->off[q], cnt = out->off[q + 1] - c0;
     if (cnt <= 0) return GFFM_OK;
+    cudaEvent_t ts = gffm_trace_begin(ctx, mg->s_dist);
+    struct TraceGuard {
+      gffm_ctx* c; cudaEvent_t a; cudaStream_t st; int q;
+      ~TraceGuard() { gffm_trace_end(c, "splitB", q, 2, a, st); }
+    } guard{ctx, ts, mg->s_dist, q};
     for (int s = 0; s < R.nsets; ++s) {
       const MgSet& S = R.sets[s];
       MatView v, v2;
@@ -397,22 +499,35 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
   const int transport = (distributed && mg->transport == GFFM_MG_NCCL_BCAST) ? GFFM_MG_NCCL_PLANES : mg->transport;
   if (transport == GFFM_MG_P2P_PLANES) {
     // ---- root: push every other rank's uint32 column range into its staging buffer (copy engines, peer memory) -------------
+    const int nc = mg->ncopy;
     if (r == root) {
-      GFFM_CUDA(cudaStreamWaitEvent(mg->s_push, bready, 0));
+      for (int j = 0; j < nc; ++j) GFFM_CUDA(cudaStreamWaitEvent(mg->s_push[j], bready, 0));
       for (int i = 1; i < nr; ++i) {
         const int q = (root + i) % nr;
         const int64_t c0 = out->off[q], cnt = out->off[q + 1] - c0;
-        GFFM_TRY(mg_wait(mg, mg->s_push, F_SPLIT_DONE, 1u << q, e - 2));  // q has consumed what this staging buffer held
-        for (int s = 0; s < R.nsrc && cnt > 0; ++s) {
-          char* dst = mg->peer_base[q] + mg->stage_off(b) + (size_t)s * per * ld_c * 4;
-          GFFM_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld_c * 4, R.src[s].p + c0 * R.src[s].ld, (size_t)R.src[s].ld * 4, (size_t)kc * 4, (size_t)cnt,
-                                      cudaMemcpyDefault, mg->s_push));
+        // the columns of q's range are cut into `nc` chunks, one per copy stream; stream 0 joins them and raises q's flag
+        const int64_t chunk = round_up(ceil_div(std::max<int64_t>(cnt, 1), nc), 8);
+        for (int j = 0; j < nc; ++j) {
+          const int64_t j0 = std::min<int64_t>(cnt, (int64_t)j * chunk), j1 = std::min<int64_t>(cnt, (int64_t)(j + 1) * chunk);
+          if (j > 0 && j1 <= j0) continue;
+          GFFM_TRY(mg_wait(mg, mg->s_push[j], F_SPLIT_DONE, 1u << q, e - 2));  // q has consumed what this staging buffer held
+          cudaEvent_t tp = gffm_trace_begin(ctx, mg->s_push[j]);
+          for (int s = 0; s < R.nsrc && j1 > j0; ++s) {
+            char* dst = mg->peer_base[q] + mg->stage_off(b) + ((size_t)s * per + j0) * ld_c * 4;
+            GFFM_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld_c * 4, R.src[s].p + (c0 + j0) * R.src[s].ld, (size_t)R.src[s].ld * 4, (size_t)kc * 4,
+                                        (size_t)(j1 - j0), cudaMemcpyDefault, mg->s_push[j]));
+          }
+          gffm_trace_end(ctx, "push", q, 4, tp, mg->s_push[j]);
+          if (j > 0) {
+            GFFM_CUDA(cudaEventRecord(mg->copy_ev[1][j], mg->s_push[j]));
+            GFFM_CUDA(cudaStreamWaitEvent(mg->s_push[0], mg->copy_ev[1][j], 0));
+          }
         }
         MgTargets t;
         t.p[0] = mg->ctl(q) + F_STAGED;
-        GFFM_TRY(mg_signal(mg, mg->s_push, t, 1, e));
+        GFFM_TRY(mg_signal(mg, mg->s_push[0], t, 1, e));
       }
-      GFFM_CUDA(cudaEventRecord(mg->ev_push, mg->s_push));
+      GFFM_CUDA(cudaEventRecord(mg->ev_push, mg->s_push[0]));
     }
     // ---- every rank: split the own range ------------------------------------------------------------------------------------
     if (r != root && !distributed) GFFM_TRY(mg_wait(mg, mg->s_dist, F_STAGED, 1u, e));
@@ -430,28 +545,48 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       GFFM_TRY(mg_signal(mg, mg->s_dist, t, k, e));
     }
     // ---- every rank: pull the other ranges' planes from their owners ----------------------------------------------------------
-    GFFM_CUDA(cudaStreamWaitEvent(mg->s_pull, mg->gemm_done[b], 0));
+    for (int j = 0; j < nc; ++j) GFFM_CUDA(cudaStreamWaitEvent(mg->s_pull[j], mg->gemm_done[b], 0));
     for (int i = 1; i < nr; ++i) {
       const int q = (r + i) % nr;
       const int64_t cnt = out->off[q + 1] - out->off[q];
-      GFFM_TRY(mg_wait(mg, mg->s_pull, F_READY, 1u << q, e));
+      // piece (set, plane, row chunk) of q's range goes to copy stream (running piece index) % nc; stream 0 joins them.  With fewer
+      // planes than copy streams every plane is cut into row chunks so that all streams (copy engines) carry a share.
+      int pl = 0, total_planes = 0;
+      for (int s = 0; s < R.nsets; ++s) total_planes += gffm_bplan_spec(R.sets[s].plan)->nplanes;
+      const int parts = total_planes >= nc ? 1 : nc / std::max(total_planes, 1);
+      bool used[gffm_mg::NCOPY] = {};
+      cudaEvent_t tpl[gffm_mg::NCOPY] = {};
       for (int s = 0; s < R.nsets && cnt > 0; ++s) {
         const BPlaneSpec* sp = gffm_bplan_spec(R.sets[s].plan);
-        const size_t rel = R.sets[s].off + (size_t)q * per * sp->Kp;
         const size_t pitch = (size_t)rowsPB * sp->Kp;
-        if (pitch < (1ull << 31)) {
-          GFFM_CUDA(cudaMemcpy2DAsync(mg->planes(b) + rel, pitch, mg->peer_base[q] + mg->planes_off(b) + rel, pitch, (size_t)cnt * sp->Kp, (size_t)sp->nplanes,
-                                      cudaMemcpyDefault, mg->s_pull));
-        } else {  // beyond the 2-D copy's pitch limit: one contiguous copy per plane
-          for (int t = 0; t < sp->nplanes; ++t)
-            GFFM_CUDA(cudaMemcpyAsync(mg->planes(b) + rel + t * pitch, mg->peer_base[q] + mg->planes_off(b) + rel + t * pitch, (size_t)cnt * sp->Kp,
-                                      cudaMemcpyDefault, mg->s_pull));
+        const int64_t rows_part = ceil_div(cnt, parts);
+        for (int t = 0; t < sp->nplanes; ++t) {
+          for (int64_t i0 = 0; i0 < cnt; i0 += rows_part, ++pl) {
+            const int64_t ni = std::min(rows_part, cnt - i0);
+            const int j = pl % nc;
+            if (!used[j]) {
+              GFFM_TRY(mg_wait(mg, mg->s_pull[j], F_READY, 1u << q, e));
+              tpl[j] = gffm_trace_begin(ctx, mg->s_pull[j]);
+              used[j] = true;
+            }
+            const size_t rel = R.sets[s].off + (size_t)t * pitch + ((size_t)q * per + i0) * sp->Kp;
+            GFFM_CUDA(cudaMemcpyAsync(mg->planes(b) + rel, mg->peer_base[q] + mg->planes_off(b) + rel, (size_t)ni * sp->Kp, cudaMemcpyDefault, mg->s_pull[j]));
+          }
         }
       }
-      GFFM_CUDA(cudaEventRecord(mg->ready_ev[b][q], mg->s_pull));
+      if (!used[0]) GFFM_TRY(mg_wait(mg, mg->s_pull[0], F_READY, 1u << q, e));  // empty range: still part of the protocol
+      for (int j = 0; j < nc; ++j) {
+        if (!used[j]) continue;
+        gffm_trace_end(ctx, "pull", q, 3, tpl[j], mg->s_pull[j]);
+        if (j > 0) {
+          GFFM_CUDA(cudaEventRecord(mg->copy_ev[0][j], mg->s_pull[j]));
+          GFFM_CUDA(cudaStreamWaitEvent(mg->s_pull[0], mg->copy_ev[0][j], 0));
+        }
+      }
+      GFFM_CUDA(cudaEventRecord(mg->ready_ev[b][q], mg->s_pull[0]));
       MgTargets t;
       t.p[0] = mg->ctl(q) + F_PULLED + r;
-      GFFM_TRY(mg_signal(mg, mg->s_pull, t, 1, e));
+      GFFM_TRY(mg_signal(mg, mg->s_pull[0], t, 1, e));
     }
     for (int i = 0; i < nr; ++i) {
       out->order[i] = (r + i) % nr;
@@ -465,6 +600,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
     const int64_t cnt_r = out->off[r + 1] - out->off[r];
     GFFM_CUDA(cudaStreamWaitEvent(mg->s_comm, bready, 0));
     GFFM_CUDA(cudaStreamWaitEvent(mg->s_comm, mg->stage_free[b], 0));
+    cudaEvent_t tsc = gffm_trace_begin(ctx, mg->s_comm);
     if (nr > 1 && !distributed) {
       MG_NCCL(nc->GroupStart());
       if (r == root) {
@@ -481,6 +617,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       }
       MG_NCCL(nc->GroupEnd());
     }
+    gffm_trace_end(ctx, "scatter", 0, 5, tsc, mg->s_comm);
     GFFM_CUDA(cudaEventRecord(mg->staged[b], mg->s_comm));
     GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->staged[b], 0));
     GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->gemm_done[b], 0));
@@ -488,6 +625,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
     GFFM_CUDA(cudaEventRecord(mg->ready_ev[b][r], mg->s_dist));
     GFFM_CUDA(cudaEventRecord(mg->stage_free[b], mg->s_dist));
     GFFM_CUDA(cudaStreamWaitEvent(mg->s_comm, mg->ready_ev[b][r], 0));
+    cudaEvent_t tag = gffm_trace_begin(ctx, mg->s_comm);
     if (nr > 1) {
       MG_NCCL(nc->GroupStart());
       for (int s = 0; s < R.nsets; ++s) {
@@ -499,6 +637,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       }
       MG_NCCL(nc->GroupEnd());
     }
+    gffm_trace_end(ctx, "allgather", 0, 5, tag, mg->s_comm);
     GFFM_CUDA(cudaEventRecord(mg->gathered[b], mg->s_comm));
     GFFM_CUDA(cudaEventRecord(mg->ev_comm, mg->s_comm));
     for (int i = 0; i < nr; ++i) {
@@ -516,10 +655,12 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
     const int64_t c0 = out->off[q], cnt = out->off[q + 1] - c0;
     if (cnt > 0 && R.fresh_data && nr > 1) {
       GFFM_CUDA(cudaStreamWaitEvent(mg->s_comm, mg->bc_consumed[q], 0));  // the previous product has turned this range into planes
+      cudaEvent_t tb = gffm_trace_begin(ctx, mg->s_comm);
       for (int s = 0; s < R.nsrc; ++s) {
         uint32_t* buf = R.src[s].p + c0 * R.src[s].ld;
         MG_NCCL(nc->Broadcast(buf, buf, (size_t)((cnt - 1) * R.src[s].ld + kc), ncclUint32, root, mg->comm, mg->s_comm));
       }
+      gffm_trace_end(ctx, "bcast", q, 5, tb, mg->s_comm);
       GFFM_CUDA(cudaEventRecord(mg->bc_ev[q], mg->s_comm));
       GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->bc_ev[q], 0));
     }
@@ -597,8 +738,13 @@ extern "C" int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nran
       return GFFM_ERR_CUDA;
     }
   }
-  cudaStream_t* ss[4] = {&mg->s_comm, &mg->s_dist, &mg->s_pull, &mg->s_push};
-  for (auto s : ss) GFFM_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+  GFFM_CUDA(cudaStreamCreateWithFlags(&mg->s_comm, cudaStreamNonBlocking));
+  GFFM_CUDA(cudaStreamCreateWithFlags(&mg->s_dist, cudaStreamNonBlocking));
+  for (int j = 0; j < gffm_mg::NCOPY; ++j) {
+    GFFM_CUDA(cudaStreamCreateWithFlags(&mg->s_pull[j], cudaStreamNonBlocking));
+    GFFM_CUDA(cudaStreamCreateWithFlags(&mg->s_push[j], cudaStreamNonBlocking));
+  }
+  if (const char* t = getenv("GFFM_MG_COPY_STREAMS")) mg->ncopy = std::max(1, std::min((int)gffm_mg::NCOPY, atoi(t)));
   if (!ctx->s_aux) GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
   auto mk = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
   for (int b = 0; b < 2; ++b) {
@@ -611,6 +757,14 @@ extern "C" int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nran
   for (int q = 0; q < nranks; ++q) {
     GFFM_CUDA(mk(&mg->bc_ev[q]));
     GFFM_CUDA(mk(&mg->bc_consumed[q]));
+  }
+  for (int k = 0; k < 2; ++k)
+    for (int j = 0; j < gffm_mg::NCOPY; ++j) GFFM_CUDA(mk(&mg->copy_ev[k][j]));
+  {
+    const char* f = getenv("GFFM_MG_FLAGS");  // "kernel": one-warp polling / signalling kernels instead of stream memory operations
+    const bool want_memops = !(f && !strcmp(f, "kernel"));
+    mg->wait_memops = want_memops && mem_ops() != nullptr;
+    mg->signal_memops = false;  // decided per arena: the write must reach PEER memory (self-test in mg_ensure_arena)
   }
   GFFM_CUDA(mk(&mg->ev_call));
   GFFM_CUDA(mk(&mg->ev_push));
@@ -651,8 +805,14 @@ extern "C" int32_t gffm_mg_destroy(gffm_mg* mg) {
   }
   for (cudaEvent_t e : {mg->ev_call, mg->ev_push, mg->ev_comm})
     if (e) cudaEventDestroy(e);
-  for (cudaStream_t s : {mg->s_comm, mg->s_dist, mg->s_pull, mg->s_push})
+  for (cudaStream_t s : {mg->s_comm, mg->s_dist})
     if (s) cudaStreamDestroy(s);
+  for (int j = 0; j < gffm_mg::NCOPY; ++j) {
+    if (mg->s_pull[j]) cudaStreamDestroy(mg->s_pull[j]);
+    if (mg->s_push[j]) cudaStreamDestroy(mg->s_push[j]);
+    for (int k = 0; k < 2; ++k)
+      if (mg->copy_ev[k][j]) cudaEventDestroy(mg->copy_ev[k][j]);
+  }
   cudaGetLastError();
   delete mg;
   return GFFM_OK;
@@ -663,7 +823,7 @@ extern "C" int32_t gffm_mg_info(gffm_mg* mg, int32_t* rank, int32_t* nranks, int
   if (rank) *rank = mg->rank;
   if (nranks) *nranks = mg->nranks;
   if (transport) *transport = mg->transport;
-  if (peer_memory) *peer_memory = mg->p2p_ok ? 1 : 0;
+  if (peer_memory) *peer_memory = (mg->p2p_ok ? 1 : 0) | (mg->wait_memops ? 2 : 0) | (mg->signal_memops ? 4 : 0);
   return GFFM_OK;
 }
 
@@ -691,6 +851,7 @@ extern "C" int32_t gffm_mg_barrier(gffm_mg* mg) {
   if (!mg) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   GFFM_ENTER_CTX(mg->ctx);
   GFFM_TRY(mg_sync_streams(mg));
+  gffm_trace_dump(mg->ctx, mg->rank);
   if (mg->nranks > 1) GFFM_TRY(mg_barrier_impl(mg));
   if (mg->base) {  // a polling kernel that gave up leaves its mark in the control words
     uint32_t err = 0;

@@ -38,6 +38,12 @@ class Context:
     def set_stream(self, cuda_stream_ptr: int):
         capi.check(self.lib.gffm_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def get_stream(self) -> int:
+        """Raw cudaStream_t of the context (e.g. for torch.cuda.ExternalStream)."""
+        p = C.c_void_p()
+        capi.check(self.lib.gffm_get_stream(self.h, C.byref(p)))
+        return p.value or 0
+
     def set_profiling(self, on: bool):
         capi.check(self.lib.gffm_set_profiling(self.h, 1 if on else 0))
 
@@ -72,7 +78,19 @@ class Context:
 _tls = threading.local()
 
 
-def default_context(device: int = 0) -> Context:
+_default_device = 0
+
+
+def set_default_device(device: int):
+    """Device of the context that `default_context()` (and every constructor called without `ctx=`) uses -- one rank per GPU sets it to
+    its LOCAL_RANK once (CUDA.device!(...) in the reference's host runtime)."""
+    global _default_device
+    _default_device = int(device)
+
+
+def default_context(device: int = None) -> Context:
+    if device is None:
+        device = _default_device
     ctxs = getattr(_tls, "ctxs", None)
     if ctxs is None:
         ctxs = _tls.ctxs = {}

@@ -256,7 +256,8 @@ class MultiGpu:
     def info(self):
         r, n, t, p = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         capi.check(self.lib.gffm_mg_info(self.h, ctypes.byref(r), ctypes.byref(n), ctypes.byref(t), ctypes.byref(p)))
-        return {"rank": r.value, "nranks": n.value, "transport": TRANSPORT_NAMES.get(t.value, str(t.value)), "peer_memory": bool(p.value)}
+        return {"rank": r.value, "nranks": n.value, "transport": TRANSPORT_NAMES.get(t.value, str(t.value)), "peer_memory": bool(p.value & 1),
+                "flag_waits": "stream memory ops" if p.value & 2 else "polling kernel", "flag_writes": "stream memory ops" if p.value & 4 else "signal kernel"}
 
     def set_transport(self, transport: int):
         capi.check(self.lib.gffm_mg_set_transport(self.h, int(transport)))

@@ -197,6 +197,7 @@ int32_t gffm_mg_unique_id(void* id128);
 /* ctx = this rank's context (its device).  NCCL is dlopen'ed (libnccl.so.2, or $GFFM_NCCL_LIB) */
 int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nranks, int32_t rank, gffm_mg** out);
 int32_t gffm_mg_destroy(gffm_mg* mg);
+/* peer_memory: bit 0 = peer mappings established, bit 1 = flag waits are stream memory operations, bit 2 = flag writes are too */
 int32_t gffm_mg_info(gffm_mg* mg, int32_t* rank, int32_t* nranks, int32_t* transport, int32_t* peer_memory);
 int32_t gffm_mg_set_transport(gffm_mg* mg, int32_t transport);
 /* drains this rank's streams, meets the other ranks, reports a peer-flag time-out of an earlier product */

@@ -32,7 +32,8 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29531")
     dist.init_process_group("gloo", rank=rank, world_size=world)  # plumbing only (id exchange, verdict reduction): CPU backend
-    ctx = g.Context(local)
+    g.set_default_device(local)  # the matrices below are created on the default context: make it this rank's device
+    ctx = g.default_context()
     mgpu = g.multigpu.MultiGpu.from_torch_distributed(dist, ctx)
     mg = g.multigpu
     results = []
