@@ -325,7 +325,7 @@ def main():
                     help="N > 1: 'cabi' = the library's multi-GPU layer (gffm_mg_gemm / gffm_mg_kmat_mul, csrc/mg.cu); 'python' = the round-1 driver "
                          "(torch.distributed broadcast of B in panels + gffm_gemm_panels), kept for A/B comparisons")
     ap.add_argument("--transport", default="tune",
-                    help="N > 1, --mg cabi: p2p_planes | nccl_planes | nccl_bcast | auto, or 'tune' (default): each available transport is tried for a few "
+                    help="N > 1, --mg cabi: p2p_push | p2p_planes | nccl_planes | nccl_bcast | auto, or 'tune' (default): each available transport is tried for a few "
                          "untimed steps and the fastest is used for the timed region (trial times in config.warmup_trials_ms)")
     ap.add_argument("--panels", type=int, default=8, help="--mg python: column panels of B per broadcast")
     ap.add_argument("--no-cpu", action="store_true")
@@ -461,8 +461,9 @@ def main():
                 else:
                     mgpu.gemm(C, A, B, root=0, b_ready=b_ready.cuda_event)
 
-            names = {"p2p_planes": g.capi.MG_P2P_PLANES, "nccl_planes": g.capi.MG_NCCL_PLANES, "nccl_bcast": g.capi.MG_NCCL_BCAST, "auto": g.capi.MG_AUTO}
-            cands = ["p2p_planes", "nccl_planes", "nccl_bcast"] if args.transport == "tune" else [t.strip() for t in args.transport.split(",")]
+            names = {"p2p_push": g.capi.MG_P2P_PUSH, "p2p_planes": g.capi.MG_P2P_PLANES, "nccl_planes": g.capi.MG_NCCL_PLANES, "nccl_bcast": g.capi.MG_NCCL_BCAST,
+                     "auto": g.capi.MG_AUTO}
+            cands = ["p2p_push", "p2p_planes", "nccl_planes", "nccl_bcast"] if args.transport == "tune" else [t.strip() for t in args.transport.split(",")]
             best = None
             for tname in cands:
                 ok_t = True

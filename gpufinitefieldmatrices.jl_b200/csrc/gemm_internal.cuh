@@ -26,6 +26,10 @@ const BPlaneSpec* gffm_bplan_spec(const GemmBPlan* plan);
 int32_t gffm_bplan_split(gffm_ctx* ctx, const GemmBPlan* plan, MatView B, const MatView* B2, uint8_t* planes, int64_t rowsPB, int64_t row0,
                          cudaStream_t st);
 
+// Fused split + push: the same split, every 16-byte chunk stored to `nbufs` plane buffers (local and peer memory) of identical layout.
+int32_t gffm_bplan_split_push(gffm_ctx* ctx, const GemmBPlan* plan, MatView B, const MatView* B2, uint8_t* const* plane_bufs, int nbufs, int64_t rowsPB,
+                              int64_t row0, cudaStream_t st);
+
 struct ExtBPlanes {
   const uint8_t* planes = nullptr;  // [nplanes][rowsPB][Kp]
   int64_t rowsPB = 0;

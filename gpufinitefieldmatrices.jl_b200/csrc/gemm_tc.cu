@@ -845,6 +845,53 @@ struct Encoder {
 // B operand (k x n column-major, K contiguous already): thread = 16 consecutive k of one column j; a warp reads 2 KiB
 // and writes 512 contiguous bytes per plane.
 // Optional second source (Karatsuba prologue fusion, reference KaratsubaKernels.jl:129-139): x = src + src2.
+// Fused split + push (multi-GPU layer, mg.cu): the same split, but every 16-byte chunk of every plane is stored to `nd` plane
+// buffers at once -- the local one and the peers' (NVLink peer memory, posted stores).  The owner of a column range of B thereby
+// delivers its operand planes to all ranks in the pass that creates them: no staging copy, no separate collective.
+struct PlaneDests {
+  uint8_t* p[32];
+  int n;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+split_b_push_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2, int K, int ncols, int64_t Kp,
+                    int64_t rowsP, const __grid_constant__ SplitParams sp, const __grid_constant__ PlaneDests dests) {
+  const int64_t k16 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const int j = blockIdx.y;
+  if (k16 >= Kp || j >= ncols) return;
+  uint32_t x[16];
+  const uint32_t* col = src + (int64_t)j * ld + k16;
+  if (k16 + 15 < K && ((reinterpret_cast<uintptr_t>(col) & 15) == 0)) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 v = reinterpret_cast<const uint4*>(col)[g];
+      x[4 * g] = v.x; x[4 * g + 1] = v.y; x[4 * g + 2] = v.z; x[4 * g + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) x[t] = (k16 + t < K) ? col[t] : 0u;
+  }
+  if (src2) {
+    const uint32_t* col2 = src2 + (int64_t)j * ld2 + k16;
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if (k16 + t < K) x[t] += col2[t];
+  }
+  Encoder<MODE, 16> enc;
+  enc.prepare(x, sp);
+  const int64_t off = (int64_t)j * Kp + k16;
+  const int64_t pstride = rowsP * Kp;
+#pragma unroll 1
+  for (int pl = 0; pl < sp.nplanes; ++pl) {
+    uint32_t w[4];
+    enc.plane(pl, sp, w);
+    const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll 1
+    for (int d = 0; d < dests.n; ++d) *reinterpret_cast<uint4*>(dests.p[d] + off + pl * pstride) = v;
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128)
 split_b_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2, int K, int ncols,
@@ -1132,8 +1179,25 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
 }
 
 int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2, int64_t k_off, int64_t kc, uint8_t* planes,
-                  int64_t Kp, int64_t rowsP, const SplitParams& sp, cudaStream_t st = nullptr) {
+                  int64_t Kp, int64_t rowsP, const SplitParams& sp, cudaStream_t st = nullptr, const PlaneDests* dests = nullptr) {
   if (!st) st = ctx->stream;
+  if (dests && !is_a) {  // fused split + push: `planes` is ignored, every destination gets the rows [row0, row0 + cols) the caller offset into dests
+    for (int64_t c0 = 0; c0 < X.cols; c0 += 65535) {
+      const int64_t nc = std::min<int64_t>(65535, X.cols - c0);
+      const uint32_t* s = X.p + k_off + c0 * X.ld;
+      const uint32_t* s2 = X2 ? X2->p + k_off + c0 * X2->ld : nullptr;
+      PlaneDests d = *dests;
+      for (int i = 0; i < d.n; ++i) d.p[i] += c0 * Kp;
+      dim3 grid((unsigned)ceil_div(Kp / 16, 128), (unsigned)nc);
+#define GFFM_SPLIT_BP(MODE) split_b_push_kernel<MODE><<<grid, 128, 0, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)nc, Kp, rowsP, sp, d)
+      if (sp.mode == 0) GFFM_SPLIT_BP(0);
+      else if (sp.mode == 1) GFFM_SPLIT_BP(1);
+      else GFFM_SPLIT_BP(2);
+#undef GFFM_SPLIT_BP
+      GFFM_LAUNCH_CHECK(ctx);
+    }
+    return GFFM_OK;
+  }
   if (is_a) {
     // A is m x K: rows = i, K along columns of the view
     const uint32_t* s = X.p + k_off * X.ld;
@@ -2120,6 +2184,18 @@ int32_t gffm_bplan_split(gffm_ctx* ctx, const GemmBPlan* g, MatView B, const Mat
   if (B.cols == 0) return GFFM_OK;
   if (row0 < 0 || row0 + B.cols > rowsPB) GFFM_FAIL(GFFM_ERR_INVALID, "plane split: rows [%lld, %lld) outside the buffer", (long long)row0, (long long)(row0 + B.cols));
   return run_split(ctx, false, B, B2, 0, g->kc, planes + row0 * g->Kp, g->Kp, rowsPB, g->sp, st);
+}
+
+int32_t gffm_bplan_split_push(gffm_ctx* ctx, const GemmBPlan* g, MatView B, const MatView* B2, uint8_t* const* plane_bufs, int nbufs, int64_t rowsPB,
+                              int64_t row0, cudaStream_t st) {
+  if (B.rows != g->kc) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "plane split: %lld rows, plan has %lld", (long long)B.rows, (long long)g->kc);
+  if (B.cols == 0 || nbufs <= 0) return GFFM_OK;
+  if (nbufs > 32) GFFM_FAIL(GFFM_ERR_INVALID, "at most 32 destinations");
+  if (row0 < 0 || row0 + B.cols > rowsPB) GFFM_FAIL(GFFM_ERR_INVALID, "plane split: rows outside the buffer");
+  PlaneDests d;
+  d.n = nbufs;
+  for (int i = 0; i < nbufs; ++i) d.p[i] = plane_bufs[i] + row0 * g->Kp;
+  return run_split(ctx, false, B, B2, 0, g->kc, nullptr, g->Kp, rowsPB, g->sp, st, &d);
 }
 
 int32_t gffm_bplan_gemm(gffm_ctx* ctx, const GemmBPlan* g, MatView Cv, MatView A, const MatView* A2, int64_t n, const ExtBPlanes& ext,

@@ -15,6 +15,10 @@
 //                       through the static tile schedule; profiles/r02_notes.md).  Kernel-based flags (bounded polling) remain as
 //                       the fallback where the memory operations are not available (GFFM_MG_FLAGS=kernel forces them).
 //                       Transfers are spread over several copy streams (one copy engine each).
+//   GFFM_MG_P2P_PUSH    the owner's split kernel stores every plane chunk to ALL ranks' plane buffers at once (fused split + push,
+//                       posted NVLink stores from the kernel that creates the planes): no staging copy of the planes, no pull, the
+//                       copy engines only carry the root's uint32 ranges.  Consumers wait for the owner's epoch flag, owners wait
+//                       for the consumers' "buffer free" flags.
 //   GFFM_MG_NCCL_PLANES the same data flow with NCCL: grouped ncclSend/ncclRecv scatter of the uint32 ranges, one grouped
 //                       in-place ncclAllGather of the planes.
 //   GFFM_MG_NCCL_BCAST  ncclBroadcast of B's uint32 column ranges, every rank splits all of B (round-1 data flow).
@@ -35,7 +39,7 @@ namespace {
 constexpr int MG_MAX_RANKS = 32;
 constexpr size_t MG_CTL_BYTES = 4096;
 // control words (uint32) at the start of every rank's arena
-enum { F_STAGED = 0, F_READY = 64, F_PULLED = 128, F_SPLIT_DONE = 192, F_ERROR = 256, F_PROBE = 320 };
+enum { F_STAGED = 0, F_READY = 64, F_PULLED = 128, F_SPLIT_DONE = 192, F_ERROR = 256, F_PROBE = 320, F_FREE = 384 };
 
 struct NcclApi {
   void* h = nullptr;
@@ -363,9 +367,9 @@ int32_t mg_ensure_arena(gffm_mg* mg, size_t stage_bytes, size_t planes_bytes) {
     GFFM_CUDA(cudaMemcpy(word, &zero, sizeof(int), cudaMemcpyHostToDevice));
     mg->signal_memops = all_sig == 1;
   }
-  if (mg->requested == GFFM_MG_P2P_PLANES && !mg->p2p_ok)
-    GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "GFFM_MG_P2P_PLANES requested but peer memory (CUDA IPC / peer access) is not available between all ranks");
-  mg->transport = mg->requested != GFFM_MG_AUTO ? mg->requested : (mg->p2p_ok ? GFFM_MG_P2P_PLANES : GFFM_MG_NCCL_PLANES);
+  if ((mg->requested == GFFM_MG_P2P_PLANES || mg->requested == GFFM_MG_P2P_PUSH) && !mg->p2p_ok)
+    GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "a peer-memory transport was requested but peer memory (CUDA IPC / peer access) is not available between all ranks");
+  mg->transport = mg->requested != GFFM_MG_AUTO ? mg->requested : (mg->p2p_ok ? GFFM_MG_P2P_PUSH : GFFM_MG_NCCL_PLANES);
   mg->epoch = 0;
   return GFFM_OK;
 }
@@ -473,6 +477,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
     GFFM_CUDA(cudaEventRecord(mg->ev_call, ctx->stream));
     bready = mg->ev_call;
   }
+  bool push_planes = false;  // GFFM_MG_P2P_PUSH: the split stores to every rank's plane buffer
   auto split_own = [&](int q, bool from_stage, int64_t ld_stage) -> int32_t {
     const int64_t c0 = out->off[q], cnt = out->off[q + 1] - c0;
     if (cnt <= 0) return GFFM_OK;
@@ -490,14 +495,22 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       };
       v = view_of_src(S.src);
       if (S.src2 >= 0) v2 = view_of_src(S.src2);
-      GFFM_TRY(gffm_bplan_split(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, out->planes + S.off, rowsPB, (int64_t)q * per, mg->s_dist));
+      if (push_planes) {
+        uint8_t* bufs[MG_MAX_RANKS];
+        for (int d = 0; d < nr; ++d) bufs[d] = (uint8_t*)((d == r ? mg->base : mg->peer_base[d]) + mg->planes_off(b) + S.off);
+        std::swap(bufs[0], bufs[r]);  // local destination first
+        GFFM_TRY(gffm_bplan_split_push(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, bufs, nr, rowsPB, (int64_t)q * per, mg->s_dist));
+      } else {
+        GFFM_TRY(gffm_bplan_split(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, out->planes + S.off, rowsPB, (int64_t)q * per, mg->s_dist));
+      }
     }
     return GFFM_OK;
   };
 
   const bool distributed = root < 0;  // every rank already holds its own column range of B: nothing to push / scatter
   const int transport = (distributed && mg->transport == GFFM_MG_NCCL_BCAST) ? GFFM_MG_NCCL_PLANES : mg->transport;
-  if (transport == GFFM_MG_P2P_PLANES) {
+  push_planes = transport == GFFM_MG_P2P_PUSH;
+  if (transport == GFFM_MG_P2P_PLANES || transport == GFFM_MG_P2P_PUSH) {
     // ---- root: push every other rank's uint32 column range into its staging buffer (copy engines, peer memory) -------------
     const int nc = mg->ncopy;
     if (r == root) {
@@ -533,7 +546,9 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
     if (r != root && !distributed) GFFM_TRY(mg_wait(mg, mg->s_dist, F_STAGED, 1u, e));
     else GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, bready, 0));
     GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->gemm_done[b], 0));                       // the local GEMMs of epoch e-2 are done with this buffer
-    GFFM_TRY(mg_wait(mg, mg->s_dist, F_PULLED, ((nr >= 32 ? 0xffffffffu : ((1u << nr) - 1u)) & ~(1u << r)), e - 2));  // ... and so are the peers' pulls
+    const uint32_t others = (nr >= 32 ? 0xffffffffu : ((1u << nr) - 1u)) & ~(1u << r);
+    if (push_planes) GFFM_TRY(mg_wait(mg, mg->s_dist, F_FREE, others, e - 2));  // every peer's GEMMs of epoch e-2 are done with ITS copy of this buffer
+    else GFFM_TRY(mg_wait(mg, mg->s_dist, F_PULLED, others, e - 2));           // ... and so are the peers' pulls from this buffer
     GFFM_TRY(split_own(r, r != root && !distributed, ld_c));
     GFFM_CUDA(cudaEventRecord(mg->ready_ev[b][r], mg->s_dist));
     {
@@ -541,8 +556,25 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       int k = 0;
       for (int q = 0; q < nr; ++q)
         if (q != r) t.p[k++] = mg->ctl(q) + F_READY + r;
-      if (r != root && !distributed) t.p[k++] = mg->ctl(root) + F_SPLIT_DONE + r;
       GFFM_TRY(mg_signal(mg, mg->s_dist, t, k, e));
+      // "my staging buffer of this parity is free again": told to EVERY rank, because any of them may be the root of a later product
+      k = 0;
+      for (int q = 0; q < nr; ++q)
+        if (q != r) t.p[k++] = mg->ctl(q) + F_SPLIT_DONE + r;
+      GFFM_TRY(mg_signal(mg, mg->s_dist, t, k, e));
+    }
+    if (push_planes) {
+      // ---- consumers: the planes arrive by themselves; the arrival stream turns the owners' flags into events for the GEMMs ----
+      for (int i = 1; i < nr; ++i) {
+        const int q = (r + i) % nr;
+        GFFM_TRY(mg_wait(mg, mg->s_pull[0], F_READY, 1u << q, e));
+        GFFM_CUDA(cudaEventRecord(mg->ready_ev[b][q], mg->s_pull[0]));
+      }
+      for (int i = 0; i < nr; ++i) {
+        out->order[i] = (r + i) % nr;
+        out->ready[i] = mg->ready_ev[b][i];
+      }
+      return GFFM_OK;
     }
     // ---- every rank: pull the other ranges' planes from their owners ----------------------------------------------------------
     for (int j = 0; j < nc; ++j) GFFM_CUDA(cudaStreamWaitEvent(mg->s_pull[j], mg->gemm_done[b], 0));
@@ -679,7 +711,17 @@ int32_t mg_round_done(gffm_mg* mg, const MgRound& R, const MgRoundOut& out) {
   gffm_ctx* ctx = mg->ctx;
   GFFM_CUDA(cudaEventRecord(mg->gemm_done[out.b], ctx->stream));
   // the caller may modify B (root) / reuse its receive buffer once the context stream has passed this point
-  if (mg->transport == GFFM_MG_P2P_PLANES) {
+  if (mg->transport == GFFM_MG_P2P_PUSH) {
+    // tell every owner that this rank's copy of plane buffer b is free again (after the GEMMs just enqueued): side stream, so the
+    // context stream carries nothing but compute
+    GFFM_CUDA(cudaStreamWaitEvent(mg->s_pull[1], mg->gemm_done[out.b], 0));
+    MgTargets t;
+    int k = 0;
+    for (int q = 0; q < mg->nranks; ++q)
+      if (q != mg->rank) t.p[k++] = mg->ctl(q) + F_FREE + mg->rank;
+    GFFM_TRY(mg_signal(mg, mg->s_pull[1], t, k, mg->epoch));
+  }
+  if (mg->transport == GFFM_MG_P2P_PLANES || mg->transport == GFFM_MG_P2P_PUSH) {
     if (mg->rank == R.root) GFFM_CUDA(cudaStreamWaitEvent(ctx->stream, mg->ev_push, 0));
   } else {
     GFFM_CUDA(cudaStreamWaitEvent(ctx->stream, mg->ev_comm, 0));
@@ -830,7 +872,7 @@ extern "C" int32_t gffm_mg_info(gffm_mg* mg, int32_t* rank, int32_t* nranks, int
 extern "C" int32_t gffm_mg_set_transport(gffm_mg* mg, int32_t transport) {
   if (!mg) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   GFFM_ENTER_CTX(mg->ctx);
-  if (transport < GFFM_MG_AUTO || transport > GFFM_MG_P2P_PLANES) GFFM_FAIL(GFFM_ERR_INVALID, "unknown transport %d", transport);
+  if (transport < GFFM_MG_AUTO || transport > GFFM_MG_P2P_PUSH) GFFM_FAIL(GFFM_ERR_INVALID, "unknown transport %d", transport);
   if (transport == mg->requested) return GFFM_OK;  // every rank passes the same value, so every rank returns here or nobody does
   // collective: drain everything, then let the next product rebuild the arena (and the peer mappings) under the new setting
   GFFM_TRY(mg_sync_streams(mg));

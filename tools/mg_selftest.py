@@ -53,7 +53,8 @@ def main():
             print(f"[mg_selftest] {'ok  ' if good else 'FAIL'} {what}", file=sys.stderr, flush=True)
         return good
 
-    transports = [(mg.capi.MG_NCCL_BCAST, "nccl_bcast"), (mg.capi.MG_NCCL_PLANES, "nccl_planes"), (mg.capi.MG_P2P_PLANES, "p2p_planes")]
+    transports = [(mg.capi.MG_NCCL_BCAST, "nccl_bcast"), (mg.capi.MG_NCCL_PLANES, "nccl_planes"), (mg.capi.MG_P2P_PLANES, "p2p_planes"),
+                  (mg.capi.MG_P2P_PUSH, "p2p_push")]
     if os.environ.get("MG_SELFTEST_TRANSPORTS"):
         want = os.environ["MG_SELFTEST_TRANSPORTS"].split(",")
         transports = [t for t in transports if t[1] in want]
