@@ -399,7 +399,7 @@ int32_t mg_wait(gffm_mg* mg, cudaStream_t st, int word0, uint32_t mask, uint32_t
     mg_wait_kernel<<<1, 32, 0, st>>>(ctl + word0, mask, target, ctl + F_ERROR, mg->timeout_ns);
     GFFM_LAUNCH_CHECK(mg->ctx);
   }
-  gffm_trace_end(mg->ctx, word0 == F_STAGED ? "wait:staged" : word0 == F_READY ? "wait:ready" : word0 == F_PULLED ? "wait:pulled" : "wait:splitdn", (int)target,
+  gffm_trace_end(mg->ctx, word0 == F_STAGED ? "wait:staged" : word0 == F_READY ? "wait:ready" : word0 == F_PULLED ? "wait:pulled" : word0 == F_FREE ? "wait:free" : "wait:splitdn", (int)target,
                  mg_sid(mg, st), tw, st);
   return GFFM_OK;
 }
