@@ -11,7 +11,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgffm.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
-SOURCES = ["api.cu", "gemm_tc.cu", "pluq.cu", "karatsuba.cu", "gemv.cu", "mg.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "pluq.cu", "karatsuba.cu", "gemv.cu", "mg.cu", "wide.cu"]
 
 
 def _newer(target, deps):

@@ -275,7 +275,6 @@ extern "C" int32_t gffm_mat_create(gffm_ctx* ctx, int64_t rows, int64_t cols, ui
   if (rows < 0 || cols < 0) GFFM_FAIL(GFFM_ERR_INVALID, "negative size");
   if (N > (1ull << 52)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "Modulus is bigger than 2^52");  // CuModMatrix.jl:55-59
   if (N == 0) GFFM_FAIL(GFFM_ERR_INVALID, "modulus must be positive");
-  if (N > (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "moduli above 2^32 need the wide (uint64) storage, not built yet");
   if (pad < 0) pad = GFFM_REF_PAD;
   gffm_mat* m = new gffm_mat();
   m->ctx = ctx;
@@ -287,13 +286,17 @@ extern "C" int32_t gffm_mat_create(gffm_ctx* ctx, int64_t rows, int64_t cols, ui
   m->pcols = cols + pad > 0 ? cols + pad : 1;
   m->owned = true;
   cudaSetDevice(ctx->device);
-  size_t bytes = (size_t)m->ld * m->pcols * sizeof(uint32_t);
-  cudaError_t e = gffm_dev_alloc(ctx, (void**)&m->data, bytes);
+  m->wide = N > (1ull << 32);  // uint64 residues (wide.cu)
+  size_t bytes = (size_t)m->ld * m->pcols * (m->wide ? sizeof(uint64_t) : sizeof(uint32_t));
+  void* mem = nullptr;
+  cudaError_t e = gffm_dev_alloc(ctx, &mem, bytes);
   if (e != cudaSuccess) {
     delete m;
     GFFM_FAIL(GFFM_ERR_OOM, "device allocation of %zu bytes failed", bytes);
   }
-  GFFM_CUDA(cudaMemsetAsync(m->data, 0, bytes, ctx->stream));
+  if (m->wide) m->data64 = mem;
+  else m->data = (uint32_t*)mem;
+  GFFM_CUDA(cudaMemsetAsync(mem, 0, bytes, ctx->stream));
   *out = m;
   return GFFM_OK;
 }
@@ -347,6 +350,7 @@ extern "C" int32_t gffm_mat_destroy(gffm_mat* m) {
   cudaSetDevice(m->ctx->device);
   if (m->cache[0].ptr || m->cache[1].ptr) free_plane_caches(m);
   if (m->owned && m->data) gffm_dev_free(m->ctx, m->data);
+  if (m->owned && m->data64) gffm_dev_free(m->ctx, m->data64);
   delete m;
   return GFFM_OK;
 }
@@ -362,7 +366,7 @@ MAT_GETTER(cols, int64_t, m->cols)
 MAT_GETTER(pad, int32_t, m->pad)
 MAT_GETTER(modulus, uint64_t, m->N)
 MAT_GETTER(ld, int64_t, m->ld)
-MAT_GETTER(device_ptr, void*, (void*)m->data)
+MAT_GETTER(device_ptr, void*, m->wide ? m->data64 : (void*)m->data)
 
 // ---- conversion kernels ----------------------------------------------------------------------
 template <typename T>
@@ -437,6 +441,7 @@ extern "C" int32_t gffm_mat_upload(gffm_mat* m, const void* host, int32_t dtype,
   gffm_touch(m);
   gffm_ctx* ctx = m->ctx;
   cudaSetDevice(ctx->device);
+  if (m->wide) return gffm_wide_upload(m, host, dtype, ld, do_mod);
   if (dtype == GFFM_U32) {
     // residues already in storage format: one strided DMA straight into the matrix, reduction in place
     GFFM_CUDA(cudaMemcpy2DAsync(m->data, (size_t)m->ld * 4, host, (size_t)ld * 4, (size_t)m->rows * 4, (size_t)m->cols,
@@ -490,6 +495,7 @@ extern "C" int32_t gffm_mat_download(gffm_mat* m, void* host, int32_t dtype, int
   if (!host) GFFM_FAIL(GFFM_ERR_INVALID, "null host buffer");
   gffm_ctx* ctx = m->ctx;
   cudaSetDevice(ctx->device);
+  if (m->wide) return gffm_wide_download(m, host, dtype, ld, with_padding);
   if (dtype == GFFM_U32 && (!with_padding || (rows <= m->ld && cols <= m->pcols))) {
     GFFM_CUDA(cudaMemcpy2DAsync(host, (size_t)ld * 4, m->data, (size_t)m->ld * 4, (size_t)rows * 4, (size_t)cols,
                                 cudaMemcpyDeviceToHost, ctx->stream));
@@ -592,6 +598,7 @@ extern "C" int32_t gffm_ewise(int32_t op, gffm_mat* C, gffm_mat* A, gffm_mat* B,
   if (!mod_override) {  // reference checks moduli unless mod_N is given (CuModMatrix.jl add!/sub! preambles)
     if (A->N != C->N || (B && B->N != C->N)) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "operands have different moduli");
   }
+  if (gffm_any_wide({C, A, B})) return gffm_wide_ewise(op, C, A, B, scalar, P);
   MatView bv;
   if (B) bv = view_of(B);
   return gffm_ew_views(C->ctx, op, view_of(C), view_of(A), B ? &bv : nullptr, scalar, P);
@@ -660,6 +667,7 @@ extern "C" int32_t gffm_mat_copy(gffm_mat* dst, gffm_mat* src) {
   if (!dst || !src) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (dst->rows != src->rows || dst->cols != src->cols) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "copy!: sizes differ");
   gffm_touch(dst);
+  if (gffm_any_wide({dst, src})) return gffm_wide_copy(dst, src);
   return gffm_copy_views(dst->ctx, view_of(dst), view_of(src));
 }
 extern "C" int32_t gffm_mat_copy_block(gffm_mat* dst, int64_t dr0, int64_t dc0, gffm_mat* src, int64_t sr0, int64_t sc0, int64_t nr, int64_t nc) {
@@ -668,6 +676,7 @@ extern "C" int32_t gffm_mat_copy_block(gffm_mat* dst, int64_t dr0, int64_t dc0, 
   if (dr0 < 0 || dc0 < 0 || sr0 < 0 || sc0 < 0 || nr < 0 || nc < 0 || dr0 + nr > dst->rows || dc0 + nc > dst->cols ||
       sr0 + nr > src->rows || sc0 + nc > src->cols)
     GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "block out of range");
+  GFFM_NARROW_ONLY(dst, src);
   gffm_touch(dst);
   return gffm_copy_views(dst->ctx, sub_view(view_of(dst), dr0, dc0, nr, nc), sub_view(view_of(src), sr0, sc0, nr, nc));
 }
@@ -675,6 +684,7 @@ extern "C" int32_t gffm_mat_fill(gffm_mat* m, int64_t value) {
   GFFM_ENTER_MAT(m);
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   gffm_touch(m);
+  if (m->wide) return gffm_wide_fill(m, value, 0, 0, 0, m->rows, m->cols);
   return gffm_fill_view(m->ctx, view_of(m), scalar_residue(value, m->N));
 }
 extern "C" int32_t gffm_mat_zero(gffm_mat* m) { return gffm_mat_fill(m, 0); }
@@ -683,6 +693,7 @@ extern "C" int32_t gffm_mat_eye(gffm_mat* m) {
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (m->rows * m->cols == 0) return GFFM_OK;
   gffm_touch(m);
+  if (m->wide) return gffm_wide_fill(m, 1, 1, 0, 0, m->rows, m->cols);
   fill_kernel<<<grid_for(m->ctx, m->rows * m->cols), 256, 0, m->ctx->stream>>>(m->data, m->ld, m->rows, m->cols, scalar_residue(1, m->N), 1);
   GFFM_LAUNCH_CHECK(m->ctx);
   return GFFM_OK;
@@ -692,6 +703,7 @@ extern "C" int32_t gffm_mat_synth(gffm_mat* m, uint64_t seed) {
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (m->rows * m->cols == 0) return GFFM_OK;
   gffm_touch(m);
+  if (m->wide) return gffm_wide_synth(m, seed);
   synth_kernel<<<grid_for(m->ctx, m->rows * m->cols), 256, 0, m->ctx->stream>>>(m->data, m->ld, m->rows, m->cols, seed, m->N);
   GFFM_LAUNCH_CHECK(m->ctx);
   return GFFM_OK;
@@ -703,7 +715,12 @@ extern "C" int32_t gffm_mat_set_modulus(gffm_mat* m, uint64_t N, int32_t reduce)
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (N == 0) GFFM_FAIL(GFFM_ERR_INVALID, "modulus must be positive");
   if (N > (1ull << 52)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "Modulus is bigger than 2^52");
-  if (N > (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "moduli above 2^32 need wide storage");
+  if (m->wide) {  // stays in uint64 storage whatever the new modulus is
+    m->N = N;
+    gffm_touch(m);
+    return reduce ? gffm_wide_ewise(GFFM_EW_MOD, m, m, nullptr, 0, N) : GFFM_OK;
+  }
+  if (N > (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "a matrix created with N <= 2^32 keeps uint32 storage: create the matrix with the larger modulus instead");
   m->N = N;
   gffm_touch(m);
   if (reduce && N < (1ull << 32)) return gffm_ew_views(m->ctx, GFFM_EW_MOD, view_of(m), view_of(m), nullptr, 0, N);
@@ -714,6 +731,7 @@ extern "C" int32_t gffm_mat_get_elem(gffm_mat* m, int64_t i, int64_t j, int64_t*
   GFFM_ENTER_MAT(m);
   if (!m || !value) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (i < 0 || j < 0 || i >= m->rows || j >= m->cols) GFFM_FAIL(GFFM_ERR_INVALID, "BoundsError");
+  if (m->wide) return gffm_wide_get(m, i, j, value);
   uint32_t v = 0;
   GFFM_CUDA(cudaMemcpyAsync(&v, m->data + j * m->ld + i, 4, cudaMemcpyDeviceToHost, m->ctx->stream));
   GFFM_CUDA(cudaStreamSynchronize(m->ctx->stream));
@@ -725,12 +743,14 @@ extern "C" int32_t gffm_mat_set_elem(gffm_mat* m, int64_t i, int64_t j, int64_t 
   if (!m) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (i < 0 || j < 0 || i >= m->rows || j >= m->cols) GFFM_FAIL(GFFM_ERR_INVALID, "BoundsError");
   gffm_touch(m);
+  if (m->wide) return gffm_wide_fill(m, value, 0, i, j, 1, 1);
   return gffm_fill_view(m->ctx, sub_view(view_of(m), i, j, 1, 1), scalar_residue(value, m->N));
 }
 extern "C" int32_t gffm_mat_transpose(gffm_mat* dst, gffm_mat* src) {
   GFFM_ENTER_MAT(dst);
   if (!dst || !src) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   if (dst->rows != src->cols || dst->cols != src->rows) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "transpose: sizes differ");
+  GFFM_NARROW_ONLY(dst, src);
   if (src->rows * src->cols == 0) return GFFM_OK;
   gffm_touch(dst);
   dim3 grid((unsigned)ceil_div(src->rows, 32), (unsigned)ceil_div(src->cols, 32));
@@ -762,6 +782,14 @@ __global__ void checksum_kernel(const uint32_t* __restrict__ a, int64_t lda, con
 }
 static int32_t checksum_impl(gffm_mat* a, gffm_mat* b, unsigned long long out[2]) {
   gffm_ctx* ctx = a->ctx;
+  if (a->wide || (b && b->wide)) {
+    if (!a->wide || (b && !b->wide)) {  // different storage kinds never compare equal
+      out[0] = 0;
+      out[1] = 1;
+      return GFFM_OK;
+    }
+    return gffm_wide_checksum(a, b, out);
+  }
   GFFM_TRY(gffm_ws_reserve(ctx, &ctx->ws_misc2, 64));
   unsigned long long* d = (unsigned long long*)ctx->ws_misc2.ptr;
   GFFM_CUDA(cudaMemsetAsync(d, 0, 16, ctx->stream));
@@ -904,6 +932,7 @@ extern "C" int32_t gffm_gemm_block(gffm_mat* C, int64_t cr0, int64_t cc0, gffm_m
                                    int32_t algo) {
   GFFM_ENTER_MAT(C);
   if (!C || !A || !B) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(C, A, B);
   if (cr0 < 0 || cc0 < 0 || ar0 < 0 || ac0 < 0 || br0 < 0 || bc0 < 0 || m < 0 || n < 0 || k < 0 || cr0 + m > C->rows ||
       cc0 + n > C->cols || ar0 + m > A->rows || ac0 + k > A->cols || br0 + k > B->rows || bc0 + n > B->cols)
     GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "gemm_block: block out of range");
@@ -922,6 +951,7 @@ extern "C" int32_t gffm_gemm_block(gffm_mat* C, int64_t cr0, int64_t cc0, gffm_m
 extern "C" int32_t gffm_gemm(gffm_mat* C, gffm_mat* A, gffm_mat* B, uint64_t R, uint64_t P, int32_t mode, int32_t algo) {
   GFFM_ENTER_MAT(C);
   if (!C || !A || !B) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(C, A, B);
   // reference check order: modulus first, then sizes (CuModMatrix.jl:769-783)
   if (!P && (A->N != B->N || A->N != C->N)) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "gemm operands have different moduli");
   if (A->cols != B->rows || C->rows != A->rows || C->cols != B->cols)

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <initializer_list>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -114,10 +115,34 @@ struct gffm_mat {
   int32_t pad = GFFM_REF_PAD;
   uint64_t N = 0;
   bool owned = true;
+  // moduli 2^32 < N <= 2^52 (CuModMatrix.jl:55-59): uint64 residues in data64, `data` stays null.  Container + elementwise API only
+  // (wide.cu); every other entry point rejects such matrices (GFFM_NARROW_ONLY).
+  bool wide = false;
+  void* data64 = nullptr;
   uint64_t version = 1;         // bumped by every API call that writes the matrix
   gffm_plane_cache cache[2];    // [0] = as A operand (transposed planes), [1] = as B operand
 };
 static inline void gffm_touch(gffm_mat* m) { m->version++; }
+
+static inline bool gffm_any_wide(std::initializer_list<const gffm_mat*> ms) {
+  for (const gffm_mat* m : ms)
+    if (m && m->wide) return true;
+  return false;
+}
+#define GFFM_NARROW_ONLY(...)                                                                                                     \
+  do {                                                                                                                            \
+    if (gffm_any_wide({__VA_ARGS__}))                                                                                             \
+      GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "matrices with a modulus above 2^32 (uint64 storage) support the container and the elementwise API only; " \
+                                      "products above 2^32 go through KaratsubaMatrix");                                            \
+  } while (0)
+int32_t gffm_wide_upload(gffm_mat* m, const void* host, int32_t dtype, int64_t ld, int32_t do_mod);
+int32_t gffm_wide_download(gffm_mat* m, void* host, int32_t dtype, int64_t ld, int32_t with_padding);
+int32_t gffm_wide_ewise(int op, gffm_mat* C, gffm_mat* A, gffm_mat* B, int64_t scalar, uint64_t P);
+int32_t gffm_wide_fill(gffm_mat* m, int64_t value, int eye, int64_t r0, int64_t c0, int64_t nr, int64_t nc);
+int32_t gffm_wide_synth(gffm_mat* m, uint64_t seed);
+int32_t gffm_wide_copy(gffm_mat* dst, gffm_mat* src);
+int32_t gffm_wide_get(gffm_mat* m, int64_t i, int64_t j, int64_t* value);
+int32_t gffm_wide_checksum(gffm_mat* a, gffm_mat* b, unsigned long long out[2]);
 
 static inline cudaEvent_t gffm_trace_begin(gffm_ctx* ctx, cudaStream_t st) {
   if (!ctx->trace) return nullptr;

@@ -2074,6 +2074,7 @@ extern "C" int32_t gffm_gemm_panels(gffm_mat* C, gffm_mat* A, gffm_mat* B, int32
                                     void* const* consumed, uint64_t R, uint64_t P) {
   GFFM_ENTER_MAT(C);
   if (!C || !A || !B || !col_off) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(C, A, B);
   if (C == A || C == B) GFFM_FAIL(GFFM_ERR_INVALID, "gemm_panels: C must not alias an operand");
   if (!P && (A->N != B->N || A->N != C->N)) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "gemm operands have different moduli");
   if (A->cols != B->rows || C->rows != A->rows || C->cols != B->cols)

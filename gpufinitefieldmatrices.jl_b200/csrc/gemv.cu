@@ -255,6 +255,7 @@ int32_t gffm_gemv_raw(gffm_ctx* ctx, uint32_t* z, const uint32_t* A, int64_t lda
 extern "C" int32_t gffm_gemv(gffm_mat* z, gffm_mat* A, gffm_mat* x, uint64_t R, uint64_t P) {
   GFFM_ENTER_MAT(z);
   if (!z || !A || !x) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(z, A, x);
   if (x->cols != 1 || z->cols != 1 || A->cols != x->rows || A->rows != z->rows)
     GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "gemv: A is %lldx%lld, x has %lld rows, z has %lld rows", (long long)A->rows, (long long)A->cols,
               (long long)x->rows, (long long)z->rows);

@@ -114,6 +114,7 @@ extern "C" int32_t gffm_kmat_mul(gffm_mat* C1, gffm_mat* C2, gffm_mat* A1, gffm_
                                  uint64_t N2) {
   GFFM_ENTER_MAT(C1);
   if (!C1 || !C2 || !A1 || !A2 || !B1 || !B2) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(C1, C2, A1, A2, B1, B2);
   if (N1 == 0 || N2 == 0 || N1 % N2 != 0) GFFM_FAIL(GFFM_ERR_INVALID, "Karatsuba product requires N2 | N1");
   if (N1 > (1ull << 26) || N1 * N2 > (1ull << 52)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "N1 <= 2^26 and N1*N2 <= 2^52 required");
   const int64_t m = A1->rows, k = A1->cols, n = B1->cols;
@@ -171,6 +172,7 @@ extern "C" int32_t gffm_kmat_ewise(int32_t op, gffm_mat* C1, gffm_mat* C2, gffm_
                                    int64_t scalar, uint64_t N1, uint64_t N2) {
   GFFM_ENTER_MAT(C1);
   if (!C1 || !C2 || !A1 || !A2) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(C1, C2, A1, A2, B1, B2);
   if (op != GFFM_EW_ADD && op != GFFM_EW_SUB && op != GFFM_EW_SMUL && op != GFFM_EW_RSSUB) GFFM_FAIL(GFFM_ERR_INVALID, "bad Karatsuba op");
   if ((op == GFFM_EW_ADD || op == GFFM_EW_SUB) && (!B1 || !B2)) GFFM_FAIL(GFFM_ERR_INVALID, "binary op needs B");
   if (N1 == 0 || N2 == 0 || N1 * N2 > (1ull << 52) || N1 > (1ull << 32) || N2 > (1ull << 32)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "bad Karatsuba moduli");
@@ -333,6 +335,7 @@ int32_t gffm_pluq_quirk(gffm_mat* A, gffm_mat** U, gffm_mat** L, int64_t* prow_p
                         int64_t* n_pcol, int64_t* rank) {
   gffm_ctx* ctx = A->ctx;
   const int m = (int)A->rows, n = (int)A->cols;
+  GFFM_NARROW_ONLY(A);
   if (A->N >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "N < 2^32 required");
   gffm_mat *W = nullptr, *Lm = nullptr;
   GFFM_TRY(gffm_mat_create(ctx, m, n, A->N, A->pad, &W));

@@ -913,6 +913,7 @@ extern "C" int32_t gffm_mg_gemm(gffm_mg* mg, gffm_mat* C, gffm_mat* A, gffm_mat*
   GFFM_TRY(mg_check_common(mg, root));
   GFFM_ENTER_CTX(mg->ctx);
   if (!C || !A || !B) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(C, A, B);
   if (C == A || C == B) GFFM_FAIL(GFFM_ERR_INVALID, "mg_gemm: C must not alias an operand");
   if (C->ctx != mg->ctx || A->ctx != mg->ctx || B->ctx != mg->ctx) GFFM_FAIL(GFFM_ERR_INVALID, "mg_gemm: matrices belong to another context");
   if (!P && (A->N != B->N || A->N != C->N)) GFFM_FAIL(GFFM_ERR_MODULUS_MISMATCH, "gemm operands have different moduli");
@@ -977,6 +978,7 @@ extern "C" int32_t gffm_mg_kmat_mul(gffm_mg* mg, gffm_mat* C1, gffm_mat* C2, gff
   GFFM_TRY(mg_check_common(mg, root));
   GFFM_ENTER_CTX(mg->ctx);
   if (!C1 || !C2 || !A1 || !A2 || !B1 || !B2) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(C1, C2, A1, A2, B1, B2);
   if (N1 == 0 || N2 == 0 || N1 % N2 != 0) GFFM_FAIL(GFFM_ERR_INVALID, "Karatsuba product requires N2 | N1");
   if (N1 > (1ull << 26) || N1 * N2 > (1ull << 52)) GFFM_FAIL(GFFM_ERR_MODULUS_TOO_LARGE, "N1 <= 2^26 and N1*N2 <= 2^52 required");
   const int64_t m = A1->rows, k = A1->cols, n = B1->cols;
@@ -1060,6 +1062,7 @@ extern "C" int32_t gffm_mg_gemv(gffm_mg* mg, gffm_mat* z, gffm_mat* A, gffm_mat*
   GFFM_TRY(mg_check_common(mg, root));
   GFFM_ENTER_CTX(mg->ctx);
   if (!z || !A || !x) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(z, A, x);
   if (x->cols != 1 || z->cols != 1 || A->cols != x->rows || A->rows != z->rows) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "mg_gemv: inconsistent sizes");
   NcclApi* nc = nccl_api();
   if (mg->nranks > 1 && x->rows > 0) {

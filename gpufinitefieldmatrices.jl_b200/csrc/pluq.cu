@@ -1539,7 +1539,13 @@ int32_t triinv_views(gffm_ctx* ctx, MatView T, MatView X, bool upper, bool unit_
 // split in two, and after the left half the right half receives U12 = L11^-1 * A12 and the Schur update
 // A22 -= L21 * U12 through the tensor-core GEMM with K = number of pivots found in the left half (up to n/2), so the
 // modular GEMM runs at large K where it is tensor-bound instead of epilogue/HBM-bound.
-constexpr int NB0 = 256;
+// width of a base block (columns factorised by cluster panels + in-block updates before the tensor-core Schur update takes over);
+// GFFM_ELIM_NB0 overrides it for experiments (multiple of 64)
+static const int NB0 = [] {
+  const char* e = getenv("GFFM_ELIM_NB0");
+  const int v = e ? atoi(e) : 256;
+  return (v >= 64 && v <= 1024 && v % 64 == 0) ? v : 256;
+}();
 
 struct ElimState {
   gffm_ctx* ctx;
@@ -1709,6 +1715,7 @@ int32_t eliminate(gffm_mat* A, Elim* out) {
   gffm_ctx* ctx = A->ctx;
   const int m = (int)A->rows, n = (int)A->cols;
   const uint64_t N = A->N;
+  GFFM_NARROW_ONLY(A);
   if (N >= (1ull << 32)) GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "elimination needs N < 2^32");
   gffm_mat *W = nullptr, *L = nullptr;
   static const bool host_prof = getenv("GFFM_HOST_PROF") != nullptr;
@@ -2056,6 +2063,7 @@ extern "C" int32_t gffm_rref(gffm_mat* A, gffm_mat** R, int64_t* pivcols, int64_
 extern "C" int32_t gffm_triinv(gffm_mat* A, int32_t upper, gffm_mat** out) {
   GFFM_ENTER_MAT(A);
   if (!A || !out) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(A);
   gffm_ctx* ctx = A->ctx;
   const int64_t rows = A->rows, cols = A->cols;
   if (!upper && rows > cols) GFFM_FAIL(GFFM_ERR_INVERSE_NOT_DEFINED, "lower triangular inverse of a tall matrix is not defined");
@@ -2088,6 +2096,7 @@ extern "C" int32_t gffm_triinv(gffm_mat* A, int32_t upper, gffm_mat** out) {
 extern "C" int32_t gffm_apply_perm(gffm_mat* A, const int64_t* pairs, int64_t n_pairs, int32_t on_cols, int32_t inverse) {
   GFFM_ENTER_MAT(A);
   if (!A || (n_pairs > 0 && !pairs)) GFFM_FAIL(GFFM_ERR_INVALID, "null");
+  GFFM_NARROW_ONLY(A);
   if (n_pairs <= 0) return GFFM_OK;
   gffm_touch(A);
   gffm_ctx* ctx = A->ctx;

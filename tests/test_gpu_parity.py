@@ -845,3 +845,45 @@ def test_elimination_reports_zero_divisor_pivot(g):
     B = np.array([[9, 0], [3, 7]])  # pivots 9 and 7: both units mod 10 -> a valid factorisation over Z/10
     U, L, pr, pc = g.pluq_gpu_kernel(g.CuModMatrix(B, 10))
     assert np.array_equal((L.to_int() @ U.to_int()) % 10, O.apply_col_perm(pc, O.apply_row_perm(pr, B)))
+
+
+def test_wide_moduli_container_and_elementwise(g):
+    """Moduli 2^32 < N <= 2^52 (the reference container accepts N <= 2^52, CuModMatrix.jl:55-59): uint64 storage behind the same
+    constructor / Array / zeros / eye / fill! / copy! / getindex / setindex! / change_modulus and the elementwise API with its mod_N
+    override; exact against python integers (products need 104 bits).  Products / eliminations above 2^32 are refused (they go
+    through KaratsubaMatrix, as in the reference)."""
+    N = 2 ** 52 - 47
+    rng = np.random.default_rng(5)
+    Ah = rng.integers(-(2 ** 62), 2 ** 62, size=(70, 45), dtype=np.int64); Bh = rng.integers(0, N, size=(70, 45), dtype=np.int64)
+    Ah[0, 0] = N - 1; Bh[0, 0] = N - 1
+    A = g.CuModMatrix(Ah, N, elem_type=np.float64); B = g.CuModMatrix(Bh, N, elem_type=np.float64)
+    Ai = np.array([[int(v) % N for v in row] for row in Ah], dtype=object); Bi = Bh.astype(object)
+    assert np.array_equal(A.to_int().astype(object), Ai)
+    assert A.unsafe_Array(np.int64).shape == (70 + 32, 45 + 32) and not A.unsafe_Array(np.int64)[70:, :].any()
+    assert np.array_equal(A.Array(np.float64), Ai.astype(np.float64))
+    assert np.array_equal((A + B).to_int().astype(object), (Ai + Bi) % N)
+    assert np.array_equal((A - B).to_int().astype(object), (Ai - Bi) % N)
+    C = g.zeros(np.float64, 70, 45, N); g.elementwise_multiply_(C, A, B)
+    assert np.array_equal(C.to_int().astype(object), (Ai * Bi) % N)
+    s = 2 ** 51 + 12345
+    assert np.array_equal((A * s).to_int().astype(object), (Ai * s) % N)
+    assert np.array_equal((s - A).to_int().astype(object), (s - Ai) % N)
+    assert np.array_equal((A / 3).to_int().astype(object), (Ai * pow(3, -1, N)) % N)
+    g.add_(C, A, B, mod_N=2 ** 40 + 15)
+    assert np.array_equal(C.to_int().astype(object), (Ai % (2 ** 40 + 15) + Bi % (2 ** 40 + 15)) % (2 ** 40 + 15))
+    E = g.eye(np.float64, 5, N); assert np.array_equal(E.to_int(), np.eye(5, dtype=np.int64))
+    g.fill_(C, -1); assert C[3, 4] == N - 1
+    C[1, 2] = N + 5; assert C[1, 2] == 5
+    D = g.copy(A); assert D.equals(A) and not D.equals(B)
+    g.change_modulus_no_alloc_(D, 2 ** 45 + 59)
+    assert np.array_equal(D.to_int().astype(object), Ai % (2 ** 45 + 59))
+    R = g.rand(np.float64, 40, 40, N, seed=3); Rh = R.to_int()
+    assert Rh.min() >= 0 and Rh.max() < N and Rh.max() > 2 ** 40 and not R.unsafe_Array(np.int64)[40:, :].any()
+    with pytest.raises(g.InexactError):
+        A.Array(np.float32)
+    with pytest.raises(g.GffmError):
+        A * B.__class__(Bh.T.copy(), N, elem_type=np.float64)  # matrix product above 2^32: KaratsubaMatrix territory
+    with pytest.raises(g.GffmError):
+        g.pluq_gpu_kernel(g.CuModMatrix(Ah[:20, :20], N, elem_type=np.float64))
+    with pytest.raises(g.CuModArrayModulusMismatchException):
+        g.CuModMatrix(Ah, 2 ** 52 + 1)
