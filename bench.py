@@ -94,12 +94,12 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-CPU_SAMPLE_N = 4096  # fixed CPU sample (the same sub-product on every host, so ratios are comparable across runs and GPU counts)
+CPU_SAMPLE_N = 8192  # fixed CPU sample (the same sub-product on every host, so ratios are comparable across runs and GPU counts)
 
 
 def cpu_arm(n_full, N, ns=CPU_SAMPLE_N, threads=None):
     """Times the C oracle (oracle/oracle_c.c, pthreads over all host cores) on a FIXED bounded sample of the workload: the leading
-    ns x ns x ns sub-product of the same synthetic matrices (ns = 4096: ~2-5 s on 16-32 cores).  Returns (GOPS, cores, description,
+    ns x ns x ns sub-product of the same synthetic matrices (ns = 8192: ~5-15 s on 16-32 cores with the blocked kernel).  Returns (GOPS, cores, description,
     seconds).  Any time for the full n is an n^3 extrapolation and labelled as such by the callers."""
     import numpy as np
     from oracle import oracle as O
@@ -177,7 +177,7 @@ def run_reference(args):
         "config": {"workload": f"{args.n}x{args.n} * {args.n}x{args.n} matmul mod {args.modulus} ({(args.modulus - 1).bit_length()}-bit modulus), A,B resident as uint32 residues",
                    "n": args.n, "modulus": args.modulus,
                    "note": "the Julia reference cannot run in this image; this arm is the reference tests' CPU ground truth mod.(A*B,N) restated in C "
-                           "(oracle/oracle_c.c) on all host cores; every step is the FIXED 4096^3 sub-product (same on every host); "
+                           "(oracle/oracle_c.c) on all host cores; every step is the FIXED 8192^3 sub-product (same on every host); "
                            "ms_per_step is EXTRAPOLATED by n^3 to the full workload", "cpu_sample_n": min(CPU_SAMPLE_N, args.n), "ms_per_step_is_extrapolated": True},
         "cpu_baseline": {"value": value, "unit": "GOPS", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "GOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

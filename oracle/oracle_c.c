@@ -32,53 +32,99 @@ void oracle_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 typedef struct {
   const uint32_t *A, *B;
   uint32_t* C;
+  uint32_t* Ap; /* A repacked: [row block of 32][k][32 rows], contiguous, so the inner loop streams 128-byte lines */
   int64_t lda, ldb, ldc, m, k, n, chunk;
   uint64_t N;
   volatile int64_t* next;
+  volatile int64_t* next_pack;
 } mm_job;
 
-static void* mm_worker(void* arg) {
-  mm_job* J = (mm_job*)arg;
-  const int64_t IB = 64;
-  uint64_t acc[64];
+#define MM_IB 32
+#define MM_JB 64
+
+static void mm_pack(mm_job* J) {
+  const int64_t nib = (J->m + MM_IB - 1) / MM_IB;
   for (;;) {
-    const int64_t i0 = __sync_fetch_and_add(J->next, IB);
-    if (i0 >= J->m) break;
-    const int64_t ib = (J->m - i0) < IB ? (J->m - i0) : IB;
-    for (int64_t j = 0; j < J->n; ++j) {
-      for (int64_t i = 0; i < ib; ++i) acc[i] = 0;
-      for (int64_t k0 = 0; k0 < J->k; k0 += J->chunk) {
-        const int64_t k1 = (k0 + J->chunk < J->k) ? k0 + J->chunk : J->k;
-        for (int64_t kk = k0; kk < k1; ++kk) {
-          const uint64_t b = J->B[j * J->ldb + kk];
-          const uint32_t* a = J->A + kk * J->lda + i0;
-          for (int64_t i = 0; i < ib; ++i) acc[i] += (uint64_t)a[i] * b;
-        }
-        for (int64_t i = 0; i < ib; ++i) acc[i] %= J->N;
-      }
-      for (int64_t i = 0; i < ib; ++i) J->C[j * J->ldc + i0 + i] = (uint32_t)acc[i];
+    const int64_t t = __sync_fetch_and_add(J->next_pack, 1);
+    if (t >= nib) break;
+    const int64_t i0 = t * MM_IB, ib = (J->m - i0) < MM_IB ? (J->m - i0) : MM_IB;
+    uint32_t* dst = J->Ap + t * J->k * MM_IB;
+    for (int64_t kk = 0; kk < J->k; ++kk) {
+      const uint32_t* a = J->A + kk * J->lda + i0;
+      for (int64_t i = 0; i < ib; ++i) dst[kk * MM_IB + i] = a[i];
+      for (int64_t i = ib; i < MM_IB; ++i) dst[kk * MM_IB + i] = 0;
     }
   }
+}
+
+/* 32 running sums of one column of C over kk in [k0, k1): the loop over i vectorises (zero-extend, 32x32->64 multiply, 64-bit add) */
+static inline void mm_kernel(const uint32_t* restrict ap, const uint32_t* restrict bcol, int64_t k0, int64_t k1, uint64_t* restrict ac) {
+  uint64_t r[MM_IB];
+  for (int i = 0; i < MM_IB; ++i) r[i] = ac[i];
+  for (int64_t kk = k0; kk < k1; ++kk) {
+    const uint64_t b = bcol[kk];
+    const uint32_t* a = ap + kk * MM_IB;
+    for (int i = 0; i < MM_IB; ++i) r[i] += (uint64_t)a[i] * b;
+  }
+  for (int i = 0; i < MM_IB; ++i) ac[i] = r[i];
+}
+
+/* Cache-blocked exact product: a task = 32 rows x 64 columns of C.  The packed 32 x chunk block of A (128 KiB at chunk = 1024) is
+ * re-read from L2 for each of the 64 columns; `chunk` is also the number of terms a uint64 sum may take before a reduction. */
+static void* mm_worker(void* arg) {
+  mm_job* J = (mm_job*)arg;
+  uint64_t acc[MM_JB][MM_IB];
+  const int64_t nib = (J->m + MM_IB - 1) / MM_IB, njb = (J->n + MM_JB - 1) / MM_JB;
+  for (;;) {
+    const int64_t t = __sync_fetch_and_add(J->next, 1);
+    if (t >= nib * njb) break;
+    const int64_t bi = t % nib, i0 = bi * MM_IB, j0 = (t / nib) * MM_JB;
+    const int64_t ib = (J->m - i0) < MM_IB ? (J->m - i0) : MM_IB, jb = (J->n - j0) < MM_JB ? (J->n - j0) : MM_JB;
+    const uint32_t* ap = J->Ap + bi * J->k * MM_IB;
+    for (int64_t j = 0; j < jb; ++j)
+      for (int i = 0; i < MM_IB; ++i) acc[j][i] = 0;
+    for (int64_t k0 = 0; k0 < J->k; k0 += J->chunk) {
+      const int64_t k1 = (k0 + J->chunk < J->k) ? k0 + J->chunk : J->k;
+      for (int64_t j = 0; j < jb; ++j) {
+        mm_kernel(ap, J->B + (j0 + j) * J->ldb, k0, k1, acc[j]);
+        for (int i = 0; i < MM_IB; ++i) acc[j][i] %= J->N;
+      }
+    }
+    for (int64_t j = 0; j < jb; ++j)
+      for (int64_t i = 0; i < ib; ++i) J->C[(j0 + j) * J->ldc + i0 + i] = (uint32_t)acc[j][i];
+  }
+  return NULL;
+}
+
+static void* mm_pack_worker(void* arg) {
+  mm_pack((mm_job*)arg);
   return NULL;
 }
 
 /* C = A*B mod N; column-major, A m x k (lda), B k x n (ldb), C m x n (ldc); entries < 2^32, N < 2^32 */
 void oracle_matmul_mod(const uint32_t* A, int64_t lda, const uint32_t* B, int64_t ldb, uint32_t* C, int64_t ldc, int64_t m,
                        int64_t k, int64_t n, uint64_t N, uint64_t in_bound) {
-  /* terms are < in_bound^2; keep partial sums below 2^63 */
+  if (m <= 0 || n <= 0) return;
+  /* terms are < in_bound^2; a reduced sum (< N) plus `chunk` terms must stay below 2^64 */
   uint64_t R = in_bound ? in_bound : N;
   long double r2 = (long double)(R - 1) * (long double)(R - 1);
-  int64_t chunk = r2 < 1 ? k : (int64_t)(9.0e18L / r2);
+  int64_t chunk = r2 < 1 ? (k > 0 ? k : 1) : (int64_t)(9.0e18L / r2);
   if (chunk < 1) chunk = 1;
-  if (chunk > 4096) chunk = 4096;
-  volatile int64_t next = 0;
-  mm_job job = {A, B, C, lda, ldb, ldc, m, k, n, chunk, N, &next};
+  if (chunk > 1024) chunk = 1024; /* also the K blocking: 32 rows x 1024 terms x 4 B = 128 KiB of A per block */
+  const int64_t nib = (m + MM_IB - 1) / MM_IB;
+  uint32_t* Ap = (uint32_t*)malloc((size_t)(nib * (k > 0 ? k : 1) * MM_IB) * sizeof(uint32_t));
+  volatile int64_t next = 0, next_pack = 0;
+  mm_job job = {A, B, C, Ap, lda, ldb, ldc, m, k, n, chunk, N, &next, &next_pack};
   const int nt = oracle_num_threads();
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nt);
+  for (int t = 1; t < nt; ++t) pthread_create(&th[t], NULL, mm_pack_worker, &job);
+  mm_pack(&job);
+  for (int t = 1; t < nt; ++t) pthread_join(th[t], NULL);
   for (int t = 1; t < nt; ++t) pthread_create(&th[t], NULL, mm_worker, &job);
   mm_worker(&job);
   for (int t = 1; t < nt; ++t) pthread_join(th[t], NULL);
   free(th);
+  free(Ap);
 }
 
 static uint64_t mod_inv_u64(uint64_t p, uint64_t P) { /* pluq_kernels.jl:11-31 */
