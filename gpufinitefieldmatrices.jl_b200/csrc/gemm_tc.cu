@@ -1189,7 +1189,11 @@ int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2,
       PlaneDests d = *dests;
       for (int i = 0; i < d.n; ++i) d.p[i] += c0 * Kp;
       dim3 grid((unsigned)ceil_div(Kp / 16, 128), (unsigned)nc);
-#define GFFM_SPLIT_BP(MODE) split_b_push_kernel<MODE><<<grid, 128, 0, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)nc, Kp, rowsP, sp, d)
+      // The push runs UNDER the persistent GEMM of the previous product and only has to keep NVLink busy: an (unused) dynamic
+      // shared-memory request caps how many of its CTAs fit next to a GEMM CTA (which owns ~197 of the SM's 227 KiB), so it takes
+      // few issue slots from the MMA-issuing warp (GFFM_PUSH_SMEM bytes per CTA, default 12 KiB = two CTAs per SM beside the GEMM)
+      static const int push_smem = getenv("GFFM_PUSH_SMEM") ? atoi(getenv("GFFM_PUSH_SMEM")) : 12288;
+#define GFFM_SPLIT_BP(MODE) split_b_push_kernel<MODE><<<grid, 128, push_smem, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)nc, Kp, rowsP, sp, d)
       if (sp.mode == 0) GFFM_SPLIT_BP(0);
       else if (sp.mode == 1) GFFM_SPLIT_BP(1);
       else GFFM_SPLIT_BP(2);
