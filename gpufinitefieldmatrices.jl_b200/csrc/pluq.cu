@@ -1543,8 +1543,8 @@ int32_t triinv_views(gffm_ctx* ctx, MatView T, MatView X, bool upper, bool unit_
 // GFFM_ELIM_NB0 overrides it for experiments (multiple of 64)
 static const int NB0 = [] {
   const char* e = getenv("GFFM_ELIM_NB0");
-  const int v = e ? atoi(e) : 256;
-  return (v >= 64 && v <= 1024 && v % 64 == 0) ? v : 256;
+  const int v = e ? atoi(e) : 512;  // measured at n = 16384 (profiles/r02_notes.md): 128 -> 127 ms, 256 -> 112 ms, 512 -> 109 ms (mod 65521)
+  return (v >= 64 && v <= 1024 && v % 64 == 0) ? v : 512;
 }();
 
 struct ElimState {
