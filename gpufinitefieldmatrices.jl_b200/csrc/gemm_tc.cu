@@ -857,38 +857,42 @@ template <int MODE>
 __global__ void __launch_bounds__(128)
 split_b_push_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2, int K, int ncols, int64_t Kp,
                     int64_t rowsP, const __grid_constant__ SplitParams sp, const __grid_constant__ PlaneDests dests) {
-  const int64_t k16 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-  const int j = blockIdx.y;
-  if (k16 >= Kp || j >= ncols) return;
-  uint32_t x[16];
-  const uint32_t* col = src + (int64_t)j * ld + k16;
-  if (k16 + 15 < K && ((reinterpret_cast<uintptr_t>(col) & 15) == 0)) {
+  // Bounded, grid-stride launch (a few CTAs per SM, no shared memory): the kernel runs UNDER the persistent tensor-core GEMM of the
+  // previous product and must neither keep GEMM CTAs from being scheduled nor flood the SMs' issue slots -- its speed is set by
+  // NVLink, not by the SMs.  Work item = 16 consecutive k of one column; consecutive threads take consecutive items.
+  const int64_t per_col = Kp / 16, items = per_col * ncols;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = w / per_col, k16 = (w - j * per_col) * 16;
+    uint32_t x[16];
+    const uint32_t* col = src + j * ld + k16;
+    if (k16 + 15 < K && ((reinterpret_cast<uintptr_t>(col) & 15) == 0)) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint4 v = reinterpret_cast<const uint4*>(col)[g];
-      x[4 * g] = v.x; x[4 * g + 1] = v.y; x[4 * g + 2] = v.z; x[4 * g + 3] = v.w;
+      for (int g = 0; g < 4; ++g) {
+        const uint4 v = reinterpret_cast<const uint4*>(col)[g];
+        x[4 * g] = v.x; x[4 * g + 1] = v.y; x[4 * g + 2] = v.z; x[4 * g + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) x[t] = (k16 + t < K) ? col[t] : 0u;
     }
-  } else {
+    if (src2) {
+      const uint32_t* col2 = src2 + j * ld2 + k16;
 #pragma unroll
-    for (int t = 0; t < 16; ++t) x[t] = (k16 + t < K) ? col[t] : 0u;
-  }
-  if (src2) {
-    const uint32_t* col2 = src2 + (int64_t)j * ld2 + k16;
-#pragma unroll
-    for (int t = 0; t < 16; ++t)
-      if (k16 + t < K) x[t] += col2[t];
-  }
-  Encoder<MODE, 16> enc;
-  enc.prepare(x, sp);
-  const int64_t off = (int64_t)j * Kp + k16;
-  const int64_t pstride = rowsP * Kp;
+      for (int t = 0; t < 16; ++t)
+        if (k16 + t < K) x[t] += col2[t];
+    }
+    Encoder<MODE, 16> enc;
+    enc.prepare(x, sp);
+    const int64_t off = j * Kp + k16;
+    const int64_t pstride = rowsP * Kp;
 #pragma unroll 1
-  for (int pl = 0; pl < sp.nplanes; ++pl) {
-    uint32_t w[4];
-    enc.plane(pl, sp, w);
-    const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int pl = 0; pl < sp.nplanes; ++pl) {
+      uint32_t wv[4];
+      enc.plane(pl, sp, wv);
+      const uint4 v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
 #pragma unroll 1
-    for (int d = 0; d < dests.n; ++d) *reinterpret_cast<uint4*>(dests.p[d] + off + pl * pstride) = v;
+      for (int d = 0; d < dests.n; ++d) *reinterpret_cast<uint4*>(dests.p[d] + off + pl * pstride) = v;
+    }
   }
 }
 
@@ -1181,25 +1185,18 @@ int32_t launch_gemm(gffm_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
 int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2, int64_t k_off, int64_t kc, uint8_t* planes,
                   int64_t Kp, int64_t rowsP, const SplitParams& sp, cudaStream_t st = nullptr, const PlaneDests* dests = nullptr) {
   if (!st) st = ctx->stream;
-  if (dests && !is_a) {  // fused split + push: `planes` is ignored, every destination gets the rows [row0, row0 + cols) the caller offset into dests
-    for (int64_t c0 = 0; c0 < X.cols; c0 += 65535) {
-      const int64_t nc = std::min<int64_t>(65535, X.cols - c0);
-      const uint32_t* s = X.p + k_off + c0 * X.ld;
-      const uint32_t* s2 = X2 ? X2->p + k_off + c0 * X2->ld : nullptr;
-      PlaneDests d = *dests;
-      for (int i = 0; i < d.n; ++i) d.p[i] += c0 * Kp;
-      dim3 grid((unsigned)ceil_div(Kp / 16, 128), (unsigned)nc);
-      // The push runs UNDER the persistent GEMM of the previous product and only has to keep NVLink busy: an (unused) dynamic
-      // shared-memory request caps how many of its CTAs fit next to a GEMM CTA (which owns ~197 of the SM's 227 KiB), so it takes
-      // few issue slots from the MMA-issuing warp (GFFM_PUSH_SMEM bytes per CTA, default 12 KiB = two CTAs per SM beside the GEMM)
-      static const int push_smem = getenv("GFFM_PUSH_SMEM") ? atoi(getenv("GFFM_PUSH_SMEM")) : 12288;
-#define GFFM_SPLIT_BP(MODE) split_b_push_kernel<MODE><<<grid, 128, push_smem, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)nc, Kp, rowsP, sp, d)
-      if (sp.mode == 0) GFFM_SPLIT_BP(0);
-      else if (sp.mode == 1) GFFM_SPLIT_BP(1);
-      else GFFM_SPLIT_BP(2);
+  if (dests && !is_a) {  // fused split + push: `planes` is ignored, every destination gets the rows the caller offset into dests
+    static const int ctas_per_sm = getenv("GFFM_PUSH_CTAS_PER_SM") ? std::max(1, atoi(getenv("GFFM_PUSH_CTAS_PER_SM"))) : 4;
+    const int64_t items = (Kp / 16) * X.cols;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, 128), (int64_t)ctx->num_sms * ctas_per_sm));
+    const uint32_t* s = X.p + k_off;
+    const uint32_t* s2 = X2 ? X2->p + k_off : nullptr;
+#define GFFM_SPLIT_BP(MODE) split_b_push_kernel<MODE><<<(unsigned)grid, 128, 0, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)X.cols, Kp, rowsP, sp, *dests)
+    if (sp.mode == 0) GFFM_SPLIT_BP(0);
+    else if (sp.mode == 1) GFFM_SPLIT_BP(1);
+    else GFFM_SPLIT_BP(2);
 #undef GFFM_SPLIT_BP
-      GFFM_LAUNCH_CHECK(ctx);
-    }
+    GFFM_LAUNCH_CHECK(ctx);
     return GFFM_OK;
   }
   if (is_a) {

@@ -105,6 +105,21 @@ def main():
             ok = ok and np.array_equal(outs[it].to_int(), OC.matmul_mod(O.synth_matrix(30 + it, m, k, N)[r0:r1], Bh, N))
         agree(ok, f"{tname}: 6 pipelined products (b_ready event, double-buffered planes)")
         del outs, As
+        # pipelined AND changing: B is rewritten on root before every product and declared ready by its own event; any stale operand
+        # plane (a race in the double-buffered distribution) shows up as a wrong product
+        ok = True
+        outs = [g.zeros(np.float32, r1 - r0, n, N) for _ in range(6)]
+        evs = [torch.cuda.Event() for _ in range(6)]
+        lib_stream = torch.cuda.ExternalStream(ctx.get_stream(), device=local)
+        for it in range(6):
+            if rank == 0:
+                g.copy_(B, g.CuModMatrix(O.synth_matrix(60 + it, k, n, N), N))
+            evs[it].record(lib_stream)
+            mgpu.gemm(outs[it], A, B, root=0, b_ready=evs[it].cuda_event)
+        for it in range(6):
+            ok = ok and np.array_equal(outs[it].to_int(), OC.matmul_mod(Ah[r0:r1], O.synth_matrix(60 + it, k, n, N), N))
+        agree(ok, f"{tname}: 6 pipelined products, B rewritten before each (per-product ready events)")
+        del outs
         # root != 0
         if world > 1:
             Bh = O.synth_matrix(40, k, n, N)
