@@ -27,8 +27,9 @@ int32_t gffm_bplan_split(gffm_ctx* ctx, const GemmBPlan* plan, MatView B, const 
                          cudaStream_t st);
 
 // Fused split + push: the same split, every 16-byte chunk stored to `nbufs` plane buffers (local and peer memory) of identical layout.
+// The kernel runs on `push_sms` dedicated SMs (one 1024-thread CTA each that no GEMM CTA can share an SM with).
 int32_t gffm_bplan_split_push(gffm_ctx* ctx, const GemmBPlan* plan, MatView B, const MatView* B2, uint8_t* const* plane_bufs, int nbufs, int64_t rowsPB,
-                              int64_t row0, cudaStream_t st);
+                              int64_t row0, cudaStream_t st, int push_sms);
 
 struct ExtBPlanes {
   const uint8_t* planes = nullptr;  // [nplanes][rowsPB][Kp]

@@ -851,15 +851,18 @@ struct Encoder {
 struct PlaneDests {
   uint8_t* p[32];
   int n;
+  int sms;  // host side: SMs (= CTAs) the push may occupy
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(1024)
 split_b_push_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src2, int64_t ld, int64_t ld2, int K, int ncols, int64_t Kp,
                     int64_t rowsP, const __grid_constant__ SplitParams sp, const __grid_constant__ PlaneDests dests) {
-  // Bounded, grid-stride launch (a few CTAs per SM, no shared memory): the kernel runs UNDER the persistent tensor-core GEMM of the
-  // previous product and must neither keep GEMM CTAs from being scheduled nor flood the SMs' issue slots -- its speed is set by
-  // NVLink, not by the SMs.  Work item = 16 consecutive k of one column; consecutive threads take consecutive items.
+  // Grid-stride over a FEW DEDICATED SMs (one 1024-thread CTA each, with a dynamic shared-memory request large enough that no
+  // tensor-core GEMM CTA fits beside it).  Measured on 8 B200 (profiles/r02_notes.md): when push CTAs share SMs with the persistent
+  // GEMM, the slow peer stores clog those SMs' path to the crossbar and the GEMM's TMA loads queue behind them (a 0.4 ms GEMM
+  // launch took 2.5 ms); on its own SMs the push is bound by NVLink, and the GEMM runs undisturbed on the remaining SMs
+  // (gffm_ctx::gemm_ctas).  Work item = 16 consecutive k of one column; consecutive threads take consecutive items.
   const int64_t per_col = Kp / 16, items = per_col * ncols;
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = w / per_col, k16 = (w - j * per_col) * 16;
@@ -1186,12 +1189,19 @@ int32_t run_split(gffm_ctx* ctx, bool is_a, const MatView& X, const MatView* X2,
                   int64_t Kp, int64_t rowsP, const SplitParams& sp, cudaStream_t st = nullptr, const PlaneDests* dests = nullptr) {
   if (!st) st = ctx->stream;
   if (dests && !is_a) {  // fused split + push: `planes` is ignored, every destination gets the rows the caller offset into dests
-    static const int ctas_per_sm = getenv("GFFM_PUSH_CTAS_PER_SM") ? std::max(1, atoi(getenv("GFFM_PUSH_CTAS_PER_SM"))) : 4;
     const int64_t items = (Kp / 16) * X.cols;
-    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, 128), (int64_t)ctx->num_sms * ctas_per_sm));
+    const int push_sms = dests->sms > 0 ? dests->sms : 20;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, 1024), push_sms));
+    constexpr int kPushSmem = 100 * 1024;  // + the GEMM CTA's ~197 KiB > 227 KiB: never co-resident with a GEMM CTA
+    static PerDeviceOnce attr_push;
+    attr_push.run(ctx->device, [] {
+      cudaFuncSetAttribute(split_b_push_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushSmem);
+      cudaFuncSetAttribute(split_b_push_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushSmem);
+      cudaFuncSetAttribute(split_b_push_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushSmem);
+    });
     const uint32_t* s = X.p + k_off;
     const uint32_t* s2 = X2 ? X2->p + k_off : nullptr;
-#define GFFM_SPLIT_BP(MODE) split_b_push_kernel<MODE><<<(unsigned)grid, 128, 0, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)X.cols, Kp, rowsP, sp, *dests)
+#define GFFM_SPLIT_BP(MODE) split_b_push_kernel<MODE><<<(unsigned)grid, 1024, kPushSmem, st>>>(s, s2, X.ld, X2 ? X2->ld : 0, (int)kc, (int)X.cols, Kp, rowsP, sp, *dests)
     if (sp.mode == 0) GFFM_SPLIT_BP(0);
     else if (sp.mode == 1) GFFM_SPLIT_BP(1);
     else GFFM_SPLIT_BP(2);
@@ -2189,13 +2199,14 @@ int32_t gffm_bplan_split(gffm_ctx* ctx, const GemmBPlan* g, MatView B, const Mat
 }
 
 int32_t gffm_bplan_split_push(gffm_ctx* ctx, const GemmBPlan* g, MatView B, const MatView* B2, uint8_t* const* plane_bufs, int nbufs, int64_t rowsPB,
-                              int64_t row0, cudaStream_t st) {
+                              int64_t row0, cudaStream_t st, int push_sms) {
   if (B.rows != g->kc) GFFM_FAIL(GFFM_ERR_SIZE_MISMATCH, "plane split: %lld rows, plan has %lld", (long long)B.rows, (long long)g->kc);
   if (B.cols == 0 || nbufs <= 0) return GFFM_OK;
   if (nbufs > 32) GFFM_FAIL(GFFM_ERR_INVALID, "at most 32 destinations");
   if (row0 < 0 || row0 + B.cols > rowsPB) GFFM_FAIL(GFFM_ERR_INVALID, "plane split: rows outside the buffer");
   PlaneDests d;
   d.n = nbufs;
+  d.sms = push_sms;
   for (int i = 0; i < nbufs; ++i) d.p[i] = plane_bufs[i] + row0 * g->Kp;
   return run_split(ctx, false, B, B2, 0, g->kc, nullptr, g->Kp, rowsPB, g->sp, st, &d);
 }

@@ -191,6 +191,10 @@ struct gffm_mg {
   cudaStream_t s_comm = nullptr, s_dist = nullptr, s_pull[NCOPY] = {}, s_push[NCOPY] = {};
   cudaEvent_t copy_ev[2][NCOPY] = {};  // joins of the copy streams (0: pulls, 1: pushes)
   int ncopy = NCOPY;
+  int push_sms = 20;      // GFFM_MG_P2P_PUSH: SMs dedicated to the fused split + push kernel (GFFM_MG_PUSH_SMS)
+  int push_ce_peers = 0;  // ... and how many of the peers get their copy from the copy engines instead (GFFM_MG_PUSH_CE_PEERS)
+  int saved_gemm_ctas = -1;
+  cudaEvent_t split_ev[2] = {}, ce_done[2] = {};
   bool wait_memops = false, signal_memops = false;  // flags through stream memory operations instead of one-warp kernels
   // arena: [control words | staging 0 | staging 1 | planes 0 | planes 1], one cudaMalloc, exported through CUDA IPC
   char* base = nullptr;
@@ -371,6 +375,14 @@ int32_t mg_ensure_arena(gffm_mg* mg, size_t stage_bytes, size_t planes_bytes) {
     GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "a peer-memory transport was requested but peer memory (CUDA IPC / peer access) is not available between all ranks");
   mg->transport = mg->requested != GFFM_MG_AUTO ? mg->requested : (mg->p2p_ok ? GFFM_MG_P2P_PUSH : GFFM_MG_NCCL_PLANES);
   mg->epoch = 0;
+  // the fused split + push kernel owns `push_sms` SMs; the persistent GEMM gets the others (unless the caller set its own cap)
+  if (mg->transport == GFFM_MG_P2P_PUSH && mg->nranks > 1) {
+    if (mg->saved_gemm_ctas < 0) mg->saved_gemm_ctas = mg->ctx->gemm_ctas;
+    if (mg->saved_gemm_ctas == 0) mg->ctx->gemm_ctas = mg->ctx->num_sms - mg->push_sms;
+  } else if (mg->saved_gemm_ctas >= 0) {
+    mg->ctx->gemm_ctas = mg->saved_gemm_ctas;
+    mg->saved_gemm_ctas = -1;
+  }
   return GFFM_OK;
 }
 
@@ -496,10 +508,13 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       v = view_of_src(S.src);
       if (S.src2 >= 0) v2 = view_of_src(S.src2);
       if (push_planes) {
+        // destinations of the kernel: the local buffer, then the peers r+1, r+2, ... except the last `ce` of them (served by copy engines)
         uint8_t* bufs[MG_MAX_RANKS];
-        for (int d = 0; d < nr; ++d) bufs[d] = (uint8_t*)((d == r ? mg->base : mg->peer_base[d]) + mg->planes_off(b) + S.off);
-        std::swap(bufs[0], bufs[r]);  // local destination first
-        GFFM_TRY(gffm_bplan_split_push(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, bufs, nr, rowsPB, (int64_t)q * per, mg->s_dist));
+        int nb = 0;
+        bufs[nb++] = (uint8_t*)(mg->base + mg->planes_off(b) + S.off);
+        const int ce = (r == R.root) ? 0 : std::min(mg->push_ce_peers, nr - 1);  // the root's copy engines already carry the uint32 ranges
+        for (int i = 1; i < nr - ce; ++i) bufs[nb++] = (uint8_t*)(mg->peer_base[(r + i) % nr] + mg->planes_off(b) + S.off);
+        GFFM_TRY(gffm_bplan_split_push(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, bufs, nb, rowsPB, (int64_t)q * per, mg->s_dist, mg->push_sms));
       } else {
         GFFM_TRY(gffm_bplan_split(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, out->planes + S.off, rowsPB, (int64_t)q * per, mg->s_dist));
       }
@@ -549,13 +564,43 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
     const uint32_t others = (nr >= 32 ? 0xffffffffu : ((1u << nr) - 1u)) & ~(1u << r);
     if (push_planes) GFFM_TRY(mg_wait(mg, mg->s_dist, F_FREE, others, e - 2));  // every peer's GEMMs of epoch e-2 are done with ITS copy of this buffer
     else GFFM_TRY(mg_wait(mg, mg->s_dist, F_PULLED, others, e - 2));           // ... and so are the peers' pulls from this buffer
+    if (push_planes) GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->ce_done[b], 0));  // copy engines of epoch e-2 no longer read this buffer
     GFFM_TRY(split_own(r, r != root && !distributed, ld_c));
     GFFM_CUDA(cudaEventRecord(mg->ready_ev[b][r], mg->s_dist));
+    const int ce_peers = (push_planes && r != root) ? std::min(mg->push_ce_peers, nr - 1) : 0;
+    if (ce_peers > 0) {
+      // the last `ce_peers` peers get the planes from the copy engines (local plane buffer -> peer plane buffer), each followed by
+      // that peer's flag, spread over the copy streams
+      GFFM_CUDA(cudaEventRecord(mg->split_ev[b], mg->s_dist));
+      const int64_t cnt = out->off[r + 1] - out->off[r];
+      for (int i = nr - ce_peers; i < nr; ++i) {
+        const int q = (r + i) % nr;
+        cudaStream_t cs = mg->s_push[1 + (i % (gffm_mg::NCOPY - 1))];
+        GFFM_CUDA(cudaStreamWaitEvent(cs, mg->split_ev[b], 0));
+        cudaEvent_t tp = gffm_trace_begin(ctx, cs);
+        for (int s2 = 0; s2 < R.nsets && cnt > 0; ++s2) {
+          const BPlaneSpec* sp = gffm_bplan_spec(R.sets[s2].plan);
+          const size_t pitch = (size_t)rowsPB * sp->Kp, rel = R.sets[s2].off + (size_t)r * per * sp->Kp;
+          for (int t = 0; t < sp->nplanes; ++t)
+            GFFM_CUDA(cudaMemcpyAsync(mg->peer_base[q] + mg->planes_off(b) + rel + t * pitch, mg->planes(b) + rel + t * pitch, (size_t)cnt * sp->Kp,
+                                      cudaMemcpyDefault, cs));
+        }
+        gffm_trace_end(ctx, "cepush", q, 4, tp, cs);
+        MgTargets t1;
+        t1.p[0] = mg->ctl(q) + F_READY + r;
+        GFFM_TRY(mg_signal(mg, cs, t1, 1, e));
+      }
+      // join: the next user of this plane buffer waits for all of them
+      for (int j = 1; j < gffm_mg::NCOPY; ++j) {
+        GFFM_CUDA(cudaEventRecord(mg->copy_ev[1][j], mg->s_push[j]));
+        GFFM_CUDA(cudaStreamWaitEvent(mg->s_pull[2], mg->copy_ev[1][j], 0));
+      }
+      GFFM_CUDA(cudaEventRecord(mg->ce_done[b], mg->s_pull[2]));
+    }
     {
       MgTargets t;
       int k = 0;
-      for (int q = 0; q < nr; ++q)
-        if (q != r) t.p[k++] = mg->ctl(q) + F_READY + r;
+      for (int i = 1; i < nr - ce_peers; ++i) t.p[k++] = mg->ctl((r + i) % nr) + F_READY + r;
       GFFM_TRY(mg_signal(mg, mg->s_dist, t, k, e));
       // "my staging buffer of this parity is free again": told to EVERY rank, because any of them may be the root of a later product
       k = 0;
@@ -808,6 +853,12 @@ extern "C" int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nran
     mg->wait_memops = want_memops && mem_ops() != nullptr;
     mg->signal_memops = false;  // decided per arena: the write must reach PEER memory (self-test in mg_ensure_arena)
   }
+  for (int b = 0; b < 2; ++b) {
+    GFFM_CUDA(mk(&mg->split_ev[b]));
+    GFFM_CUDA(mk(&mg->ce_done[b]));
+  }
+  if (const char* t = getenv("GFFM_MG_PUSH_SMS")) mg->push_sms = std::max(1, std::min(ctx->num_sms / 2, atoi(t)));
+  if (const char* t = getenv("GFFM_MG_PUSH_CE_PEERS")) mg->push_ce_peers = std::max(0, atoi(t));
   GFFM_CUDA(mk(&mg->ev_call));
   GFFM_CUDA(mk(&mg->ev_push));
   GFFM_CUDA(mk(&mg->ev_comm));
@@ -845,8 +896,9 @@ extern "C" int32_t gffm_mg_destroy(gffm_mg* mg) {
     if (mg->bc_ev[q]) cudaEventDestroy(mg->bc_ev[q]);
     if (mg->bc_consumed[q]) cudaEventDestroy(mg->bc_consumed[q]);
   }
-  for (cudaEvent_t e : {mg->ev_call, mg->ev_push, mg->ev_comm})
+  for (cudaEvent_t e : {mg->ev_call, mg->ev_push, mg->ev_comm, mg->split_ev[0], mg->split_ev[1], mg->ce_done[0], mg->ce_done[1]})
     if (e) cudaEventDestroy(e);
+  if (mg->saved_gemm_ctas >= 0) mg->ctx->gemm_ctas = mg->saved_gemm_ctas;
   for (cudaStream_t s : {mg->s_comm, mg->s_dist})
     if (s) cudaStreamDestroy(s);
   for (int j = 0; j < gffm_mg::NCOPY; ++j) {
