@@ -23,8 +23,8 @@
 //                       in-place ncclAllGather of the planes.
 //   GFFM_MG_NCCL_BCAST  ncclBroadcast of B's uint32 column ranges, every rank splits all of B (round-1 data flow).
 //
-// Plane buffers and staging are double-buffered by epoch parity, so the distribution of product e+1 runs entirely under the
-// GEMMs of product e when the caller says that B is ready (b_ready event).  NCCL is loaded with dlopen (libnccl.so.2): the
+// Plane buffers and staging are triple-buffered by epoch, so the distribution of product e+1 runs under the GEMMs of products
+// e-1 and e when the caller says that B is ready (b_ready event).  NCCL is loaded with dlopen (libnccl.so.2): the
 // library has no link-time dependency on it and shares the copy a host runtime (e.g. torch) has already loaded.
 #include <cuda.h>
 #include <dlfcn.h>
@@ -37,6 +37,10 @@
 namespace {
 
 constexpr int MG_MAX_RANKS = 32;
+// Plane / staging buffers per rank: the distribution of product e+1 may start while product e-1 is still being multiplied and has two
+// whole products' worth of time to complete (measured on 8 B200: with two buffers it could only start when EVERY rank had finished
+// product e-1, and its ~3 ms did not fit under one ~3.4 ms product once the ranks' skew was added; profiles/r02_notes.md)
+constexpr int MG_NBUF = 3;
 constexpr size_t MG_CTL_BYTES = 4096;
 // control words (uint32) at the start of every rank's arena
 enum { F_STAGED = 0, F_READY = 64, F_PULLED = 128, F_SPLIT_DONE = 192, F_ERROR = 256, F_PROBE = 320, F_FREE = 384 };
@@ -194,9 +198,9 @@ struct gffm_mg {
   int push_sms = 20;      // GFFM_MG_P2P_PUSH: SMs dedicated to the fused split + push kernel (GFFM_MG_PUSH_SMS)
   int push_ce_peers = 0;  // ... and how many of the peers get their copy from the copy engines instead (GFFM_MG_PUSH_CE_PEERS)
   int saved_gemm_ctas = -1;
-  cudaEvent_t split_ev[2] = {}, ce_done[2] = {};
+  cudaEvent_t split_ev[MG_NBUF] = {}, ce_done[MG_NBUF] = {};
   bool wait_memops = false, signal_memops = false;  // flags through stream memory operations instead of one-warp kernels
-  // arena: [control words | staging 0 | staging 1 | planes 0 | planes 1], one cudaMalloc, exported through CUDA IPC
+  // arena: [control words | MG_NBUF staging buffers | MG_NBUF plane buffers], one cudaMalloc, exported through CUDA IPC
   char* base = nullptr;
   size_t arena_bytes = 0, stage_bytes = 0, planes_bytes = 0;
   char* peer_base[MG_MAX_RANKS] = {};
@@ -204,15 +208,15 @@ struct gffm_mg {
   uint32_t epoch = 0;
   unsigned long long timeout_ns = 30ull * 1000000000ull;
   // events
-  cudaEvent_t gemm_done[2] = {}, stage_free[2] = {}, staged[2] = {}, gathered[2] = {};
-  cudaEvent_t ready_ev[2][MG_MAX_RANKS] = {};
+  cudaEvent_t gemm_done[MG_NBUF] = {}, stage_free[MG_NBUF] = {}, staged[MG_NBUF] = {}, gathered[MG_NBUF] = {};
+  cudaEvent_t ready_ev[MG_NBUF][MG_MAX_RANKS] = {};
   cudaEvent_t bc_ev[MG_MAX_RANKS] = {}, bc_consumed[MG_MAX_RANKS] = {};
   cudaEvent_t ev_call = nullptr, ev_push = nullptr, ev_comm = nullptr;
   void* xchg_dev = nullptr;  // (nranks + 1) * 128 bytes + barrier word
   int64_t rounds = 0;
   char* stage(int b) const { return base + MG_CTL_BYTES + (size_t)b * stage_bytes; }
-  char* planes(int b) const { return base + MG_CTL_BYTES + 2 * stage_bytes + (size_t)b * planes_bytes; }
-  size_t planes_off(int b) const { return MG_CTL_BYTES + 2 * stage_bytes + (size_t)b * planes_bytes; }
+  char* planes(int b) const { return base + MG_CTL_BYTES + MG_NBUF * stage_bytes + (size_t)b * planes_bytes; }
+  size_t planes_off(int b) const { return MG_CTL_BYTES + MG_NBUF * stage_bytes + (size_t)b * planes_bytes; }
   size_t stage_off(int b) const { return MG_CTL_BYTES + (size_t)b * stage_bytes; }
   uint32_t* ctl(int q) const { return reinterpret_cast<uint32_t*>(q == rank ? base : peer_base[q]); }
 };
@@ -265,7 +269,7 @@ int32_t mg_ensure_arena(gffm_mg* mg, size_t stage_bytes, size_t planes_bytes) {
   }
   mg->stage_bytes = std::max(mg->stage_bytes, stage_bytes);
   mg->planes_bytes = std::max(mg->planes_bytes, planes_bytes);
-  mg->arena_bytes = MG_CTL_BYTES + 2 * mg->stage_bytes + 2 * mg->planes_bytes;
+  mg->arena_bytes = MG_CTL_BYTES + MG_NBUF * (mg->stage_bytes + mg->planes_bytes);
   MgXchg mine;
   memset(&mine, 0, sizeof(mine));
   mine.ok = 1;
@@ -478,7 +482,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
   const size_t stage_bytes = (size_t)R.nsrc * per * std::max(ld_c, ld_b) * 4;
   GFFM_TRY(mg_ensure_arena(mg, stage_bytes, planes_bytes));
   const uint32_t e = ++mg->epoch;
-  const int b = (int)(e & 1u);
+  const int b = (int)(e % (uint32_t)MG_NBUF);
   mg->rounds++;
   out->b = b;
   out->planes = (uint8_t*)mg->planes(b);
@@ -538,7 +542,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
         for (int j = 0; j < nc; ++j) {
           const int64_t j0 = std::min<int64_t>(cnt, (int64_t)j * chunk), j1 = std::min<int64_t>(cnt, (int64_t)(j + 1) * chunk);
           if (j > 0 && j1 <= j0) continue;
-          GFFM_TRY(mg_wait(mg, mg->s_push[j], F_SPLIT_DONE, 1u << q, e - 2));  // q has consumed what this staging buffer held
+          GFFM_TRY(mg_wait(mg, mg->s_push[j], F_SPLIT_DONE, 1u << q, e - MG_NBUF));  // q has consumed what this staging buffer held
           cudaEvent_t tp = gffm_trace_begin(ctx, mg->s_push[j]);
           for (int s = 0; s < R.nsrc && j1 > j0; ++s) {
             char* dst = mg->peer_base[q] + mg->stage_off(b) + ((size_t)s * per + j0) * ld_c * 4;
@@ -562,8 +566,8 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
     else GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, bready, 0));
     GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->gemm_done[b], 0));                       // the local GEMMs of epoch e-2 are done with this buffer
     const uint32_t others = (nr >= 32 ? 0xffffffffu : ((1u << nr) - 1u)) & ~(1u << r);
-    if (push_planes) GFFM_TRY(mg_wait(mg, mg->s_dist, F_FREE, others, e - 2));  // every peer's GEMMs of epoch e-2 are done with ITS copy of this buffer
-    else GFFM_TRY(mg_wait(mg, mg->s_dist, F_PULLED, others, e - 2));           // ... and so are the peers' pulls from this buffer
+    if (push_planes) GFFM_TRY(mg_wait(mg, mg->s_dist, F_FREE, others, e - MG_NBUF));  // every peer's GEMMs of the epoch that used this buffer before are done with ITS copy
+    else GFFM_TRY(mg_wait(mg, mg->s_dist, F_PULLED, others, e - MG_NBUF));           // ... and so are the peers' pulls from this buffer
     if (push_planes) GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->ce_done[b], 0));  // copy engines of epoch e-2 no longer read this buffer
     GFFM_TRY(split_own(r, r != root && !distributed, ld_c));
     GFFM_CUDA(cudaEventRecord(mg->ready_ev[b][r], mg->s_dist));
@@ -834,7 +838,7 @@ extern "C" int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nran
   if (const char* t = getenv("GFFM_MG_COPY_STREAMS")) mg->ncopy = std::max(1, std::min((int)gffm_mg::NCOPY, atoi(t)));
   if (!ctx->s_aux) GFFM_CUDA(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
   auto mk = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < MG_NBUF; ++b) {
     GFFM_CUDA(mk(&mg->gemm_done[b]));
     GFFM_CUDA(mk(&mg->stage_free[b]));
     GFFM_CUDA(mk(&mg->staged[b]));
@@ -853,7 +857,7 @@ extern "C" int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nran
     mg->wait_memops = want_memops && mem_ops() != nullptr;
     mg->signal_memops = false;  // decided per arena: the write must reach PEER memory (self-test in mg_ensure_arena)
   }
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < MG_NBUF; ++b) {
     GFFM_CUDA(mk(&mg->split_ev[b]));
     GFFM_CUDA(mk(&mg->ce_done[b]));
   }
@@ -886,7 +890,7 @@ extern "C" int32_t gffm_mg_destroy(gffm_mg* mg) {
   if (mg->xchg_dev) cudaFree(mg->xchg_dev);
   NcclApi* nc = nccl_api();
   if (nc && mg->comm) nc->CommDestroy(mg->comm);
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < MG_NBUF; ++b) {
     for (cudaEvent_t e : {mg->gemm_done[b], mg->stage_free[b], mg->staged[b], mg->gathered[b]})
       if (e) cudaEventDestroy(e);
     for (int q = 0; q < MG_MAX_RANKS; ++q)
@@ -896,8 +900,11 @@ extern "C" int32_t gffm_mg_destroy(gffm_mg* mg) {
     if (mg->bc_ev[q]) cudaEventDestroy(mg->bc_ev[q]);
     if (mg->bc_consumed[q]) cudaEventDestroy(mg->bc_consumed[q]);
   }
-  for (cudaEvent_t e : {mg->ev_call, mg->ev_push, mg->ev_comm, mg->split_ev[0], mg->split_ev[1], mg->ce_done[0], mg->ce_done[1]})
+  for (cudaEvent_t e : {mg->ev_call, mg->ev_push, mg->ev_comm})
     if (e) cudaEventDestroy(e);
+  for (int b = 0; b < MG_NBUF; ++b)
+    for (cudaEvent_t e : {mg->split_ev[b], mg->ce_done[b]})
+      if (e) cudaEventDestroy(e);
   if (mg->saved_gemm_ctas >= 0) mg->ctx->gemm_ctas = mg->saved_gemm_ctas;
   for (cudaStream_t s : {mg->s_comm, mg->s_dist})
     if (s) cudaStreamDestroy(s);
