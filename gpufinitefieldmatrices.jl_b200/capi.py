@@ -84,6 +84,7 @@ SIGNATURES = {
     "gffm_last_timings": [_vp, C.POINTER(C.c_double), _i32, _pi32],
     "gffm_set_gemm_ctas": [_vp, _i32],
     "gffm_launch_count": [_vp, _pi64],
+    "gffm_alloc_stats": [_vp, _pi64, _pi64],
     "gffm_mat_create": [_vp, _i64, _i64, _u64, _i32, _pvp],
     "gffm_mat_wrap": [_vp, _vp, _i64, _i64, _i64, _u64, _pvp],
     "gffm_mat_destroy": [_vp],

@@ -67,6 +67,8 @@ extern "C" int32_t gffm_create(int32_t device, gffm_ctx** out) {
 }
 
 cudaError_t gffm_dev_alloc(gffm_ctx* ctx, void** ptr, size_t bytes) {
+  ctx->alloc_bytes += (int64_t)bytes;
+  ctx->alloc_calls++;
   cudaError_t e = cudaMallocAsync(ptr, bytes ? bytes : 4, ctx->stream);
   if (e != cudaSuccess) {  // pool fragmented or exhausted: hand cached blocks back to the driver and retry once
     cudaGetLastError();
@@ -228,6 +230,14 @@ extern "C" int32_t gffm_launch_count(gffm_ctx* ctx, int64_t* count) {
   return GFFM_OK;
 }
 
+extern "C" int32_t gffm_alloc_stats(gffm_ctx* ctx, int64_t* bytes, int64_t* calls) {
+  GFFM_ENTER_CTX(ctx);
+  if (!ctx) GFFM_FAIL(GFFM_ERR_INVALID, "null ctx");
+  if (bytes) *bytes = ctx->alloc_bytes;
+  if (calls) *calls = ctx->alloc_calls;
+  return GFFM_OK;
+}
+
 int32_t gffm_ws_reserve(gffm_ctx* ctx, gffm_workspace* ws, size_t bytes) {
   if (ws->bytes >= bytes) return GFFM_OK;
   if (ws->ptr) {
@@ -237,6 +247,8 @@ int32_t gffm_ws_reserve(gffm_ctx* ctx, gffm_workspace* ws, size_t bytes) {
     ws->bytes = 0;
   }
   size_t want = bytes + bytes / 8 + 4096;
+  ctx->alloc_bytes += (int64_t)want;
+  ctx->alloc_calls++;
   cudaError_t e = cudaMalloc(&ws->ptr, want);
   if (e != cudaSuccess) {
     cudaGetLastError();

@@ -71,6 +71,7 @@ struct gffm_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int64_t launches = 0;
+  int64_t alloc_bytes = 0, alloc_calls = 0;  // device memory requested by the library on this context since creation (gffm_alloc_stats)
   int gemm_ctas = 0;  // cap on the persistent GEMM grid (0 = one CTA per SM); leaves SMs to concurrent NCCL kernels (gffm_set_gemm_ctas)
   // grow-only scratch buffers (stream-ordered reuse)
   gffm_workspace ws_planes_a, ws_planes_b, ws_eplanes, ws_misc, ws_misc2, ws_pinned, ws_invtab, ws_scratch, ws_host, ws_gemv;

@@ -62,6 +62,13 @@ class Context:
         capi.check(self.lib.gffm_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def alloc_stats(self):
+        """(bytes, calls): device memory requested by the library on this context since creation -- the counterpart of
+        CUDA.@timed's gpu_bytes in the reference's allocation tests (test/CuModMatrix/allocations_test.jl:21-52)"""
+        b, c = C.c_int64(0), C.c_int64(0)
+        capi.check(self.lib.gffm_alloc_stats(self.h, C.byref(b), C.byref(c)))
+        return b.value, c.value
+
     def modinv_batch(self, values, N: int):
         v = np.ascontiguousarray(values, dtype=np.uint64)
         out = np.zeros_like(v)

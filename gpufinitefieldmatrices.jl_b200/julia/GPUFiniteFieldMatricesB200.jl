@@ -61,6 +61,7 @@ device_count() = (r = Ref{Int32}(0); check(ccall((:gffm_device_count, libgffm), 
 synchronize(c::Context=default_context()) = check(ccall((:gffm_sync, libgffm), Int32, (Ptr{Cvoid},), c.h))
 set_stream!(c::Context, s::Ptr{Cvoid}) = check(ccall((:gffm_set_stream, libgffm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), c.h, s))
 get_stream(c::Context) = (r = Ref{Ptr{Cvoid}}(C_NULL); check(ccall((:gffm_get_stream, libgffm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), c.h, r)); r[])
+alloc_stats(c::Context=default_context()) = (b = Ref{Int64}(0); k = Ref{Int64}(0); check(ccall((:gffm_alloc_stats, libgffm), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), c.h, b, k)); (b[], k[]))
 launch_count(c::Context=default_context()) = (r = Ref{Int64}(0); check(ccall((:gffm_launch_count, libgffm), Int32, (Ptr{Cvoid}, Ref{Int64}), c.h, r)); r[])
 set_gemm_ctas!(c::Context, n::Integer) = check(ccall((:gffm_set_gemm_ctas, libgffm), Int32, (Ptr{Cvoid}, Int32), c.h, n))
 set_profiling!(c::Context, on::Bool) = check(ccall((:gffm_set_profiling, libgffm), Int32, (Ptr{Cvoid}, Int32), c.h, on ? 1 : 0))

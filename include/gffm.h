@@ -106,6 +106,10 @@ int32_t gffm_last_timings(gffm_ctx* ctx, double* ms, int32_t capacity, int32_t* 
 int32_t gffm_set_gemm_ctas(gffm_ctx* ctx, int32_t ctas);
 /* number of library kernels launched on this context since creation (bench.py's gpu_launches) */
 int32_t gffm_launch_count(gffm_ctx* ctx, int64_t* count);
+/* device memory the library has requested on this context since creation (matrices, plane caches, workspaces): cumulative
+ * bytes and number of requests.  The difference across a call is what CUDA.@timed's gpu_bytes reports for the reference
+ * (test/CuModMatrix/allocations_test.jl:21-52: 0 for the in-place elementwise methods, < 20 for a warm mul!) */
+int32_t gffm_alloc_stats(gffm_ctx* ctx, int64_t* bytes, int64_t* calls);
 
 /* ---- container: struct CuModArray + ctors, CuModMatrix.jl:42-181, :510-556 ------------------------ */
 /* zeros(T, rows, cols, N) with +pad zero slack (CuModMatrix.jl:530-534); pad < 0 selects the reference's 32 */

@@ -887,3 +887,46 @@ def test_wide_moduli_container_and_elementwise(g):
         g.pluq_gpu_kernel(g.CuModMatrix(Ah[:20, :20], N, elem_type=np.float64))
     with pytest.raises(g.CuModArrayModulusMismatchException):
         g.CuModMatrix(Ah, 2 ** 52 + 1)
+
+
+# ---------------------------------------------------------------- allocations (test/CuModMatrix/allocations_test.jl:21-52) ----
+def test_inplace_methods_allocate_no_device_memory(g):
+    """The reference's allocation contract, restated with the library's own allocation counter (gffm_alloc_stats) in the role of
+    CUDA.@timed's gpu_bytes, and cross-checked against the driver's free-memory figure: the in-place elementwise methods request
+    ZERO device bytes (allocations_test.jl:21-46, `== 0`), a warm mul! (matrix and vector form) requests none either
+    (:48-52, `< 20`)."""
+    import torch
+    n = 3003
+    rng = np.random.default_rng(5)
+    Ad = rng.integers(0, 11, size=(n, n)); Bd = rng.integers(0, 11, size=(n, n)); xd = rng.integers(0, 11, size=n)
+    A = g.CuModMatrix(Ad, 11); B = g.CuModMatrix(Bd, 11); x = g.CuModVector(xd, 11)
+    C_ = g.zeros(np.float32, n, n, 11); z = g.zeros(np.float32, n, 1, 11)
+    ctx = g.default_context()
+    cases = [
+        ("add!", lambda: g.add_(C_, A, B)), ("sub!", lambda: g.sub_(C_, A, B)), ("negate!", lambda: g.negate_(C_, A)),
+        ("scalar_add!", lambda: g.scalar_add_(C_, A, 2)), ("scalar_sub!", lambda: g.scalar_sub_(C_, A, 2)),
+        ("mul!(C,A,2)", lambda: g.mul_(C_, A, 2)), ("elementwise_multiply!", lambda: g.elementwise_multiply_(C_, A, B)),
+        ("copy!", lambda: g.copy_(C_, A)), ("mod_elements!", lambda: g.mod_elements_(C_, 3)),
+    ]
+    for name, fn in cases:  # no warm-up: these never allocate
+        ctx.sync()
+        b0, c0 = ctx.alloc_stats()
+        free0 = torch.cuda.mem_get_info()[0]
+        fn()
+        ctx.sync()
+        b1, c1 = ctx.alloc_stats()
+        assert (b1 - b0, c1 - c0) == (0, 0), name
+        assert torch.cuda.mem_get_info()[0] >= free0, name
+    g.mod_elements_(C_, 11)
+    for name, fn in [("mul!(C,A,B)", lambda: g.mul_(C_, A, B)), ("mul!(z,A,x)", lambda: g.mul_(z, A, x))]:
+        fn()  # the reference primes CUDA.@timed the same way: workspaces and operand-plane caches exist after the first call
+        ctx.sync()
+        b0, c0 = ctx.alloc_stats()
+        free0 = torch.cuda.mem_get_info()[0]
+        fn()
+        ctx.sync()
+        b1, _ = ctx.alloc_stats()
+        assert b1 - b0 < 20, (name, b1 - b0)
+        assert torch.cuda.mem_get_info()[0] >= free0, name
+    assert np.array_equal(C_.to_int(), (Ad.astype(object).dot(Bd.astype(object)) % 11).astype(np.int64))
+    assert np.array_equal(z.to_int().ravel(), (Ad.dot(xd) % 11))
