@@ -123,6 +123,7 @@ SIGNATURES = {
     "gffm_mg_set_transport": [_vp, _i32],
     "gffm_mg_barrier": [_vp],
     "gffm_mg_owner_ranges": [_i64, _i32, _pi64],
+    "gffm_mg_owner_ranges_root_free": [_i64, _i32, _i32, _pi64],
     "gffm_mg_gemm": [_vp, _vp, _vp, _vp, _i32, _vp, _u64, _u64],
     "gffm_mg_kmat_mul": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _i32, _vp],
     "gffm_mg_gemv": [_vp, _vp, _vp, _vp, _i32, _u64, _u64],

@@ -197,6 +197,7 @@ struct gffm_mg {
   int ncopy = NCOPY;
   int push_sms = 20;      // GFFM_MG_P2P_PUSH: SMs dedicated to the fused split + push kernel (GFFM_MG_PUSH_SMS)
   int push_ce_peers = 0;  // ... and how many of the peers get their copy from the copy engines instead (GFFM_MG_PUSH_CE_PEERS)
+  int root_free_min = 6;  // peer-memory transports: from this many ranks on the root owns no column range of B (0: never; GFFM_MG_ROOT_FREE_MIN)
   int saved_gemm_ctas = -1;
   cudaEvent_t split_ev[MG_NBUF] = {}, ce_done[MG_NBUF] = {};
   bool wait_memops = false, signal_memops = false;  // flags through stream memory operations instead of one-warp kernels
@@ -463,13 +464,29 @@ struct MgRoundOut {
   cudaEvent_t ready[MG_MAX_RANKS];
 };
 
+// the 256-column blocks of B dealt to every rank but `root` (rank order, the first owners take the remainder); off[root + 1] == off[root]
+void mg_root_free_ranges(int64_t n, int nr, int root, int64_t* off) {
+  const int64_t blocks = ceil_div(n, 256), base = blocks / (nr - 1), extra = blocks % (nr - 1);
+  off[0] = 0;
+  for (int q = 0, o = 0; q < nr; ++q) {
+    const int64_t nb = q == root ? 0 : base + (o++ < extra ? 1 : 0);
+    off[q + 1] = std::min<int64_t>(n, off[q] + nb * 256);
+  }
+}
+
 int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
   gffm_ctx* ctx = mg->ctx;
   NcclApi* nc = nccl_api();
   const int nr = mg->nranks, r = mg->rank, root = R.root;
   const int64_t n = R.n, kc = R.kc;
   const int64_t per = round_up(ceil_div(n, nr), 256), rowsPB = per * nr;
-  for (int q = 0; q <= nr; ++q) out->off[q] = std::min<int64_t>(n, (int64_t)q * per);
+  // With many ranks the root's NVLink egress is the bottleneck of the peer-memory transports when it owns a column range like
+  // everybody else: it sends the other ranks' uint32 ranges (4 bytes per element) AND its own range's planes to every peer (8 x 1
+  // byte per element and peer) -- 2.75 GB per 16384^2 product at 8 ranks against 1.9 GB for the others (measured: the root's split +
+  // push kernel takes 4.8 ms, everybody else's 2.9 ms, and the 4 ms step waits for it; profiles/r02_notes.md).  From `root_free_min`
+  // ranks on the root therefore owns NO range: the 256-column blocks of B are dealt to the other ranks, the root only scatters.
+  const bool root_free_possible = root >= 0 && mg->root_free_min > 0 && nr >= mg->root_free_min && nr >= 2;
+  const int64_t per_stage = root_free_possible ? round_up(ceil_div(n, nr - 1), 256) : per;  // upper bound of any owner's range
   // plane-set offsets and sizes
   size_t planes_bytes = 0;
   for (int s = 0; s < R.nsets; ++s) {
@@ -479,8 +496,16 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
   }
   const int64_t ld_c = round_up(kc, 32);                      // compact staging columns (peer-memory transport)
   const int64_t ld_b = R.src[0].ld;                           // NCCL scatter keeps the source's leading dimension
-  const size_t stage_bytes = (size_t)R.nsrc * per * std::max(ld_c, ld_b) * 4;
+  const size_t stage_bytes = (size_t)R.nsrc * per_stage * std::max(ld_c, ld_b) * 4;
   GFFM_TRY(mg_ensure_arena(mg, stage_bytes, planes_bytes));
+  const bool distributed = root < 0;  // every rank already holds its own column range of B: nothing to push / scatter
+  const int transport = (distributed && mg->transport == GFFM_MG_NCCL_BCAST) ? GFFM_MG_NCCL_PLANES : mg->transport;
+  const bool root_free = root_free_possible && (transport == GFFM_MG_P2P_PLANES || transport == GFFM_MG_P2P_PUSH);
+  if (!root_free) {
+    for (int q = 0; q <= nr; ++q) out->off[q] = std::min<int64_t>(n, (int64_t)q * per);
+  } else {
+    mg_root_free_ranges(n, nr, root, out->off);
+  }
   const uint32_t e = ++mg->epoch;
   const int b = (int)(e % (uint32_t)MG_NBUF);
   mg->rounds++;
@@ -506,7 +531,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       const MgSet& S = R.sets[s];
       MatView v, v2;
       auto view_of_src = [&](int which) {
-        if (from_stage) return MatView{reinterpret_cast<uint32_t*>(mg->stage(b)) + (size_t)which * per * ld_stage, ld_stage, kc, cnt};
+        if (from_stage) return MatView{reinterpret_cast<uint32_t*>(mg->stage(b)) + (size_t)which * per_stage * ld_stage, ld_stage, kc, cnt};
         return sub_view(R.src[which], 0, R.root < 0 ? 0 : c0, kc, cnt);  // distributed B: the local matrix IS the own range
       };
       v = view_of_src(S.src);
@@ -518,16 +543,14 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
         bufs[nb++] = (uint8_t*)(mg->base + mg->planes_off(b) + S.off);
         const int ce = (r == R.root) ? 0 : std::min(mg->push_ce_peers, nr - 1);  // the root's copy engines already carry the uint32 ranges
         for (int i = 1; i < nr - ce; ++i) bufs[nb++] = (uint8_t*)(mg->peer_base[(r + i) % nr] + mg->planes_off(b) + S.off);
-        GFFM_TRY(gffm_bplan_split_push(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, bufs, nb, rowsPB, (int64_t)q * per, mg->s_dist, mg->push_sms));
+        GFFM_TRY(gffm_bplan_split_push(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, bufs, nb, rowsPB, c0, mg->s_dist, mg->push_sms));
       } else {
-        GFFM_TRY(gffm_bplan_split(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, out->planes + S.off, rowsPB, (int64_t)q * per, mg->s_dist));
+        GFFM_TRY(gffm_bplan_split(ctx, S.plan, v, S.src2 >= 0 ? &v2 : nullptr, out->planes + S.off, rowsPB, c0, mg->s_dist));
       }
     }
     return GFFM_OK;
   };
 
-  const bool distributed = root < 0;  // every rank already holds its own column range of B: nothing to push / scatter
-  const int transport = (distributed && mg->transport == GFFM_MG_NCCL_BCAST) ? GFFM_MG_NCCL_PLANES : mg->transport;
   push_planes = transport == GFFM_MG_P2P_PUSH;
   if (transport == GFFM_MG_P2P_PLANES || transport == GFFM_MG_P2P_PUSH) {
     // ---- root: push every other rank's uint32 column range into its staging buffer (copy engines, peer memory) -------------
@@ -545,7 +568,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
           GFFM_TRY(mg_wait(mg, mg->s_push[j], F_SPLIT_DONE, 1u << q, e - MG_NBUF));  // q has consumed what this staging buffer held
           cudaEvent_t tp = gffm_trace_begin(ctx, mg->s_push[j]);
           for (int s = 0; s < R.nsrc && j1 > j0; ++s) {
-            char* dst = mg->peer_base[q] + mg->stage_off(b) + ((size_t)s * per + j0) * ld_c * 4;
+            char* dst = mg->peer_base[q] + mg->stage_off(b) + ((size_t)s * per_stage + j0) * ld_c * 4;
             GFFM_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld_c * 4, R.src[s].p + (c0 + j0) * R.src[s].ld, (size_t)R.src[s].ld * 4, (size_t)kc * 4,
                                         (size_t)(j1 - j0), cudaMemcpyDefault, mg->s_push[j]));
           }
@@ -584,7 +607,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
         cudaEvent_t tp = gffm_trace_begin(ctx, cs);
         for (int s2 = 0; s2 < R.nsets && cnt > 0; ++s2) {
           const BPlaneSpec* sp = gffm_bplan_spec(R.sets[s2].plan);
-          const size_t pitch = (size_t)rowsPB * sp->Kp, rel = R.sets[s2].off + (size_t)r * per * sp->Kp;
+          const size_t pitch = (size_t)rowsPB * sp->Kp, rel = R.sets[s2].off + (size_t)out->off[r] * sp->Kp;
           for (int t = 0; t < sp->nplanes; ++t)
             GFFM_CUDA(cudaMemcpyAsync(mg->peer_base[q] + mg->planes_off(b) + rel + t * pitch, mg->planes(b) + rel + t * pitch, (size_t)cnt * sp->Kp,
                                       cudaMemcpyDefault, cs));
@@ -650,7 +673,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
               tpl[j] = gffm_trace_begin(ctx, mg->s_pull[j]);
               used[j] = true;
             }
-            const size_t rel = R.sets[s].off + (size_t)t * pitch + ((size_t)q * per + i0) * sp->Kp;
+            const size_t rel = R.sets[s].off + (size_t)t * pitch + ((size_t)out->off[q] + i0) * sp->Kp;
             GFFM_CUDA(cudaMemcpyAsync(mg->planes(b) + rel, mg->peer_base[q] + mg->planes_off(b) + rel, (size_t)ni * sp->Kp, cudaMemcpyDefault, mg->s_pull[j]));
           }
         }
@@ -693,7 +716,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
         }
       } else if (cnt_r > 0) {
         for (int s = 0; s < R.nsrc; ++s)
-          MG_NCCL(nc->Recv(reinterpret_cast<uint32_t*>(mg->stage(b)) + (size_t)s * per * ld_b, (size_t)((cnt_r - 1) * ld_b + kc), ncclUint32, root, mg->comm,
+          MG_NCCL(nc->Recv(reinterpret_cast<uint32_t*>(mg->stage(b)) + (size_t)s * per_stage * ld_b, (size_t)((cnt_r - 1) * ld_b + kc), ncclUint32, root, mg->comm,
                            mg->s_comm));
       }
       MG_NCCL(nc->GroupEnd());
@@ -809,6 +832,12 @@ extern "C" int32_t gffm_mg_owner_ranges(int64_t n, int32_t nranks, int64_t* off)
   return GFFM_OK;
 }
 
+extern "C" int32_t gffm_mg_owner_ranges_root_free(int64_t n, int32_t nranks, int32_t root, int64_t* off) {
+  if (!off || nranks < 2 || nranks > MG_MAX_RANKS || n < 0 || root < 0 || root >= nranks) GFFM_FAIL(GFFM_ERR_INVALID, "bad arguments");
+  mg_root_free_ranges(n, nranks, root, off);
+  return GFFM_OK;
+}
+
 extern "C" int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nranks, int32_t rank, gffm_mg** out) {
   GFFM_ENTER_CTX(ctx);
   if (!ctx || !id128 || !out) GFFM_FAIL(GFFM_ERR_INVALID, "null");
@@ -863,6 +892,7 @@ extern "C" int32_t gffm_mg_create(gffm_ctx* ctx, const void* id128, int32_t nran
   }
   if (const char* t = getenv("GFFM_MG_PUSH_SMS")) mg->push_sms = std::max(1, std::min(ctx->num_sms / 2, atoi(t)));
   if (const char* t = getenv("GFFM_MG_PUSH_CE_PEERS")) mg->push_ce_peers = std::max(0, atoi(t));
+  if (const char* t = getenv("GFFM_MG_ROOT_FREE_MIN")) mg->root_free_min = std::max(0, atoi(t));
   GFFM_CUDA(mk(&mg->ev_call));
   GFFM_CUDA(mk(&mg->ev_push));
   GFFM_CUDA(mk(&mg->ev_comm));

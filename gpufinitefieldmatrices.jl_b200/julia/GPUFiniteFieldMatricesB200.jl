@@ -390,6 +390,7 @@ function mg_info(m::MultiGpu)
 end
 mg_set_transport!(m::MultiGpu, t::Integer) = check(ccall((:gffm_mg_set_transport, libgffm), Int32, (Ptr{Cvoid}, Int32), m.h, t))
 mg_barrier(m::MultiGpu) = check(ccall((:gffm_mg_barrier, libgffm), Int32, (Ptr{Cvoid},), m.h))
+mg_owner_ranges_root_free(n::Integer, nranks::Integer, root::Integer) = (off = Base.zeros(Int64, nranks + 1); check(ccall((:gffm_mg_owner_ranges_root_free, libgffm), Int32, (Int64, Int32, Int32, Ptr{Int64}), n, nranks, root, off)); off)
 mg_owner_ranges(n::Integer, nranks::Integer) = (off = Base.zeros(Int64, nranks + 1); check(ccall((:gffm_mg_owner_ranges, libgffm), Int32, (Int64, Int32, Ptr{Int64}), n, nranks, off)); off)
 # mul!(C, A, B) on row blocks: C, A = this rank's row blocks, B = the matrix on root (a same-shape matrix elsewhere)
 function mg_mul!(m::MultiGpu, C::CuModArray{T,2}, A::CuModArray{T,2}, B::CuModArray{T,2}; root::Integer=0, b_ready::Ptr{Cvoid}=C_NULL, R::Integer=0, P::Integer=0) where {T}

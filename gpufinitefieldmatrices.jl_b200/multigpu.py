@@ -224,6 +224,13 @@ def owner_ranges(n: int, nranks: int) -> List[int]:
     return [int(v) for v in off]
 
 
+def owner_ranges_root_free(n: int, nranks: int, root: int) -> List[int]:
+    """The ranges the peer-memory transports use with many ranks (gffm_mg_owner_ranges_root_free): the root owns no columns."""
+    off = (ctypes.c_int64 * (nranks + 1))()
+    capi.check(capi.load().gffm_mg_owner_ranges_root_free(int(n), int(nranks), int(root), off))
+    return [int(v) for v in off]
+
+
 class MultiGpu:
     """One rank of the library's own multi-GPU layer: sharded products through `gffm_mg_gemm` / `gffm_mg_kmat_mul` /
     `gffm_mg_gemv`.  The 128-byte id comes from `MultiGpu.unique_id()` on one rank and reaches the others by any channel

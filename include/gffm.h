@@ -209,6 +209,10 @@ int32_t gffm_mg_set_transport(gffm_mg* mg, int32_t transport);
 int32_t gffm_mg_barrier(gffm_mg* mg);
 /* column ranges of B owned by the ranks: off[0..nranks] (equal widths, multiples of 256) -- pure function, no GPU needed */
 int32_t gffm_mg_owner_ranges(int64_t n, int32_t nranks, int64_t* off);
+/* the ranges the peer-memory transports use from GFFM_MG_ROOT_FREE_MIN (default 6) ranks on when B lives on `root`: the root owns
+ * nothing (its NVLink egress already carries everybody else's uint32 ranges), the 256-column blocks are dealt to the other ranks in
+ * rank order; off[root + 1] == off[root] -- pure function, no GPU needed */
+int32_t gffm_mg_owner_ranges_root_free(int64_t n, int32_t nranks, int32_t root, int64_t* off);
 /* C_shard = A_shard * B mod P: mul!(C,A,B) (CuModMatrix.jl:767-787) on row blocks.  B holds the matrix on `root`; on the other
  * ranks it is a same-shape matrix created the same way (receive buffer of the broadcast transport, otherwise untouched).
  * b_ready_event: cudaEvent_t recorded after B's last modification on root, or NULL = B is ready in context-stream order.  With an

@@ -106,4 +106,16 @@ def test_mg_owner_ranges_is_a_pure_function():
     assert g.multigpu.owner_ranges(0, 3) == [0, 0, 0, 0]
     with pytest.raises(g.GffmError):
         g.multigpu.owner_ranges(10, 0)
+    # root-free ranges (peer-memory transports from 6 ranks on): the root owns nothing, 256-column blocks dealt to the others
+    assert g.multigpu.owner_ranges_root_free(16384, 8, 0) == [0, 0, 2560, 4864, 7168, 9472, 11776, 14080, 16384]
+    assert g.multigpu.owner_ranges_root_free(16384, 8, 7) == [0, 2560, 4864, 7168, 9472, 11776, 14080, 16384, 16384]
+    assert g.multigpu.owner_ranges_root_free(1000, 2, 1) == [0, 1000, 1000]
+    for n, nr, root in [(300, 4, 2), (0, 3, 1), (32768, 8, 3), (5000, 6, 5), (257, 32, 31)]:
+        off = g.multigpu.owner_ranges_root_free(n, nr, root)
+        assert off[0] == 0 and off[-1] == n and off[root] == off[root + 1] and all(b >= a for a, b in zip(off, off[1:]))
+        assert all(o % 256 == 0 or o == n for o in off)
+        widths = [b - a for q, (a, b) in enumerate(zip(off, off[1:])) if q != root]
+        assert max(widths) - min(widths) <= 256 or n < 256 * (nr - 1)
+    with pytest.raises(g.GffmError):
+        g.multigpu.owner_ranges_root_free(10, 1, 0)
     assert len(g.multigpu.MultiGpu.unique_id()) == 128  # NCCL is dlopen'ed on demand, no link-time dependency
