@@ -892,10 +892,9 @@ def test_wide_moduli_container_and_elementwise(g):
 # ---------------------------------------------------------------- allocations (test/CuModMatrix/allocations_test.jl:21-52) ----
 def test_inplace_methods_allocate_no_device_memory(g):
     """The reference's allocation contract, restated with the library's own allocation counter (gffm_alloc_stats) in the role of
-    CUDA.@timed's gpu_bytes, and cross-checked against the driver's free-memory figure: the in-place elementwise methods request
-    ZERO device bytes (allocations_test.jl:21-46, `== 0`), a warm mul! (matrix and vector form) requests none either
-    (:48-52, `< 20`)."""
-    import torch
+    CUDA.@timed's gpu_bytes (which likewise counts the requests made to CUDA.jl's pool, not driver-level page mappings such as lazily
+    loaded kernel code): the in-place elementwise methods request ZERO device bytes (allocations_test.jl:21-46, `== 0`), a warm mul!
+    (matrix and vector form) requests none either (:48-52, `< 20`)."""
     n = 3003
     rng = np.random.default_rng(5)
     Ad = rng.integers(0, 11, size=(n, n)); Bd = rng.integers(0, 11, size=(n, n)); xd = rng.integers(0, 11, size=n)
@@ -911,22 +910,18 @@ def test_inplace_methods_allocate_no_device_memory(g):
     for name, fn in cases:  # no warm-up: these never allocate
         ctx.sync()
         b0, c0 = ctx.alloc_stats()
-        free0 = torch.cuda.mem_get_info()[0]
         fn()
         ctx.sync()
         b1, c1 = ctx.alloc_stats()
         assert (b1 - b0, c1 - c0) == (0, 0), name
-        assert torch.cuda.mem_get_info()[0] >= free0, name
     g.mod_elements_(C_, 11)
     for name, fn in [("mul!(C,A,B)", lambda: g.mul_(C_, A, B)), ("mul!(z,A,x)", lambda: g.mul_(z, A, x))]:
         fn()  # the reference primes CUDA.@timed the same way: workspaces and operand-plane caches exist after the first call
         ctx.sync()
         b0, c0 = ctx.alloc_stats()
-        free0 = torch.cuda.mem_get_info()[0]
         fn()
         ctx.sync()
         b1, _ = ctx.alloc_stats()
         assert b1 - b0 < 20, (name, b1 - b0)
-        assert torch.cuda.mem_get_info()[0] >= free0, name
-    assert np.array_equal(C_.to_int(), (Ad.astype(object).dot(Bd.astype(object)) % 11).astype(np.int64))
+    assert np.array_equal(C_.to_int(), np.mod(Ad.astype(np.float64) @ Bd.astype(np.float64), 11).astype(np.int64))  # exact: sums < 2^53
     assert np.array_equal(z.to_int().ravel(), (Ad.dot(xd) % 11))
