@@ -461,10 +461,21 @@ def main():
                 else:
                     mgpu.gemm(C, A, B, root=0, b_ready=b_ready.cuda_event)
 
-            names = {"p2p_push": g.capi.MG_P2P_PUSH, "p2p_planes": g.capi.MG_P2P_PLANES, "nccl_planes": g.capi.MG_NCCL_PLANES, "nccl_bcast": g.capi.MG_NCCL_BCAST,
+            names = {"p2p_raw": g.capi.MG_P2P_RAW, "p2p_push": g.capi.MG_P2P_PUSH, "p2p_planes": g.capi.MG_P2P_PLANES, "nccl_planes": g.capi.MG_NCCL_PLANES, "nccl_bcast": g.capi.MG_NCCL_BCAST,
                      "auto": g.capi.MG_AUTO}
-            cands = ["p2p_push", "p2p_planes", "nccl_planes", "nccl_bcast"] if args.transport == "tune" else [t.strip() for t in args.transport.split(",")]
+            cands = ["p2p_raw", "p2p_push", "p2p_planes", "nccl_planes", "nccl_bcast"] if args.transport == "tune" else [t.strip() for t in args.transport.split(",")]
             best = None
+            # reference result for the trials: the product through the NCCL broadcast transport (every rank splits all of B itself)
+            outs = [CK.data1, CK.data2] if kara else [C]
+            refs = None
+            if len(cands) > 1:
+                mgpu.set_transport(g.capi.MG_NCCL_BCAST)
+                step()
+                mgpu.barrier()
+                refs = [g.zeros(np.float32, mloc, n, o.N, ctx=ctx) for o in outs]
+                for rf, o in zip(refs, outs):
+                    g.copy_(rf, o)
+                ctx.sync()
             for tname in cands:
                 ok_t = True
                 try:
@@ -477,6 +488,9 @@ def main():
                     tune[tname] = f"unavailable: {str(ex)[:160]}"
                 if not allmin_flag(ok_t):  # a transport is used only if every rank can use it
                     tune.setdefault(tname, "unavailable on another rank")
+                    continue
+                if refs is not None and not allmin_flag(all(o.equals(rf) for o, rf in zip(outs, refs))):  # ... and only if its product is bit-equal
+                    tune[tname] = "rejected: result differs from the NCCL broadcast transport's"
                     continue
                 if len(cands) == 1:
                     best = tname
@@ -495,6 +509,7 @@ def main():
                 tune[tname] = allmax(a0.elapsed_time(a1) / 12)
                 if best is None or tune[tname] < tune[best]:
                     best = tname
+            del refs
             if best is None:
                 raise SystemExit("no multi-GPU transport is usable: " + json.dumps(tune))
             # ties (within 3 %) go to the library's default transport: its trial times have been the reproducible ones (see above)

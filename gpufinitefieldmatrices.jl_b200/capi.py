@@ -17,7 +17,7 @@ EW_MOD, EW_ADD, EW_SUB, EW_MUL, EW_SADD, EW_SSUB, EW_RSSUB, EW_SMUL, EW_SDIV = r
 GEMM_STORE, GEMM_ADD, GEMM_SUB = range(3)
 ALGO_AUTO, ALGO_SIMT, ALGO_LIMB, ALGO_RNS = range(4)
 PIVOT_CORRECT, PIVOT_REFERENCE_QUIRK = range(2)
-MG_AUTO, MG_NCCL_BCAST, MG_NCCL_PLANES, MG_P2P_PLANES, MG_P2P_PUSH = range(5)
+MG_AUTO, MG_NCCL_BCAST, MG_NCCL_PLANES, MG_P2P_PLANES, MG_P2P_PUSH, MG_P2P_RAW = range(6)
 MG_DISTRIBUTED = -1
 
 

@@ -19,6 +19,12 @@
 //                       posted NVLink stores from the kernel that creates the planes): no staging copy of the planes, no pull, the
 //                       copy engines only carry the root's uint32 ranges.  Consumers wait for the owner's epoch flag, owners wait
 //                       for the consumers' "buffer free" flags.
+//   GFFM_MG_P2P_RAW     what travels is the uint32 residues (4 bytes per element instead of 8 one-byte planes): the root's copy engines
+//                       push every owner's range into that owner's staging buffer, every owner's copy engines FORWARD the range to all
+//                       other ranks' staging buffers (an all-gather by posted peer writes; the root needs nothing, it holds B), and
+//                       every rank splits every range locally as it arrives, under its own GEMMs.  No SM of any GPU is used for
+//                       communication and the GEMM keeps all SMs; the price is the replicated split (HBM-bound, 0.6 ms per 16384^2
+//                       operand when alone).  Half the NVLink bytes of the plane transports.
 //   GFFM_MG_NCCL_PLANES the same data flow with NCCL: grouped ncclSend/ncclRecv scatter of the uint32 ranges, one grouped
 //                       in-place ncclAllGather of the planes.
 //   GFFM_MG_NCCL_BCAST  ncclBroadcast of B's uint32 column ranges, every rank splits all of B (round-1 data flow).
@@ -376,7 +382,7 @@ int32_t mg_ensure_arena(gffm_mg* mg, size_t stage_bytes, size_t planes_bytes) {
     GFFM_CUDA(cudaMemcpy(word, &zero, sizeof(int), cudaMemcpyHostToDevice));
     mg->signal_memops = all_sig == 1;
   }
-  if ((mg->requested == GFFM_MG_P2P_PLANES || mg->requested == GFFM_MG_P2P_PUSH) && !mg->p2p_ok)
+  if ((mg->requested == GFFM_MG_P2P_PLANES || mg->requested == GFFM_MG_P2P_PUSH || mg->requested == GFFM_MG_P2P_RAW) && !mg->p2p_ok)
     GFFM_FAIL(GFFM_ERR_UNSUPPORTED, "a peer-memory transport was requested but peer memory (CUDA IPC / peer access) is not available between all ranks");
   mg->transport = mg->requested != GFFM_MG_AUTO ? mg->requested : (mg->p2p_ok ? GFFM_MG_P2P_PUSH : GFFM_MG_NCCL_PLANES);
   mg->epoch = 0;
@@ -496,11 +502,12 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
   }
   const int64_t ld_c = round_up(kc, 32);                      // compact staging columns (peer-memory transport)
   const int64_t ld_b = R.src[0].ld;                           // NCCL scatter keeps the source's leading dimension
-  const size_t stage_bytes = (size_t)R.nsrc * per_stage * std::max(ld_c, ld_b) * 4;
+  // GFFM_MG_P2P_RAW stages ALL of B (compact columns) on every rank, the other transports only the own range
+  const size_t stage_bytes = mg->requested == GFFM_MG_P2P_RAW ? (size_t)R.nsrc * rowsPB * ld_c * 4 : (size_t)R.nsrc * per_stage * std::max(ld_c, ld_b) * 4;
   GFFM_TRY(mg_ensure_arena(mg, stage_bytes, planes_bytes));
   const bool distributed = root < 0;  // every rank already holds its own column range of B: nothing to push / scatter
   const int transport = (distributed && mg->transport == GFFM_MG_NCCL_BCAST) ? GFFM_MG_NCCL_PLANES : mg->transport;
-  const bool root_free = root_free_possible && (transport == GFFM_MG_P2P_PLANES || transport == GFFM_MG_P2P_PUSH);
+  const bool root_free = root_free_possible && (transport == GFFM_MG_P2P_PLANES || transport == GFFM_MG_P2P_PUSH || transport == GFFM_MG_P2P_RAW);
   if (!root_free) {
     for (int q = 0; q <= nr; ++q) out->off[q] = std::min<int64_t>(n, (int64_t)q * per);
   } else {
@@ -519,6 +526,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
     bready = mg->ev_call;
   }
   bool push_planes = false;  // GFFM_MG_P2P_PUSH: the split stores to every rank's plane buffer
+  const bool raw_stage = transport == GFFM_MG_P2P_RAW;  // staging holds all of B: source s, column c at ((s * rowsPB + c) * ld_c) words
   auto split_own = [&](int q, bool from_stage, int64_t ld_stage) -> int32_t {
     const int64_t c0 = out->off[q], cnt = out->off[q + 1] - c0;
     if (cnt <= 0) return GFFM_OK;
@@ -531,6 +539,7 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       const MgSet& S = R.sets[s];
       MatView v, v2;
       auto view_of_src = [&](int which) {
+        if (from_stage && raw_stage) return MatView{reinterpret_cast<uint32_t*>(mg->stage(b)) + ((size_t)which * rowsPB + c0) * ld_stage, ld_stage, kc, cnt};
         if (from_stage) return MatView{reinterpret_cast<uint32_t*>(mg->stage(b)) + (size_t)which * per_stage * ld_stage, ld_stage, kc, cnt};
         return sub_view(R.src[which], 0, R.root < 0 ? 0 : c0, kc, cnt);  // distributed B: the local matrix IS the own range
       };
@@ -552,6 +561,103 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
   };
 
   push_planes = transport == GFFM_MG_P2P_PUSH;
+  if (transport == GFFM_MG_P2P_RAW) {
+    const int nc = mg->ncopy;
+    const bool have_b = r == root || distributed;  // this rank reads its own range (root: every range) straight from its matrix
+    auto stage_at = [&](int q, int s, int64_t c) { return mg->peer_base[q] + mg->stage_off(b) + ((size_t)s * rowsPB + c) * ld_c * 4; };
+    bool used_push[gffm_mg::NCOPY] = {};
+    // ---- root: every owner's uint32 range into that owner's staging buffer (copy engines, peer memory) -----------------------
+    if (r == root) {
+      for (int j = 0; j < nc; ++j) GFFM_CUDA(cudaStreamWaitEvent(mg->s_push[j], bready, 0));
+      for (int i = 1; i < nr; ++i) {
+        const int q = (root + i) % nr;
+        const int64_t c0 = out->off[q], cnt = out->off[q + 1] - c0;
+        const int64_t chunk = round_up(ceil_div(std::max<int64_t>(cnt, 1), nc), 8);
+        for (int j = 0; j < nc; ++j) {
+          const int64_t j0 = std::min<int64_t>(cnt, (int64_t)j * chunk), j1 = std::min<int64_t>(cnt, (int64_t)(j + 1) * chunk);
+          if (j > 0 && j1 <= j0) continue;
+          used_push[j] = true;
+          GFFM_TRY(mg_wait(mg, mg->s_push[j], F_SPLIT_DONE, 1u << q, e - MG_NBUF));  // q is done with what this staging buffer held
+          cudaEvent_t tp = gffm_trace_begin(ctx, mg->s_push[j]);
+          for (int s = 0; s < R.nsrc && j1 > j0; ++s)
+            GFFM_CUDA(cudaMemcpy2DAsync(stage_at(q, s, c0 + j0), (size_t)ld_c * 4, R.src[s].p + (c0 + j0) * R.src[s].ld, (size_t)R.src[s].ld * 4,
+                                        (size_t)kc * 4, (size_t)(j1 - j0), cudaMemcpyDefault, mg->s_push[j]));
+          gffm_trace_end(ctx, "push", q, 4, tp, mg->s_push[j]);
+          if (j > 0) {
+            GFFM_CUDA(cudaEventRecord(mg->copy_ev[1][j], mg->s_push[j]));
+            GFFM_CUDA(cudaStreamWaitEvent(mg->s_push[0], mg->copy_ev[1][j], 0));
+          }
+        }
+        MgTargets t;
+        t.p[0] = mg->ctl(q) + F_STAGED;
+        GFFM_TRY(mg_signal(mg, mg->s_push[0], t, 1, e));
+      }
+    }
+    // ---- distribution stream: the own range is there (pushed by the root / part of the local matrix), the plane buffer is free -------
+    if (!have_b) GFFM_TRY(mg_wait(mg, mg->s_dist, F_STAGED, 1u, e));
+    else GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, bready, 0));
+    GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->gemm_done[b], 0));  // the local GEMMs of the epoch that used plane buffer b before are done
+    // ---- owners: forward the own range to every rank that does not hold B (copy engines; posted writes over NVLink) ----------------
+    {
+      const int64_t c0 = out->off[r], cnt = out->off[r + 1] - c0;
+      for (int i = 1; i < nr && cnt > 0; ++i) {  // an empty range has no flag: every rank knows the ranges
+        const int p = (r + i) % nr;
+        if (p == root) continue;  // the root splits from its own matrix
+        cudaStream_t cs = mg->s_push[i % nc];
+        used_push[i % nc] = true;
+        {
+          // the copy streams wait for the own range themselves (not through the distribution stream, which is still busy with the
+          // previous product's splits): the forwards of product e+1 run while product e is being split
+          if (!have_b) GFFM_TRY(mg_wait(mg, cs, F_STAGED, 1u, e));
+          else GFFM_CUDA(cudaStreamWaitEvent(cs, bready, 0));
+          GFFM_TRY(mg_wait(mg, cs, F_SPLIT_DONE, 1u << p, e - MG_NBUF));  // p is done with what its staging buffer b held
+          cudaEvent_t tp = gffm_trace_begin(ctx, cs);
+          for (int s = 0; s < R.nsrc; ++s) {
+            if (have_b) {
+              const uint32_t* src = R.src[s].p + (distributed ? 0 : c0) * R.src[s].ld;
+              GFFM_CUDA(cudaMemcpy2DAsync(stage_at(p, s, c0), (size_t)ld_c * 4, src, (size_t)R.src[s].ld * 4, (size_t)kc * 4, (size_t)cnt, cudaMemcpyDefault, cs));
+            } else {
+              GFFM_CUDA(cudaMemcpyAsync(stage_at(p, s, c0), mg->stage(b) + ((size_t)s * rowsPB + c0) * ld_c * 4, (size_t)cnt * ld_c * 4, cudaMemcpyDefault, cs));
+            }
+          }
+          gffm_trace_end(ctx, "fwd", p, 4, tp, cs);
+        }
+        MgTargets t;
+        t.p[0] = mg->ctl(p) + F_READY + r;
+        GFFM_TRY(mg_signal(mg, cs, t, 1, e));
+      }
+    }
+    // the copies that READ this rank's matrix / staging buffer: joined on copy stream 0 (ev_push: the caller may modify B; the
+    // distribution stream waits for it before it declares the staging buffer consumed)
+    for (int j = 1; j < gffm_mg::NCOPY; ++j) {
+      if (!used_push[j]) continue;
+      GFFM_CUDA(cudaEventRecord(mg->copy_ev[1][j], mg->s_push[j]));
+      GFFM_CUDA(cudaStreamWaitEvent(mg->s_push[0], mg->copy_ev[1][j], 0));
+    }
+    GFFM_CUDA(cudaEventRecord(mg->ev_push, mg->s_push[0]));
+    // ---- every rank: split every range as it arrives, the own one first ------------------------------------------------------------
+    for (int i = 0; i < nr; ++i) {
+      const int q = (r + i) % nr;
+      const bool local_src = q == r ? have_b : r == root;  // read from the matrix itself instead of the staging buffer
+      if (!local_src && q != r && out->off[q + 1] > out->off[q]) GFFM_TRY(mg_wait(mg, mg->s_dist, F_READY, 1u << q, e));
+      GFFM_TRY(split_own(q, !local_src, ld_c));
+      GFFM_CUDA(cudaEventRecord(mg->ready_ev[b][q], mg->s_dist));
+      out->order[i] = q;
+      out->ready[q] = mg->ready_ev[b][q];
+    }
+    // "staging buffer b of this rank is consumed": after the splits AND after the forwards that read it
+    GFFM_CUDA(cudaStreamWaitEvent(mg->s_dist, mg->ev_push, 0));
+    {
+      MgTargets t;
+      int k = 0;
+      for (int q = 0; q < nr; ++q)
+        if (q != r) t.p[k++] = mg->ctl(q) + F_SPLIT_DONE + r;
+      GFFM_TRY(mg_signal(mg, mg->s_dist, t, k, e));
+    }
+    GFFM_CUDA(cudaEventRecord(mg->split_ev[b], mg->s_dist));
+    return GFFM_OK;
+  }
+
   if (transport == GFFM_MG_P2P_PLANES || transport == GFFM_MG_P2P_PUSH) {
     // ---- root: push every other rank's uint32 column range into its staging buffer (copy engines, peer memory) -------------
     const int nc = mg->ncopy;
@@ -793,7 +899,14 @@ int32_t mg_round_done(gffm_mg* mg, const MgRound& R, const MgRoundOut& out) {
       if (q != mg->rank) t.p[k++] = mg->ctl(q) + F_FREE + mg->rank;
     GFFM_TRY(mg_signal(mg, mg->s_pull[1], t, k, mg->epoch));
   }
-  if (mg->transport == GFFM_MG_P2P_PLANES || mg->transport == GFFM_MG_P2P_PUSH) {
+  if (mg->transport == GFFM_MG_P2P_RAW) {
+    // copies that read this rank's matrix (root: scatter + forward of its own range; distributed B: forward) and EVERY split that read
+    // it or the staging buffer (the last one on the distribution stream) precede whatever the caller enqueues next
+    if (mg->rank == R.root || R.root < 0) {
+      GFFM_CUDA(cudaStreamWaitEvent(ctx->stream, mg->ev_push, 0));
+      GFFM_CUDA(cudaStreamWaitEvent(ctx->stream, mg->split_ev[out.b], 0));
+    }
+  } else if (mg->transport == GFFM_MG_P2P_PLANES || mg->transport == GFFM_MG_P2P_PUSH) {
     if (mg->rank == R.root) GFFM_CUDA(cudaStreamWaitEvent(ctx->stream, mg->ev_push, 0));
   } else {
     GFFM_CUDA(cudaStreamWaitEvent(ctx->stream, mg->ev_comm, 0));
@@ -961,7 +1074,7 @@ extern "C" int32_t gffm_mg_info(gffm_mg* mg, int32_t* rank, int32_t* nranks, int
 extern "C" int32_t gffm_mg_set_transport(gffm_mg* mg, int32_t transport) {
   if (!mg) GFFM_FAIL(GFFM_ERR_INVALID, "null");
   GFFM_ENTER_CTX(mg->ctx);
-  if (transport < GFFM_MG_AUTO || transport > GFFM_MG_P2P_PUSH) GFFM_FAIL(GFFM_ERR_INVALID, "unknown transport %d", transport);
+  if (transport < GFFM_MG_AUTO || transport > GFFM_MG_P2P_RAW) GFFM_FAIL(GFFM_ERR_INVALID, "unknown transport %d", transport);
   if (transport == mg->requested) return GFFM_OK;  // every rank passes the same value, so every rank returns here or nobody does
   // collective: drain everything, then let the next product rebuild the arena (and the peer mappings) under the new setting
   GFFM_TRY(mg_sync_streams(mg));

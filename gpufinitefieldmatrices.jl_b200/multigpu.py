@@ -214,7 +214,7 @@ class BroadcastMatmul:
 
 
 # ---- the multi-GPU layer of the C ABI (gffm_mg_*, csrc/mg.cu) ---------------------------------------------------------------------
-TRANSPORT_NAMES = {capi.MG_AUTO: "auto", capi.MG_NCCL_BCAST: "nccl_bcast", capi.MG_NCCL_PLANES: "nccl_planes", capi.MG_P2P_PLANES: "p2p_planes", capi.MG_P2P_PUSH: "p2p_push"}
+TRANSPORT_NAMES = {capi.MG_AUTO: "auto", capi.MG_NCCL_BCAST: "nccl_bcast", capi.MG_NCCL_PLANES: "nccl_planes", capi.MG_P2P_PLANES: "p2p_planes", capi.MG_P2P_PUSH: "p2p_push", capi.MG_P2P_RAW: "p2p_raw"}
 
 
 def owner_ranges(n: int, nranks: int) -> List[int]:

@@ -192,7 +192,8 @@ enum {
   GFFM_MG_NCCL_BCAST = 1,   /* ncclBroadcast of B's uint32 column ranges, every rank splits all of B */
   GFFM_MG_NCCL_PLANES = 2,  /* grouped ncclSend/ncclRecv scatter of the ranges, owner split, grouped in-place ncclAllGather of the planes */
   GFFM_MG_P2P_PLANES = 3,   /* copy-engine push of the ranges / pull of the planes through peer memory, epoch flags, no SM used */
-  GFFM_MG_P2P_PUSH = 4      /* fused split + push: the owner's split kernel stores its planes into every rank's buffer (NVLink stores) */
+  GFFM_MG_P2P_PUSH = 4,     /* fused split + push: the owner's split kernel stores its planes into every rank's buffer (NVLink stores) */
+  GFFM_MG_P2P_RAW = 5       /* copy-engine scatter + forward of the uint32 ranges (4 bytes per element), every rank splits every range locally */
 };
 /* root argument of gffm_mg_gemm for a B that is ALREADY distributed: every rank passes its own column range
  * [off[rank], off[rank+1]) (gffm_mg_owner_ranges) as a k x width matrix -- e.g. uploaded from the host over that GPU's own PCIe link */

@@ -24,7 +24,7 @@ def g():
     return gffm_b200
 
 
-@pytest.mark.parametrize("transport", ["MG_NCCL_BCAST", "MG_NCCL_PLANES", "MG_P2P_PLANES", "MG_P2P_PUSH", "MG_AUTO"])
+@pytest.mark.parametrize("transport", ["MG_NCCL_BCAST", "MG_NCCL_PLANES", "MG_P2P_PLANES", "MG_P2P_PUSH", "MG_P2P_RAW", "MG_AUTO"])
 def test_single_rank_products_through_the_mg_layer(g, transport):
     """One rank: the whole data flow (owner split into the plane arena, external-plane GEMM per column range, CRT) with a
     1-rank NCCL communicator; results bit-exact vs the oracle for RNS / two-limb / one-limb moduli, Karatsuba and mat-vec."""

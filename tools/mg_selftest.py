@@ -54,7 +54,7 @@ def main():
         return good
 
     transports = [(mg.capi.MG_NCCL_BCAST, "nccl_bcast"), (mg.capi.MG_NCCL_PLANES, "nccl_planes"), (mg.capi.MG_P2P_PLANES, "p2p_planes"),
-                  (mg.capi.MG_P2P_PUSH, "p2p_push")]
+                  (mg.capi.MG_P2P_PUSH, "p2p_push"), (mg.capi.MG_P2P_RAW, "p2p_raw")]
     if os.environ.get("MG_SELFTEST_TRANSPORTS"):
         want = os.environ["MG_SELFTEST_TRANSPORTS"].split(",")
         transports = [t for t in transports if t[1] in want]
