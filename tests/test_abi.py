@@ -96,6 +96,25 @@ def test_plain_c_client_runs_on_the_gpu(tmp_path):
     assert "C = [" in run.stdout and "no CPU fallback" not in run.stdout
 
 
+def test_build_reuses_objects_by_content_hash_not_by_file_time(tmp_path):
+    """build.py decides by the SHA-256 of source + headers + flags + compiler version (build/manifest.json): an untouched tree reuses every
+    object whatever the file times say, a changed input hash recompiles exactly that object (checked on the decision, without running nvcc)."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("gffm_build_t", os.path.join(ROOT, "gpufinitefieldmatrices.jl_b200", "build.py"))
+    bm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bm)
+    bm.build()  # brings the tree up to date if it is not (the driver's build() has normally done that already)
+    os.utime(os.path.join(bm.CSRC, "gemv.cu"))  # newer file time, same content
+    bm.build()
+    rep = bm.last_build_report()
+    assert rep["compiled"] == [] and sorted(rep["reused"]) == sorted(bm.SOURCES) and rep["linked"] is False
+    man = json.load(open(bm.MANIFEST))
+    assert set(man["objects"]) == set(bm.SOURCES) and all(len(h) == 64 for h in man["objects"].values())
+    info = json.load(open(os.path.join(bm.LIBDIR, "build_info.json")))
+    assert info["object_inputs_sha256"] == man["objects"] and "compute_100a" in " ".join(info["flags"])
+
+
 def test_mg_owner_ranges_is_a_pure_function():
     """Column ranges of B owned by the ranks (gffm_mg_owner_ranges): equal widths, multiples of 256, covering [0, n) -- no GPU needed."""
     import gffm_b200 as g
