@@ -635,9 +635,10 @@ int32_t mg_distribute(gffm_mg* mg, MgRound& R, MgRoundOut* out) {
       GFFM_CUDA(cudaStreamWaitEvent(mg->s_push[0], mg->copy_ev[1][j], 0));
     }
     GFFM_CUDA(cudaEventRecord(mg->ev_push, mg->s_push[0]));
-    // ---- every rank: split every range as it arrives, the own one first ------------------------------------------------------------
+    // ---- every rank: split every range as it arrives, the own one first, then r-1, r-2, ...: owner q forwards to q+1, q+2, ... in
+    // that order, so in "slot" i every rank receives the range of a different owner (r-i) and needs exactly that one next (a ring) ----
     for (int i = 0; i < nr; ++i) {
-      const int q = (r + i) % nr;
+      const int q = (r + nr - i) % nr;
       const bool local_src = q == r ? have_b : r == root;  // read from the matrix itself instead of the staging buffer
       if (!local_src && q != r && out->off[q + 1] > out->off[q]) GFFM_TRY(mg_wait(mg, mg->s_dist, F_READY, 1u << q, e));
       GFFM_TRY(split_own(q, !local_src, ld_c));

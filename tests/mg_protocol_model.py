@@ -233,7 +233,7 @@ class Rank:
                     w.wait_event(r, "push0", f"copy_ev1_{j}")
             w.record(r, "push0", "ev_push")
             for i in range(nr):
-                qq = (r + i) % nr
+                qq = (r - i) % nr  # arrival order of the forwards (owner q sends to q+1, q+2, ...)
                 local = have_b if qq == r else r == root
                 if not local and qq != r and cnt[qq] > 0:
                     w.wait_flag(r, "dist", "READY", qq, e)
@@ -293,7 +293,7 @@ class Rank:
 
         # ---- gffm_bplan_gemm: per range, in the order own-first: wait for the planes, GEMM on the context stream ----
         for i in range(nr):
-            qq = (r + i) % nr
+            qq = (r - i) % nr if tr == "raw" else (r + i) % nr  # out->order
             if cnt[qq] <= 0:
                 continue
             w.wait_event(r, "ctx", f"ready{b}_{qq}")
