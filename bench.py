@@ -360,7 +360,16 @@ def main():
             os.environ["NCCL_DEBUG"] = os.environ["GFFM_NCCL_DEBUG"]
         if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log")
+            # one file set per run (world size + rendezvous port in the name): runs at several N on one box must not read each other's logs
+            tag = f"w{world}.p{os.environ.get('MASTER_PORT', '0')}"
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", f"nccl_debug.{tag}.%h.%p.log")
+            if rank == 0:  # leftovers of an earlier run with the same tag; NCCL is initialised only after rank 0 has handed out its id
+                import glob
+                for f_ in glob.glob(os.environ["NCCL_DEBUG_FILE"].replace("%h", "*").replace("%p", "*")):
+                    try:
+                        os.remove(f_)
+                    except OSError:
+                        pass
         # torch.distributed is plumbing only (id exchange, barriers, max over ranks): the gloo (CPU) backend.  The data path's NCCL
         # communicator lives inside the library (gffm_mg_create).  Not using torch's NCCL backend / stream pool also keeps the process below
         # CUDA_DEVICE_MAX_CONNECTIONS streams, so the multi-GPU layer's streams never share a hardware queue (profiles/r02_notes.md).
