@@ -146,3 +146,81 @@ def test_panel_quotient_estimates(P):
         for x in adversarial(min(limit, 2 ** 32)):
             r = x - ((x * mu32) >> 32) * P
             assert 0 <= r < 2 * P
+
+
+# ---------------------------------------------------------------- round 2: GEMV accumulation budget, 64-bit Barrett, wide products ----
+def _mod_u64(v, P):
+    """common.cuh mod_u64: q = mulhi64(v, floor((2^64-1)/P)), r = v - q*P (mod 2^64), two conditional subtractions"""
+    mu = (2 ** 64 - 1) // P
+    q = (v * mu) >> 64
+    r = (v - q * P) % 2 ** 64
+    if r >= P:
+        r -= P
+    if r >= P:
+        r -= P
+    return r
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 11, 65521, 33554393, 2 ** 32 - 5, 2 ** 32 - 1, 8191 * 8191, 2 ** 52 - 1, 2 ** 52, (1 << 26) ** 2])
+def test_barrett_u64_two_corrections_suffice(P):
+    """mod_u64 is used with ARBITRARY 64-bit inputs (raw uint64 accumulators in gemv.cu, Karatsuba sums): the quotient estimate is at
+    most 2 short for every v < 2^64 and every P the library passes (P <= 2^52), so two conditional subtractions finish the reduction."""
+    rng = np.random.default_rng(P % 1000)
+    vs = [0, 1, P - 1, P, P + 1, 2 * P - 1, 2 * P, 2 ** 64 - 1, 2 ** 64 - P, 2 ** 63, 2 ** 63 - 1, (2 ** 64 - 1) // P * P, (2 ** 64 - 1) // P * P - 1]
+    vs += [int(x) for x in rng.integers(0, 2 ** 63, size=4000, dtype=np.int64)] + [int(x) + 2 ** 63 for x in rng.integers(0, 2 ** 63, size=4000, dtype=np.int64)]
+    for v in vs:
+        if 0 <= v < 2 ** 64:
+            assert _mod_u64(v, P) == v % P, (v, P)
+
+
+def _terms_budget(bound2):
+    """gemv.cu terms_budget: floor(9.0e18 / bound2), capped at 2^20"""
+    if bound2 < 1:
+        return 1 << 20
+    return min(1 << 20, int(9.0e18 / bound2))
+
+
+@pytest.mark.parametrize("R,P", [(11, 11), (65521, 65521), (33554393, 33554393), (2 ** 32 - 5, 65521), (2 ** 32, 2 ** 32 - 5), (2 ** 31, 3), (4294967291, 4294967291),
+                                 (2 ** 29 + 1, 2 ** 29 + 1), (1518500250, 7), (3037000500, 7)])
+def test_gemv_accumulation_budget_never_wraps(R, P):
+    """gemv_kernel<0>: raw products (< (R-1)^2) are added to a uint64 accumulator, reduced whenever the NEXT batch of GV_UNROLL terms
+    could exceed the budget T, the reduced value counting as one term.  Worst case (every product maximal): the accumulator must stay
+    below 2^64 at every step; when the budget cannot hold two batches the kernel switches to MODE 1 (every product reduced)."""
+    GV_UNROLL = 8
+    b2 = (R - 1) ** 2
+    budget = _terms_budget(float(max(b2, P)))
+    mode = 1 if budget < 2 * GV_UNROLL else 0
+    T = (1 << 20) if mode else budget
+    term = (P - 1) if mode else b2  # MODE 1 adds mod_u64(product) < P
+    acc, since, peak = 0, 0, 0
+    for _ in range(40000 // GV_UNROLL):
+        acc += GV_UNROLL * term
+        peak = max(peak, acc)
+        since += GV_UNROLL
+        if since + GV_UNROLL > T:
+            acc = P - 1  # worst reduced value
+            since = 1
+    assert peak < 2 ** 64, (R, P, mode, T, peak.bit_length())
+    if mode == 1:
+        assert (1 << 20) * (P - 1) < 2 ** 64
+    # the cross-warp and K-slice sums add at most 8 + 64 reduced values
+    assert 72 * (P - 1) < 2 ** 64
+
+
+@pytest.mark.parametrize("P", [2 ** 32 + 15, 2 ** 45 + 59, 2 ** 52 - 47, 2 ** 52, 8191 * 8191 * 8191])
+def test_wide_mulmod_through_byte_steps(P):
+    """wide.cu mulmod_u64 (2^32 < P <= 2^52): hi = (a*b) >> 64 < 2^40, acc = hi % P, then eight steps acc = ((acc << 8) | byte) % P over
+    the low word -- every intermediate stays below 2^60 and the result is (a*b) mod P."""
+    rng = np.random.default_rng(7)
+    cases = [(P - 1, P - 1), (P - 1, 1), (0, P - 1), (2 ** 32, 2 ** 32 % P), (P // 2, P // 2 + 1)]
+    cases += [(int(a) % P, int(b) % P) for a, b in rng.integers(0, 2 ** 62, size=(3000, 2), dtype=np.int64)]
+    for a, b in cases:
+        prod = a * b
+        hi, lo = prod >> 64, prod % 2 ** 64
+        assert hi < 2 ** 40
+        acc = hi % P
+        for k in range(0, 64, 8):
+            sh = (acc << 8) | ((lo >> (56 - k)) & 0xFF)
+            assert sh < 2 ** 60
+            acc = sh % P
+        assert acc == prod % P
