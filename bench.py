@@ -849,9 +849,12 @@ def main():
         if world == 1:
             sharding = "single GPU"
         elif mgpu is not None:
+            flow = {"p2p_raw": "the owners' copy engines forward their uint32 column ranges to every rank over NVLink peer memory and every rank splits every range into 8-bit planes itself",
+                    "nccl_bcast": "ncclBroadcast of the uint32 column ranges, every rank splits every range into 8-bit planes itself"}.get(
+                        transport_used, "each owner splits its column range of B into 8-bit planes and the planes are exchanged over NVLink")
             sharding = (f"{world} row blocks of A and C over {world} GPUs; B lives on rank 0 and is distributed EVERY step by the library's multi-GPU layer "
-                        f"(gffm_mg_{'kmat_mul' if kara else 'gemm'}, transport {transport_used}): each rank splits 1/{world} of B's columns into 8-bit planes, the planes "
-                        f"are exchanged over NVLink while the GEMMs of the ranges that have arrived run; the distribution of step t+1 overlaps the GEMMs of step t")
+                        f"(gffm_mg_{'kmat_mul' if kara else 'gemm'}, transport {transport_used}): {flow}, while the GEMMs of the ranges that have arrived run; "
+                        f"the distribution of step t+1 overlaps the GEMMs of step t")
         else:
             sharding = f"{world} row blocks of A over {world} GPUs, {transport_used}"
         out = {
