@@ -116,10 +116,28 @@ def exact_matmul_mod(A: np.ndarray, B: np.ndarray, N: int) -> np.ndarray:
     amax = int(np.abs(A).max()) if A.size else 0
     bmax = int(np.abs(B).max()) if B.size else 0
     K = A.shape[1]
+    if amax * bmax >= 2 ** 62 and amax < 2 ** 32 and bmax < 2 ** 32 and N <= 2 ** 63 and A.size and B.size and int(A.min()) >= 0 and int(B.min()) >= 0:
+        # 32-bit residues: every single product fits uint64, so one exact column-times-row step per k (reduced at once); the same
+        # numbers as the python-integer product below, without its per-element interpreter cost
+        Au, Bu = A.astype(np.uint64), B.astype(np.uint64)
+        C = np.zeros((A.shape[0], B.shape[1]), dtype=np.uint64)
+        for k in range(K):
+            C = (C + (Au[:, k:k + 1] * Bu[k:k + 1, :]) % N) % N  # C < N <= 2^63 and the reduced product < N: the sum fits
+        return C.astype(np.int64)
     if amax * bmax >= 2 ** 62:
         Ao = A.astype(object)
         Bo = B.astype(object)
         return np.array((Ao @ Bo) % N, dtype=np.int64) if N < 2 ** 63 else (Ao @ Bo) % N
+    if amax * bmax < 2 ** 52 and N < 2 ** 62:
+        # float64 BLAS on K-chunks whose partial sums stay below 2^53: every product and every partial sum is an exactly representable
+        # integer, so the result is the exact integer product whatever the summation order (same numbers as the int64 path, ~50x faster)
+        chunk = max(1, min(max(K, 1), (2 ** 53 - 1) // max(1, amax * bmax)))
+        Af, Bf = A.astype(np.float64), B.astype(np.float64)
+        C = np.zeros((A.shape[0], B.shape[1]), dtype=np.int64)
+        for k0 in range(0, K, chunk):
+            k1 = min(K, k0 + chunk)
+            C = (C + np.mod((Af[:, k0:k1] @ Bf[k0:k1, :]).astype(np.int64), N)) % N
+        return np.mod(C, N)
     chunk = max(1, min(max(K, 1), (2 ** 62) // max(1, amax * bmax)))
     C = np.zeros((A.shape[0], B.shape[1]), dtype=np.int64)
     for k0 in range(0, K, chunk):
@@ -230,17 +248,25 @@ def perm_array_to_matrix(perm, n=None, perm_stack=False):
 # PLUQ: rref_lu_pluq/pluq_kernels.jl:46-157 (host loop), :179-202 (find_pivot),
 #       :307-320 (swap+scale), :385-393 (move col), :411-440 (rank-1 update)
 # --------------------------------------------------------------------------------------
-def pluq_reference(A: np.ndarray, N: int):
+def _elim_dtype(N: int, python_ints: bool):
+    """integer type in which x + m*y (x, m, y < N) is exact: int64 below 2^31, uint64 up to 2^32 ((N-1)*N < 2^64), python integers above"""
+    if python_ints or N > 2 ** 32:
+        return object
+    return np.int64 if N < 2 ** 31 else np.uint64
+
+
+def pluq_reference(A: np.ndarray, N: int, python_ints: bool = False):
     """Literal restatement of pluq_gpu_kernel, INCLUDING its rank-deficient quirk
     (an all-zero pivot column is swapped with the fixed last column `cols` and the swapped-in
     column is then skipped: pluq_kernels.jl:88,103,193).  Returns (U, L, Perm_rows, Perm_cols)
     with 1-based transposition tuples.  Pivot = maximum residue at/below `row`, first index on
     ties (findmax, :189).  L is written at column `col` (:343,389), as in the reference.
     """
-    dA = np.mod(np.asarray(A, dtype=np.int64), N).astype(object)
+    dt = _elim_dtype(N, python_ints)
+    dA = np.mod(np.asarray(A, dtype=np.int64), N).astype(dt)
     rows, cols = dA.shape
     ldim = max(rows, cols)
-    dL = np.zeros((rows, ldim), dtype=object)  # reference allocates prow x prow (padded); we keep enough cols
+    dL = np.zeros((rows, ldim), dtype=dt)  # reference allocates prow x prow (padded); we keep enough cols
     perm_rows, perm_cols = [], []
     row = col = 0
     last = cols - 1  # Perm_col_idx = cols, never changes (:88)
@@ -286,7 +312,7 @@ def pluq_reference(A: np.ndarray, N: int):
     return U, L, perm_rows, perm_cols
 
 
-def echelon(A: np.ndarray, N: int):
+def echelon(A: np.ndarray, N: int, python_ints: bool = False):
     """Well-defined rank-revealing elimination used by the new `pluq(correct)`, `lu`, `rref`:
     same pivot rule (max residue, first index; pluq_kernels.jl:189), same scaling conventions
     (unit pivots in U, pivot values on diag(L), un-normalised sub-column in L; :314,:343,:389),
@@ -295,9 +321,14 @@ def echelon(A: np.ndarray, N: int):
     (rows >= rank are zero), L rows x rows lower-triangular (columns >= rank zero),
     P*A = L*E with P the product of the transpositions.
     """
-    E = np.mod(np.asarray(A, dtype=np.int64), N).astype(object)
+    key = (int(N), np.asarray(A).shape, hash(np.ascontiguousarray(np.asarray(A, dtype=np.int64)).tobytes()))
+    if not python_ints and _ECHELON_CACHE.get("key") == key:  # pluq / lu / rref / inverse of the same input: one elimination (the callers get copies)
+        E_, L_, pr_, pc_ = _ECHELON_CACHE["val"]
+        return E_.copy(), L_.copy(), list(pr_), list(pc_)
+    dt = _elim_dtype(N, python_ints)
+    E = np.mod(np.asarray(A, dtype=np.int64), N).astype(dt)
     rows, cols = E.shape
-    L = np.zeros((rows, rows), dtype=object)
+    L = np.zeros((rows, rows), dtype=dt)
     perm_rows, pivcols = [], []
     row = 0
     for col in range(cols):
@@ -324,7 +355,12 @@ def echelon(A: np.ndarray, N: int):
             E[row + 1:, col + 1:] = (E[row + 1:, col + 1:] + np.outer(mult, E[row, col + 1:])) % N
         pivcols.append(col)
         row += 1
-    return np.array(E, dtype=np.int64), np.array(L, dtype=np.int64), perm_rows, pivcols
+    out = (np.array(E, dtype=np.int64), np.array(L, dtype=np.int64), perm_rows, pivcols)
+    _ECHELON_CACHE["key"], _ECHELON_CACHE["val"] = key, (out[0].copy(), out[1].copy(), list(perm_rows), list(pivcols))
+    return out
+
+
+_ECHELON_CACHE = {}
 
 
 def pivcols_to_perm(pivcols, cols):
@@ -367,12 +403,12 @@ def lu(A: np.ndarray, N: int):
 def rref(A: np.ndarray, N: int):
     """Unique reduced row echelon form (intended rref_gpu_type, rref_gpu_type.jl:8-51)."""
     E, _, _, pivcols = echelon(A, N)
-    R = E.astype(object)
+    R = E.astype(_elim_dtype(N, False))
     for t in range(len(pivcols) - 1, -1, -1):
         c = pivcols[t]
         if t > 0:
-            f = R[:t, c].copy()
-            R[:t, :] = (R[:t, :] - np.outer(f, R[t, :])) % N
+            f = (N - R[:t, c]) % N  # x - f*y == x + (N - f)*y (mod N): no negative intermediate, exact in the unsigned type too
+            R[:t, :] = (R[:t, :] + np.outer(f, R[t, :])) % N
     return np.array(R, dtype=np.int64), pivcols
 
 
@@ -412,9 +448,27 @@ def lower_triangular_inverse(A: np.ndarray, N: int) -> np.ndarray:
     return upper_triangular_inverse(A[:rows, :rows].T, N)[:rows, :rows].T.copy()
 
 
-def _fast_tri_inverse_upper(T: np.ndarray, N: int) -> np.ndarray:
-    """Vectorised unit/non-unit upper-triangular inverse (same result as above, O(n) numpy steps)."""
+def _fast_tri_inverse_upper(T: np.ndarray, N: int, python_ints: bool = False) -> np.ndarray:
+    """Vectorised unit/non-unit upper-triangular inverse (same result as above, O(n) numpy steps).  N < 2^31: int64 rows with the
+    row-times-matrix product through exact_matmul_mod (exact K-chunks); larger N: python integers."""
     n = T.shape[0]
+    if N < 2 ** 31 and not python_ints:
+        T = np.mod(np.asarray(T, dtype=np.int64), N)
+        X = np.zeros((n, n), dtype=np.int64)
+        for i in range(n - 1, -1, -1):
+            rhs = (N - exact_matmul_mod(T[i, i + 1:].reshape(1, -1), X[i + 1:, :], N).reshape(-1)) % N if i + 1 < n else np.zeros(n, dtype=np.int64)
+            rhs[i] = (rhs[i] + 1) % N
+            X[i, :] = (rhs * mod_inv(int(T[i, i]), N)) % N  # < N * N < 2^62
+        return X
+    if N <= 2 ** 32 and not python_ints:  # 2^31 <= N <= 2^32: uint64, products reduced one by one, sums of n residues < 2^63
+        T = np.mod(np.asarray(T, dtype=np.int64), N).astype(np.uint64)
+        X = np.zeros((n, n), dtype=np.uint64)
+        for i in range(n - 1, -1, -1):
+            dot = ((T[i, i + 1:, None] * X[i + 1:, :]) % N).sum(axis=0, dtype=np.uint64) % N if i + 1 < n else np.zeros(n, dtype=np.uint64)
+            rhs = (N - dot) % N
+            rhs[i] = (rhs[i] + 1) % N
+            X[i, :] = (rhs * mod_inv(int(T[i, i]), N)) % N
+        return X.astype(np.int64)
     T = np.mod(np.asarray(T, dtype=np.int64), N).astype(object)
     X = np.zeros((n, n), dtype=object)
     dinv = [mod_inv(int(T[i, i]), N) for i in range(n)]

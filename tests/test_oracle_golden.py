@@ -256,3 +256,42 @@ def test_sampled_row_helpers_match_full_oracle():
     M = O.synth_matrix(9, 8, 8, 97)
     assert np.array_equal(M[S.perm_to_map(pairs, 8)], O.apply_row_perm(pairs, M))
     assert np.array_equal(M[:, S.perm_to_map(pairs, 8)], O.apply_col_perm(pairs, M))
+
+
+def test_oracle_fast_paths_equal_the_python_integer_paths():
+    """The oracle's int64 (N < 2^31) / uint64 (N <= 2^32) eliminations, triangular inverses and RREF, its float64-BLAS exact product
+    (partial sums < 2^53) and its uint64 per-k product are the same numbers as the python-integer restatements they replace -- checked on
+    random and on adversarial (all N-1) inputs up to the edge of their ranges."""
+    rng = np.random.default_rng(11)
+    for (m, n, N) in [(40, 40, 7), (60, 45, 65521), (45, 60, 33554393), (50, 50, 2 ** 31 - 1), (30, 30, 2), (50, 50, 2147483659), (45, 45, 4294967291)]:
+        for adversarial in (False, True):
+            A = rng.integers(0, N, size=(m, n), dtype=np.int64)
+            if adversarial:
+                A[:] = N - 1
+                A[::3, ::2] = N - 2
+                A[5, :] = 0
+            fast = O.echelon(A, N)
+            slow = O.echelon(A, N, python_ints=True)
+            assert np.array_equal(fast[0], slow[0]) and np.array_equal(fast[1], slow[1]) and fast[2] == slow[2] and fast[3] == slow[3]
+            again = O.echelon(A, N)  # served from the one-entry cache: equal, and not aliased with the first answer
+            assert np.array_equal(again[0], fast[0]) and again[0] is not fast[0]
+            fr, sr = O.pluq_reference(A, N), O.pluq_reference(A, N, python_ints=True)
+            assert np.array_equal(fr[0], sr[0]) and np.array_equal(fr[1], sr[1]) and fr[2:] == sr[2:]
+            if m == n:
+                T = np.triu(rng.integers(0, N, size=(n, n), dtype=np.int64))
+                T[np.arange(n), np.arange(n)] = rng.integers(1, N, size=n) if N > 2 else 1
+                if adversarial:
+                    T[np.triu_indices(n, 1)] = N - 1
+                assert np.array_equal(O._fast_tri_inverse_upper(T, N), O._fast_tri_inverse_upper(T, N, python_ints=True))
+            Eo, _, _, piv = slow  # RREF from python integers
+            Ro = Eo.astype(object)
+            for t in range(len(piv) - 1, 0, -1):
+                fcol = Ro[:t, piv[t]].copy()
+                Ro[:t, :] = (Ro[:t, :] - np.outer(fcol, Ro[t, :])) % N
+            assert np.array_equal(O.rref(A, N)[0], np.array(Ro, dtype=np.int64))
+    for (m, k, n, hi, N) in [(30, 700, 20, 1331, 1331), (20, 300, 25, 2 ** 26 - 1, 2 ** 26 - 5), (10, 50, 10, 2 ** 31, 4294967291), (12, 40, 9, 2 ** 32 - 1, 4294967291),
+                              (8, 30, 8, 2 ** 32 - 1, 2 ** 52 - 47)]:
+        A = rng.integers(0, hi + 1, size=(m, k), dtype=np.int64); B = rng.integers(0, hi + 1, size=(k, n), dtype=np.int64)
+        A[0, :] = hi; B[:, 0] = hi
+        want = np.array((A.astype(object) @ B.astype(object)) % N, dtype=np.int64)
+        assert np.array_equal(O.exact_matmul_mod(A, B, N), want)
