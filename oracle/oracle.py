@@ -128,7 +128,7 @@ def exact_matmul_mod(A: np.ndarray, B: np.ndarray, N: int) -> np.ndarray:
         Ao = A.astype(object)
         Bo = B.astype(object)
         return np.array((Ao @ Bo) % N, dtype=np.int64) if N < 2 ** 63 else (Ao @ Bo) % N
-    if amax * bmax < 2 ** 52 and N < 2 ** 62:
+    if amax * bmax < 2 ** 47 and N < 2 ** 62:  # at least 64 terms per BLAS call; larger entries take the int64 chunks below
         # float64 BLAS on K-chunks whose partial sums stay below 2^53: every product and every partial sum is an exactly representable
         # integer, so the result is the exact integer product whatever the summation order (same numbers as the int64 path, ~50x faster)
         chunk = max(1, min(max(K, 1), (2 ** 53 - 1) // max(1, amax * bmax)))
