@@ -155,14 +155,22 @@ int64_t oracle_echelon(uint32_t* W, int64_t ld, uint32_t* L, int64_t ldl, int64_
     for (int64_t c = 0; c < m; ++c) { uint32_t t = L[c * ldl + bi]; L[c * ldl + bi] = L[c * ldl + row]; L[c * ldl + row] = t; }
     L[row * ldl + row] = best;
     for (int64_t i = row + 1; i < m; ++i) { L[row * ldl + i] = W[col * ld + i]; W[col * ld + i] = 0; }
+    /* w[i] -= l[i] * u  ==  w[i] += l[i] * (N - u)  (mod N): x = w + l * (N - u) <= (N - 1) * N < 2^64 for N <= 2^32, reduced with a
+     * precomputed reciprocal (quotient estimate at most 2 short) instead of two hardware divisions per element */
+    const uint64_t mu = N > 1 ? (uint64_t)(~(uint64_t)0 / N) : 0;
     for (int64_t c = col + 1; c < n; ++c) {
       const uint64_t u = W[c * ld + row];
       if (u == 0) continue;
+      const uint64_t nu = N - u;
       uint32_t* wc = W + c * ld;
       const uint32_t* lc = L + row * ldl;
       for (int64_t i = row + 1; i < m; ++i) {
-        const uint64_t l = lc[i];
-        if (l) wc[i] = (uint32_t)(((uint64_t)wc[i] + N - (l * u) % N) % N);
+        const uint64_t x = (uint64_t)wc[i] + (uint64_t)lc[i] * nu;
+        const uint64_t q = (uint64_t)(((unsigned __int128)x * mu) >> 64);
+        uint64_t r = x - q * N;
+        if (r >= N) r -= N;
+        if (r >= N) r -= N;
+        wc[i] = (uint32_t)r;
       }
     }
     pivcol[row] = col; swp[row] = bi;
