@@ -376,6 +376,9 @@ end
 mutable struct MultiGpu
     h::Ptr{Cvoid}; ctx::Context; rank::Int; nranks::Int
 end
+# transports of mg_set_transport! (enum in include/gffm.h) and the root value of an already distributed B
+const MG_AUTO = 0; const MG_NCCL_BCAST = 1; const MG_NCCL_PLANES = 2; const MG_P2P_PLANES = 3; const MG_P2P_PUSH = 4; const MG_P2P_RAW = 5
+const MG_DISTRIBUTED = -1
 mg_unique_id() = (id = Base.zeros(UInt8, 128); check(ccall((:gffm_mg_unique_id, libgffm), Int32, (Ptr{UInt8},), id)); id)
 function MultiGpu(id::Vector{UInt8}, nranks::Integer, rank::Integer; ctx::Context=default_context())      # rank is 0-based like NCCL's
     r = Ref{Ptr{Cvoid}}(C_NULL)
