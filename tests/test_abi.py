@@ -138,3 +138,22 @@ def test_mg_owner_ranges_is_a_pure_function():
     with pytest.raises(g.GffmError):
         g.multigpu.owner_ranges_root_free(10, 1, 0)
     assert len(g.multigpu.MultiGpu.unique_id()) == 128  # NCCL is dlopen'ed on demand, no link-time dependency
+
+
+def test_enum_values_agree_between_header_ctypes_mirror_and_julia_shim():
+    """Every enumerator of include/gffm.h that the ctypes mirror (capi.py) or the Julia shim names carries the header's value -- the
+    boundary passes plain integers, so a renumbered enum would silently select another operation / transport."""
+    import gffm_b200 as g
+    hdr = open(os.path.join(ROOT, "include", "gffm.h")).read()
+    enums = {name: int(val) for name, val in re.findall(r"\b(GFFM_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)}
+    assert enums["GFFM_MG_P2P_RAW"] == 5 and enums["GFFM_MG_DISTRIBUTED"] == -1 and len(enums) > 40
+    checked = 0
+    for name, val in enums.items():
+        short = name[len("GFFM_"):]
+        if hasattr(g.capi, short):
+            assert getattr(g.capi, short) == val, name
+            checked += 1
+    assert checked >= 25, checked
+    jl = open(os.path.join(ROOT, "gpufinitefieldmatrices.jl_b200", "julia", "GPUFiniteFieldMatricesB200.jl")).read()
+    for jname, jval in re.findall(r"const (MG_[A-Z0-9_]+) = (-?\d+)", jl):
+        assert enums["GFFM_" + jname] == int(jval), jname
